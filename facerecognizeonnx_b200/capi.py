@@ -1,0 +1,417 @@
+"""ctypes binding of include/fr_capi.h (libfr_b200.so).
+
+The shared library is the product; this module only marshals numpy arrays /
+raw device pointers across the C ABI.  It fails loudly when the library is
+missing or was not built -- there is no Python/CPU fallback for any stage.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import List, Optional, Sequence
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libfr_b200.so")
+
+FR_OK = 0
+FR_ERR_INVALID_ARG, FR_ERR_NOT_LOADED, FR_ERR_CUDA, FR_ERR_MODEL = -1, -2, -3, -4
+FR_ERR_ALIGN, FR_ERR_CAPACITY, FR_ERR_UNSUPPORTED = -5, -6, -7
+FR_MEM_HOST, FR_MEM_DEVICE = 0, 1
+FR_MODEL_DET, FR_MODEL_REC = 0, 1
+DET_SIZE, REC_SIZE, FEAT_DIM, NUM_ANCHORS = 640, 112, 512, 16800
+HEAD_N = (12800, 3200, 800)
+HEAD_C = (1, 4, 10)
+
+FACE_DTYPE = np.dtype([("x", "<i4"), ("y", "<i4"), ("w", "<i4"), ("h", "<i4"),
+                       ("score", "<f4"), ("lm", "<f4", (10,))])
+assert FACE_DTYPE.itemsize == 60
+
+# every symbol include/fr_capi.h declares (tests/test_capi_host.py checks the .so exports them)
+SYMBOLS = [
+    "fr_weights_create", "fr_weights_destroy", "fr_weights_model", "fr_weights_from_onnx",
+    "fr_weights_num_tensors", "fr_weights_tensor_info", "fr_weights_tensor_get",
+    "fr_weights_tensor_set", "fr_weights_last_error",
+    "fr_create", "fr_destroy", "fr_last_error", "fr_set_stream", "fr_synchronize", "fr_launch_count",
+    "fr_detect", "fr_detect_batch",
+    "fr_embed", "fr_embed_faces_batch", "fr_embed_simple", "fr_embed_aligned_batch",
+    "fr_compare", "fr_compare_batch", "fr_pipeline_batch",
+    "fr_gallery_create", "fr_gallery_destroy", "fr_gallery_add", "fr_gallery_fill_synthetic",
+    "fr_gallery_get_rows", "fr_gallery_size", "fr_gallery_search", "fr_topk_merge",
+    "fr_det_preprocess", "fr_scrfd_forward", "fr_scrfd_decode_nms", "fr_estimate_alignment",
+    "fr_align_faces", "fr_warp_affine", "fr_resize_linear", "fr_iresnet_forward", "fr_iresnet_tap",
+    "fr_l2_normalize", "fr_test_conv",
+]
+
+
+class FrError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"fr error {code}: {msg}")
+        self.code = code
+
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(
+                f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(nvcc, sm_100a).  There is no fallback implementation.")
+        _lib = C.CDLL(LIB_PATH)
+        _declare(_lib)
+    return _lib
+
+
+def _declare(L: C.CDLL) -> None:
+    vp, i32, i64, u64, f32, sz = C.c_void_p, C.c_int, C.c_int64, C.c_uint64, C.c_float, C.c_size_t
+    L.fr_weights_create.argtypes = [C.POINTER(vp), i32, C.c_char_p, u64]
+    L.fr_weights_destroy.argtypes = [vp]
+    L.fr_weights_destroy.restype = None
+    L.fr_weights_num_tensors.argtypes = [vp]
+    L.fr_weights_model.argtypes = [vp]
+    L.fr_weights_from_onnx.argtypes = [vp]
+    L.fr_weights_tensor_info.argtypes = [vp, i32, C.c_char_p, i32, C.POINTER(i64), C.POINTER(i32)]
+    L.fr_weights_tensor_get.argtypes = [vp, i32, vp, sz]
+    L.fr_weights_tensor_set.argtypes = [vp, i32, vp, sz]
+    L.fr_weights_last_error.restype = C.c_char_p
+    L.fr_create.argtypes = [C.POINTER(vp), i32, vp, vp]
+    L.fr_destroy.argtypes = [vp]
+    L.fr_destroy.restype = None
+    L.fr_last_error.argtypes = [vp]
+    L.fr_last_error.restype = C.c_char_p
+    L.fr_set_stream.argtypes = [vp, vp]
+    L.fr_synchronize.argtypes = [vp]
+    L.fr_launch_count.argtypes = [vp]
+    L.fr_launch_count.restype = u64
+    L.fr_detect.argtypes = [vp, vp, i32, i32, sz, f32, f32, vp, i32, C.POINTER(i32)]
+    L.fr_detect_batch.argtypes = [vp, vp, vp, vp, vp, i32, i32, f32, f32, vp, i32, vp]
+    L.fr_embed.argtypes = [vp, vp, i32, i32, sz, vp, vp]
+    L.fr_embed_faces_batch.argtypes = [vp, vp, vp, vp, vp, i32, i32, vp, vp, i32, vp, vp]
+    L.fr_embed_simple.argtypes = [vp, vp, i32, i32, sz, vp]
+    L.fr_embed_aligned_batch.argtypes = [vp, vp, i32, i32, vp]
+    L.fr_compare.argtypes = [vp, i32, vp, i32]
+    L.fr_compare.restype = f32
+    L.fr_compare_batch.argtypes = [vp, vp, vp, i32, i32, i32, vp]
+    L.fr_pipeline_batch.argtypes = [vp, vp, vp, vp, vp, i32, i32, f32, f32, i32, vp, vp, vp, vp, vp]
+    L.fr_gallery_create.argtypes = [vp, C.POINTER(vp), i64, i64]
+    L.fr_gallery_destroy.argtypes = [vp]
+    L.fr_gallery_destroy.restype = None
+    L.fr_gallery_add.argtypes = [vp, vp, i64, i32]
+    L.fr_gallery_fill_synthetic.argtypes = [vp, i64, u64]
+    L.fr_gallery_get_rows.argtypes = [vp, i64, i64, vp]
+    L.fr_gallery_size.argtypes = [vp]
+    L.fr_gallery_size.restype = i64
+    L.fr_gallery_search.argtypes = [vp, vp, i32, i32, i32, vp, vp]
+    L.fr_topk_merge.argtypes = [vp, vp, vp, i32, i32, i32, i32, vp, vp]
+    L.fr_det_preprocess.argtypes = [vp, vp, vp, vp, vp, i32, i32, vp, vp]
+    L.fr_scrfd_forward.argtypes = [vp, vp, i32, vp]
+    L.fr_scrfd_decode_nms.argtypes = [vp, vp, i32, vp, f32, f32, vp, i32, vp]
+    L.fr_estimate_alignment.argtypes = [vp, vp, i32, vp, vp]
+    L.fr_align_faces.argtypes = [vp, vp, i32, i32, sz, vp, i32, vp, vp]
+    L.fr_warp_affine.argtypes = [vp, vp, i32, i32, sz, vp, vp]
+    L.fr_resize_linear.argtypes = [vp, vp, i32, i32, sz, i32, i32, vp]
+    L.fr_iresnet_forward.argtypes = [vp, vp, i32, vp]
+    L.fr_iresnet_tap.argtypes = [vp, i32, i32, vp, sz]
+    L.fr_l2_normalize.argtypes = [vp, vp, i32, i32, i32, vp]
+    L.fr_test_conv.argtypes = [vp, vp, i32, i32, i32, i32, vp, i32, i32, i32, vp, vp, vp, vp, vp, vp]
+
+
+def _ptr(a) -> Optional[int]:
+    if a is None:
+        return None
+    if isinstance(a, int):
+        return a
+    return a.ctypes.data
+
+
+# ---------------------------------------------------------------- weights --
+class Weights:
+    """Host-only canonical weight store (fr_weights_*)."""
+
+    def __init__(self, model: int, onnx_path: Optional[str] = None, seed: int = 0):
+        L = lib()
+        h = C.c_void_p()
+        s = L.fr_weights_create(C.byref(h), model, onnx_path.encode() if onnx_path else None, seed)
+        if s != FR_OK:
+            raise FrError(s, L.fr_weights_last_error().decode())
+        self.h = h
+        self.model = model
+
+    def close(self):
+        if getattr(self, "h", None):
+            lib().fr_weights_destroy(self.h)
+            self.h = None
+
+    __del__ = close
+
+    @property
+    def from_onnx(self) -> bool:
+        return bool(lib().fr_weights_from_onnx(self.h))
+
+    def specs(self):
+        L = lib()
+        out = []
+        for i in range(L.fr_weights_num_tensors(self.h)):
+            name = C.create_string_buffer(128)
+            dims = (C.c_int64 * 4)()
+            nd = C.c_int()
+            L.fr_weights_tensor_info(self.h, i, name, 128, dims, C.byref(nd))
+            out.append((name.value.decode(), tuple(int(dims[k]) for k in range(nd.value))))
+        return out
+
+    def to_dict(self):
+        L = lib()
+        d = {}
+        for i, (name, shape) in enumerate(self.specs()):
+            a = np.empty(shape, np.float32)
+            s = L.fr_weights_tensor_get(self.h, i, a.ctypes.data, a.size)
+            if s != FR_OK:
+                raise FrError(s, "tensor_get " + name)
+            d[name] = a
+        return d
+
+    def set(self, name: str, value: np.ndarray):
+        for i, (n, shape) in enumerate(self.specs()):
+            if n == name:
+                a = np.ascontiguousarray(value, np.float32).reshape(shape)
+                s = lib().fr_weights_tensor_set(self.h, i, a.ctypes.data, a.size)
+                if s != FR_OK:
+                    raise FrError(s, "tensor_set " + name)
+                return
+        raise KeyError(name)
+
+
+# -------------------------------------------------------------------- ctx --
+class _ImageBatch:
+    """Marshals a list of HxWx3 uint8 BGR images (numpy, possibly strided rows)
+    or raw device pointers into the (ptr[], rows[], cols[], step[]) arrays."""
+
+    def __init__(self, images: Sequence, memspace: int, shapes=None):
+        n = len(images)
+        self.n = n
+        self.ptrs = (C.c_void_p * n)()
+        self.rows = (C.c_int * n)()
+        self.cols = (C.c_int * n)()
+        self.step = (C.c_size_t * n)()
+        self.keep = []
+        for i, im in enumerate(images):
+            if memspace == FR_MEM_DEVICE:
+                ptr, r, c, st = im if isinstance(im, tuple) else (im, *shapes[i])
+                self.ptrs[i], self.rows[i], self.cols[i], self.step[i] = ptr, r, c, st
+            else:
+                assert im.dtype == np.uint8 and im.ndim == 3 and im.shape[2] == 3
+                if im.strides[2] != 1 or im.strides[1] != 3:
+                    im = np.ascontiguousarray(im)
+                self.keep.append(im)
+                self.ptrs[i] = im.ctypes.data
+                self.rows[i], self.cols[i] = im.shape[0], im.shape[1]
+                self.step[i] = im.strides[0]
+
+
+class Context:
+    def __init__(self, device: int = 0, det: Optional[Weights] = None, rec: Optional[Weights] = None):
+        L = lib()
+        h = C.c_void_p()
+        s = L.fr_create(C.byref(h), device, det.h if det else None, rec.h if rec else None)
+        if s != FR_OK:
+            raise FrError(s, "fr_create failed (needs a CUDA sm_100 device; there is no CPU path)")
+        self.h = h
+        self.device = device
+
+    def close(self):
+        if getattr(self, "h", None):
+            lib().fr_destroy(self.h)
+            self.h = None
+
+    __del__ = close
+
+    def _check(self, s: int):
+        if s != FR_OK:
+            raise FrError(s, lib().fr_last_error(self.h).decode())
+
+    def set_stream(self, stream_ptr: Optional[int]):
+        self._check(lib().fr_set_stream(self.h, stream_ptr))
+
+    def synchronize(self):
+        self._check(lib().fr_synchronize(self.h))
+
+    def launch_count(self) -> int:
+        return int(lib().fr_launch_count(self.h))
+
+    # -- detection
+    def detect_batch(self, images: Sequence[np.ndarray], score_thr=0.5, nms_thr=0.4, cap=256):
+        b = _ImageBatch(images, FR_MEM_HOST)
+        out = np.zeros((b.n, cap), FACE_DTYPE)
+        n_out = np.zeros(b.n, np.int32)
+        self._check(lib().fr_detect_batch(self.h, b.ptrs, b.rows, b.cols, b.step, b.n, FR_MEM_HOST,
+                                          score_thr, nms_thr, out.ctypes.data, cap, n_out.ctypes.data))
+        return [out[i, :n_out[i]].copy() for i in range(b.n)]
+
+    def detect(self, image: np.ndarray, score_thr=0.5, nms_thr=0.4, cap=256):
+        return self.detect_batch([image], score_thr, nms_thr, cap)[0]
+
+    # -- recognition
+    def embed_faces(self, images: Sequence[np.ndarray], faces: np.ndarray, face_img: Sequence[int]):
+        b = _ImageBatch(images, FR_MEM_HOST)
+        faces = np.ascontiguousarray(faces, FACE_DTYPE)
+        fi = np.ascontiguousarray(face_img, np.int32)
+        n = faces.shape[0]
+        out = np.zeros((n, FEAT_DIM), np.float32)
+        valid = np.zeros(n, np.int32)
+        self._check(lib().fr_embed_faces_batch(self.h, b.ptrs, b.rows, b.cols, b.step, b.n, FR_MEM_HOST,
+                                               faces.ctypes.data, fi.ctypes.data, n, out.ctypes.data,
+                                               valid.ctypes.data))
+        return out, valid
+
+    def embed_simple(self, image: np.ndarray) -> np.ndarray:
+        b = _ImageBatch([image], FR_MEM_HOST)
+        out = np.zeros(FEAT_DIM, np.float32)
+        self._check(lib().fr_embed_simple(self.h, b.ptrs[0], b.rows[0], b.cols[0], b.step[0], out.ctypes.data))
+        return out
+
+    def embed_aligned(self, crops: np.ndarray) -> np.ndarray:
+        crops = np.ascontiguousarray(crops, np.uint8)
+        n = crops.shape[0]
+        assert crops.shape[1:] == (REC_SIZE, REC_SIZE, 3)
+        out = np.zeros((n, FEAT_DIM), np.float32)
+        self._check(lib().fr_embed_aligned_batch(self.h, crops.ctypes.data, n, FR_MEM_HOST, out.ctypes.data))
+        return out
+
+    def embed_aligned_dev(self, crops_ptr: int, n: int, out_ptr: int):
+        self._check(lib().fr_embed_aligned_batch(self.h, crops_ptr, n, FR_MEM_DEVICE, out_ptr))
+
+    def compare_batch(self, a: np.ndarray, b: np.ndarray) -> np.ndarray:
+        a = np.ascontiguousarray(a, np.float32)
+        b = np.ascontiguousarray(b, np.float32)
+        out = np.zeros(a.shape[0], np.float32)
+        self._check(lib().fr_compare_batch(self.h, a.ctypes.data, b.ctypes.data, a.shape[0], a.shape[1],
+                                           FR_MEM_HOST, out.ctypes.data))
+        return out
+
+    # -- fused pipeline
+    def pipeline(self, images: Sequence[np.ndarray], faces_per_img: int, pad_faces: Optional[np.ndarray] = None,
+                 score_thr=0.5, nms_thr=0.4):
+        b = _ImageBatch(images, FR_MEM_HOST)
+        K = faces_per_img
+        faces = np.zeros((b.n, K), FACE_DTYPE)
+        n_det = np.zeros(b.n, np.int32)
+        emb = np.zeros((b.n, K, FEAT_DIM), np.float32)
+        valid = np.zeros((b.n, K), np.int32)
+        pad = np.ascontiguousarray(pad_faces, FACE_DTYPE) if pad_faces is not None else None
+        self._check(lib().fr_pipeline_batch(self.h, b.ptrs, b.rows, b.cols, b.step, b.n, FR_MEM_HOST,
+                                            score_thr, nms_thr, K, _ptr(pad), faces.ctypes.data,
+                                            n_det.ctypes.data, emb.ctypes.data, valid.ctypes.data))
+        return faces, n_det, emb, valid
+
+    def pipeline_dev(self, frame_ptrs: Sequence[int], rows: int, cols: int, step: int, faces_per_img: int,
+                     pad_ptr: Optional[int], out_faces_ptr: Optional[int], out_ndet_ptr: Optional[int],
+                     out_emb_ptr: int, out_valid_ptr: Optional[int], score_thr=0.5, nms_thr=0.4):
+        n = len(frame_ptrs)
+        b = _ImageBatch([(p, rows, cols, step) for p in frame_ptrs], FR_MEM_DEVICE)
+        self._check(lib().fr_pipeline_batch(self.h, b.ptrs, b.rows, b.cols, b.step, n, FR_MEM_DEVICE,
+                                            score_thr, nms_thr, faces_per_img, pad_ptr, out_faces_ptr,
+                                            out_ndet_ptr, out_emb_ptr, out_valid_ptr))
+
+    # -- stage hooks
+    def det_preprocess(self, images: Sequence[np.ndarray]):
+        b = _ImageBatch(images, FR_MEM_HOST)
+        out = np.zeros((b.n, 3, DET_SIZE, DET_SIZE), np.float32)
+        scale = np.zeros(b.n, np.float32)
+        self._check(lib().fr_det_preprocess(self.h, b.ptrs, b.rows, b.cols, b.step, b.n, FR_MEM_HOST,
+                                            out.ctypes.data, scale.ctypes.data))
+        return out, scale
+
+    def scrfd_forward(self, chw: np.ndarray) -> List[np.ndarray]:
+        chw = np.ascontiguousarray(chw, np.float32)
+        n = chw.shape[0]
+        heads = [np.zeros((n, HEAD_N[s], HEAD_C[k]), np.float32) for k in range(3) for s in range(3)]
+        arr = (C.c_void_p * 9)(*[h.ctypes.data for h in heads])
+        self._check(lib().fr_scrfd_forward(self.h, chw.ctypes.data, n, arr))
+        return heads
+
+    def scrfd_decode_nms(self, heads: Sequence[np.ndarray], scales, score_thr=0.5, nms_thr=0.4, cap=256):
+        hs = [np.ascontiguousarray(h, np.float32) for h in heads]
+        n = hs[0].shape[0]
+        for k in range(3):
+            for s in range(3):
+                assert hs[k * 3 + s].size == n * HEAD_N[s] * HEAD_C[k]
+        arr = (C.c_void_p * 9)(*[h.ctypes.data for h in hs])
+        sc = np.ascontiguousarray(scales, np.float32)
+        out = np.zeros((n, cap), FACE_DTYPE)
+        n_out = np.zeros(n, np.int32)
+        self._check(lib().fr_scrfd_decode_nms(self.h, arr, n, sc.ctypes.data, score_thr, nms_thr,
+                                              out.ctypes.data, cap, n_out.ctypes.data))
+        return [out[i, :n_out[i]].copy() for i in range(n)]
+
+    def estimate_alignment(self, landmarks: np.ndarray):
+        lm = np.ascontiguousarray(landmarks, np.float32).reshape(-1, 10)
+        n = lm.shape[0]
+        M = np.zeros((n, 2, 3), np.float64)
+        ok = np.zeros(n, np.int32)
+        self._check(lib().fr_estimate_alignment(self.h, lm.ctypes.data, n, M.ctypes.data, ok.ctypes.data))
+        return M, ok
+
+    def align_faces(self, image: np.ndarray, faces: np.ndarray):
+        b = _ImageBatch([image], FR_MEM_HOST)
+        faces = np.ascontiguousarray(faces, FACE_DTYPE)
+        n = faces.shape[0]
+        crops = np.zeros((n, REC_SIZE, REC_SIZE, 3), np.uint8)
+        valid = np.zeros(n, np.int32)
+        self._check(lib().fr_align_faces(self.h, b.ptrs[0], b.rows[0], b.cols[0], b.step[0], faces.ctypes.data,
+                                         n, crops.ctypes.data, valid.ctypes.data))
+        return crops, valid
+
+    def warp_affine(self, image: np.ndarray, M: np.ndarray) -> np.ndarray:
+        b = _ImageBatch([image], FR_MEM_HOST)
+        M = np.ascontiguousarray(M, np.float64).reshape(6)
+        out = np.zeros((REC_SIZE, REC_SIZE, 3), np.uint8)
+        self._check(lib().fr_warp_affine(self.h, b.ptrs[0], b.rows[0], b.cols[0], b.step[0], M.ctypes.data,
+                                         out.ctypes.data))
+        return out
+
+    def resize_linear(self, image: np.ndarray, new_w: int, new_h: int) -> np.ndarray:
+        b = _ImageBatch([image], FR_MEM_HOST)
+        out = np.zeros((new_h, new_w, 3), np.uint8)
+        self._check(lib().fr_resize_linear(self.h, b.ptrs[0], b.rows[0], b.cols[0], b.step[0], new_w, new_h,
+                                           out.ctypes.data))
+        return out
+
+    def iresnet_forward(self, chw: np.ndarray) -> np.ndarray:
+        chw = np.ascontiguousarray(chw, np.float32)
+        n = chw.shape[0]
+        out = np.zeros((n, FEAT_DIM), np.float32)
+        self._check(lib().fr_iresnet_forward(self.h, chw.ctypes.data, n, out.ctypes.data))
+        return out
+
+    def iresnet_tap(self, tap: int, n: int, shape) -> np.ndarray:
+        out = np.zeros((n,) + tuple(shape), np.float32)
+        self._check(lib().fr_iresnet_tap(self.h, tap, n, out.ctypes.data, out.size))
+        return out
+
+    def l2_normalize(self, x: np.ndarray) -> np.ndarray:
+        x = np.ascontiguousarray(x, np.float32)
+        out = np.zeros_like(x)
+        self._check(lib().fr_l2_normalize(self.h, x.ctypes.data, x.shape[0], x.shape[1], FR_MEM_HOST, out.ctypes.data))
+        return out
+
+    def test_conv(self, x, w, stride=1, pre_scale=None, pre_shift=None, bias=None, prelu=None, residual=None):
+        x = np.ascontiguousarray(x, np.float32)
+        w = np.ascontiguousarray(w, np.float32)
+        n, cin, h, wd = x.shape
+        cout, _, k, _ = w.shape
+        y = np.zeros((n, cout, h // stride, wd // stride), np.float32)
+        arrs = [None if a is None else np.ascontiguousarray(a, np.float32)
+                for a in (pre_scale, pre_shift, bias, prelu, residual)]
+        self._check(lib().fr_test_conv(self.h, x.ctypes.data, n, cin, h, wd, w.ctypes.data, cout, k, stride,
+                                       *[_ptr(a) for a in arrs], y.ctypes.data))
+        return y
+
+
+def compare(a: np.ndarray, b: np.ndarray) -> float:
+    a = np.ascontiguousarray(a, np.float32).reshape(-1)
+    b = np.ascontiguousarray(b, np.float32).reshape(-1)
+    return float(lib().fr_compare(a.ctypes.data, a.size, b.ctypes.data, b.size))

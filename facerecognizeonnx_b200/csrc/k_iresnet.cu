@@ -1,0 +1,826 @@
+// K6/K7: ArcFace w600k_r50 (IResNet-50) forward -- the replacement for
+// `session_->Run` in FaceRecognizer::extractFeature (reference src/face_recognizer.cpp:270-283)
+// plus FaceRecognizer::preprocess (:135-150, fused into the stem) and ::normalize (:306-318).
+//
+// All 3x3 / 1x1 convolutions and the FC run on the tcgen05 shift-GEMM kernel (tc_gemm.cuh):
+//   * activations: NHWC bf16, padded flat layout (one shared zero halo row/column)
+//   * the pre-conv BatchNorm of every IBasicBlock is folded exactly: its scale into conv1's
+//     weights, its shift into a per-border-class bias table (the shift only reaches a pixel
+//     through the taps that are inside the image)
+//   * PReLU, bias and the residual add live in the GEMM epilogue; the stride-2 conv reads a
+//     space-to-depth copy written by conv1's epilogue; the 1x1 stride-2 shortcut conv is a
+//     tenth tap accumulating into the same TMEM tile
+//   * BN2d -> flatten -> FC -> BN1d folds into one GEMM with K = 64 cells x 512 channels
+// The 3->64 stem (0.3 % of the FLOPs, K = 27) is a SIMT kernel that also does the
+// BGR->RGB / (v-127.5)/128 preprocess on the fly.
+#include <cmath>
+#include <cstring>
+
+#include "common.h"
+#include "tc_gemm.cuh"
+
+namespace {
+
+typedef __nv_bfloat16 bf16;
+
+// ------------------------------------------------------------ driver entry point
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                  const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+}  // namespace
+
+// 2-D bf16 tensor map [rows, cols] with row pitch `pitch_elems`, box = box_rows x 64, SW128.
+bool tc_make_map_2d(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols,
+                    uint64_t pitch_elems, uint32_t box_rows) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return false;
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {pitch_elems * 2};
+  cuuint32_t box[2] = {64, box_rows};
+  cuuint32_t es[2] = {1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides,
+                  box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
+}
+
+struct ConvLaunch {
+  CUtensorMap a0, a1, b0, b1;
+  tc::Params p;
+  int bn = 64;
+  int rows_per_img = 1;  // Hp*Wp of the output geometry
+};
+
+int tc_launch(fr_ctx* ctx, ConvLaunch& L, int m_rows) {
+  L.p.m_rows = m_rows;
+  L.p.num_m_tiles = ceil_div(m_rows, tc::BM);
+  const int total = L.p.num_m_tiles * L.p.n_tiles_n;
+  if (total <= 0) return FR_OK;
+  static int num_sms = 0;
+  static bool attrs = false;
+  if (!attrs) {
+    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, ctx->device);
+    FR_CUDA_OK(ctx, cudaFuncSetAttribute(tc::shift_gemm_kernel<64>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         tc::Cfg<64>::SMEM_BYTES));
+    FR_CUDA_OK(ctx, cudaFuncSetAttribute(tc::shift_gemm_kernel<128>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         tc::Cfg<128>::SMEM_BYTES));
+    FR_CUDA_OK(ctx, cudaFuncSetAttribute(tc::shift_gemm_kernel<256>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         tc::Cfg<256>::SMEM_BYTES));
+    attrs = true;
+  }
+  const int grid = std::min(total, num_sms);
+  switch (L.bn) {
+    case 64:
+      tc::shift_gemm_kernel<64><<<grid, tc::NUM_THREADS, tc::Cfg<64>::SMEM_BYTES, ctx->stream>>>(
+          L.a0, L.a1, L.b0, L.b1, L.p);
+      break;
+    case 128:
+      tc::shift_gemm_kernel<128><<<grid, tc::NUM_THREADS, tc::Cfg<128>::SMEM_BYTES, ctx->stream>>>(
+          L.a0, L.a1, L.b0, L.b1, L.p);
+      break;
+    default:
+      tc::shift_gemm_kernel<256><<<grid, tc::NUM_THREADS, tc::Cfg<256>::SMEM_BYTES, ctx->stream>>>(
+          L.a0, L.a1, L.b0, L.b1, L.p);
+      break;
+  }
+  ctx->launches++;
+  FR_CUDA_OK(ctx, cudaGetLastError());
+  return FR_OK;
+}
+
+namespace {
+
+constexpr int REC = FR_REC_SIZE;
+
+struct Act {          // one activation tensor in padded flat NHWC layout
+  bf16* p = nullptr;
+  int H = 0, W = 0, C = 0;  // valid extent (cells for s2d) and channels per row
+  int Hp = 0, Wp = 0;
+  size_t rows(int n) const { return (size_t)n * Hp * Wp; }
+  size_t bytes(int n) const { return rows(n) * C * 2; }
+};
+
+struct BlockW {       // device weights of one IBasicBlock
+  bf16* w1 = nullptr;     // [9][planes][cin]   (bn1 scale folded)
+  float* b1 = nullptr;    // [9 classes][planes]
+  float* prelu = nullptr; // [planes]
+  bf16* w2 = nullptr;     // [9][planes][planes]
+  bf16* wds = nullptr;    // [planes][cin] or null
+  float* b2 = nullptr;    // [planes] (conv2 bias + ds bias)
+  int cin = 0, planes = 0, stride = 1;
+};
+
+}  // namespace
+
+struct RecModel {
+  // stem
+  float* stem_w = nullptr;  // [27][64], k = (r*3+s)*3 + c (c in RGB order)
+  float* stem_b = nullptr;
+  float* stem_prelu = nullptr;
+  std::vector<BlockW> blocks;
+  bf16* fc_w = nullptr;     // [512][64*512] (bn2, feat affine folded; zero at halo cells)
+  float* fc_b = nullptr;
+  std::vector<void*> allocs;
+  int* err_flag = nullptr;
+
+  // plan (per capacity)
+  int cap = 0;
+  std::vector<void*> plan_allocs;
+  Act x0, x0e;
+  struct BlockBufs { Act h, out, out_even; };
+  std::vector<BlockBufs> bufs;
+  std::vector<ConvLaunch> conv1, conv2;
+  ConvLaunch fc;
+  float* fc_out = nullptr;   // [cap,512] raw
+  float* chw_stage = nullptr;
+  size_t chw_stage_cap = 0;
+};
+
+namespace {
+
+template <typename T> T* dev_upload(fr_ctx* ctx, RecModel* m, const std::vector<T>& h) {
+  T* d = nullptr;
+  if (cudaMalloc(&d, h.size() * sizeof(T)) != cudaSuccess) return nullptr;
+  cudaMemcpyAsync(d, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice, ctx->stream);
+  cudaStreamSynchronize(ctx->stream);
+  m->allocs.push_back(d);
+  return d;
+}
+
+std::vector<bf16> to_bf16(const std::vector<float>& v) {
+  std::vector<bf16> o(v.size());
+  for (size_t i = 0; i < v.size(); ++i) o[i] = __float2bfloat16_rn(v[i]);
+  return o;
+}
+
+// ------------------------------------------------------------------- stem kernel
+// One thread = 2 horizontally adjacent output pixels x 64 channels.  Input either u8 BGR HWC
+// crops (FaceRecognizer::preprocess fused: BGR->RGB, (v-127.5)/128) or fp32 CHW RGB.
+template <bool U8>
+__global__ void __launch_bounds__(128)
+stem_kernel(const void* __restrict__ in_, int n, const float* __restrict__ w,
+            const float* __restrict__ b, const float* __restrict__ slope, bf16* __restrict__ x0,
+            bf16* __restrict__ x0e) {
+  __shared__ __align__(16) float sw[27 * 64];
+  __shared__ __align__(16) float sb[64];
+  __shared__ __align__(16) float ss[64];
+  for (int i = threadIdx.x; i < 27 * 64; i += blockDim.x) sw[i] = w[i];
+  if (threadIdx.x < 64) { sb[threadIdx.x] = b[threadIdx.x]; ss[threadIdx.x] = slope[threadIdx.x]; }
+  __syncthreads();
+  const int pairs_per_img = REC * (REC / 2);
+  const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid >= (long long)n * pairs_per_img) return;
+  const int img = (int)(gid / pairs_per_img);
+  const int rem = (int)(gid % pairs_per_img);
+  const int y = rem / (REC / 2);
+  const int x = (rem % (REC / 2)) * 2;
+  // 3 rows x 4 cols x 3 channels input window (RGB order)
+  float win[3][4][3];
+#pragma unroll
+  for (int r = 0; r < 3; ++r)
+#pragma unroll
+    for (int s = 0; s < 4; ++s) {
+      const int yy = y + r - 1, xx = x + s - 1;
+      const bool ok = yy >= 0 && yy < REC && xx >= 0 && xx < REC;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        float v = 0.f;
+        if (ok) {
+          if (U8) {
+            const uint8_t* p = reinterpret_cast<const uint8_t*>(in_) +
+                               ((size_t)img * REC * REC + (size_t)yy * REC + xx) * 3;
+            v = ((float)p[2 - c] - 127.5f) * (1.0f / 128.0f);
+          } else {
+            v = reinterpret_cast<const float*>(in_)[((size_t)img * 3 + c) * REC * REC +
+                                                    (size_t)yy * REC + xx];
+          }
+        }
+        win[r][s][c] = v;
+      }
+    }
+  const int Wp = REC + 1, Hp = REC + 1, We = REC / 2 + 1, He = REC / 2 + 1;
+  bf16* o0 = x0 + ((size_t)(img * Hp + y) * Wp + x) * 64;
+  bf16* o1 = o0 + 64;
+  bf16* oe = (!(y & 1)) ? x0e + ((size_t)(img * He + (y >> 1)) * We + (x >> 1)) * 64 : nullptr;
+#pragma unroll 1
+  for (int cg = 0; cg < 64; cg += 16) {
+    float a0[16], a1[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) { a0[i] = sb[cg + i]; a1[i] = a0[i]; }
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+      for (int s = 0; s < 3; ++s)
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          const float v0 = win[r][s][c], v1 = win[r][s + 1][c];
+          const float4* wp = reinterpret_cast<const float4*>(&sw[((r * 3 + s) * 3 + c) * 64 + cg]);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float4 w4 = wp[i];
+            a0[4 * i] = fmaf(v0, w4.x, a0[4 * i]);
+            a0[4 * i + 1] = fmaf(v0, w4.y, a0[4 * i + 1]);
+            a0[4 * i + 2] = fmaf(v0, w4.z, a0[4 * i + 2]);
+            a0[4 * i + 3] = fmaf(v0, w4.w, a0[4 * i + 3]);
+            a1[4 * i] = fmaf(v1, w4.x, a1[4 * i]);
+            a1[4 * i + 1] = fmaf(v1, w4.y, a1[4 * i + 1]);
+            a1[4 * i + 2] = fmaf(v1, w4.z, a1[4 * i + 2]);
+            a1[4 * i + 3] = fmaf(v1, w4.w, a1[4 * i + 3]);
+          }
+        }
+    uint4 p0[2], p1[2];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const float sl = ss[cg + i];
+      a0[i] = a0[i] > 0.f ? a0[i] : a0[i] * sl;
+      a1[i] = a1[i] > 0.f ? a1[i] : a1[i] * sl;
+    }
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      p0[i].x = tc::pack_bf16(a0[8 * i], a0[8 * i + 1]);
+      p0[i].y = tc::pack_bf16(a0[8 * i + 2], a0[8 * i + 3]);
+      p0[i].z = tc::pack_bf16(a0[8 * i + 4], a0[8 * i + 5]);
+      p0[i].w = tc::pack_bf16(a0[8 * i + 6], a0[8 * i + 7]);
+      p1[i].x = tc::pack_bf16(a1[8 * i], a1[8 * i + 1]);
+      p1[i].y = tc::pack_bf16(a1[8 * i + 2], a1[8 * i + 3]);
+      p1[i].z = tc::pack_bf16(a1[8 * i + 4], a1[8 * i + 5]);
+      p1[i].w = tc::pack_bf16(a1[8 * i + 6], a1[8 * i + 7]);
+    }
+    reinterpret_cast<uint4*>(o0 + cg)[0] = p0[0];
+    reinterpret_cast<uint4*>(o0 + cg)[1] = p0[1];
+    reinterpret_cast<uint4*>(o1 + cg)[0] = p1[0];
+    reinterpret_cast<uint4*>(o1 + cg)[1] = p1[1];
+    if (oe) {
+      reinterpret_cast<uint4*>(oe + cg)[0] = p0[0];
+      reinterpret_cast<uint4*>(oe + cg)[1] = p0[1];
+    }
+  }
+}
+
+// R4: FaceRecognizer::normalize (src/face_recognizer.cpp:306-318): one warp per row.
+__global__ void l2_normalize_kernel(const float* __restrict__ in, int n, int dim,
+                                    float* __restrict__ out, const int* __restrict__ valid) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= n) return;
+  const float* r = in + (size_t)row * dim;
+  float* o = out + (size_t)row * dim;
+  if (valid && valid[row] == 0) {
+    for (int i = lane; i < dim; i += 32) o[i] = 0.f;
+    return;
+  }
+  float s = 0.f;
+  for (int i = lane; i < dim; i += 32) s = fmaf(r[i], r[i], s);
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+  const float norm = sqrtf(s);
+  for (int i = lane; i < dim; i += 32) o[i] = norm > 0.f ? __fdiv_rn(r[i], norm) : r[i];
+}
+
+// K8 batched: out[i] = (dot(a_i, b_i) + 1) / 2 (src/face_recognizer.cpp:326-333).
+__global__ void compare_batch_kernel(const float* __restrict__ a, const float* __restrict__ b,
+                                     int n, int dim, float* __restrict__ out) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= n) return;
+  float s = 0.f;
+  for (int i = lane; i < dim; i += 32) s = fmaf(a[(size_t)row * dim + i], b[(size_t)row * dim + i], s);
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+  if (lane == 0) out[row] = (s + 1.0f) / 2.0f;
+}
+
+// --------------------------------------------------------------- weight packing
+// conv OIHW fp32 -> [tap][co][ci] bf16 with optional per-ci scale
+std::vector<bf16> pack_conv3(const fr_tensor& w, const std::vector<float>* scale) {
+  const int co = (int)w.dims[0], ci = (int)w.dims[1], k = (int)w.dims[2];
+  std::vector<bf16> o((size_t)k * k * co * ci);
+  for (int r = 0; r < k; ++r)
+    for (int s = 0; s < k; ++s)
+      for (int a = 0; a < co; ++a)
+        for (int c = 0; c < ci; ++c) {
+          float v = w.data[(((size_t)a * ci + c) * k + r) * k + s];
+          if (scale) v *= (*scale)[c];
+          o[(((size_t)(r * k + s)) * co + a) * ci + c] = __float2bfloat16_rn(v);
+        }
+  return o;
+}
+
+// bias table [9][co]: b[co] + sum over taps valid in the border class of W[co,ci,r,s]*shift[ci]
+std::vector<float> border_bias(const fr_tensor& w, const std::vector<float>& b,
+                               const std::vector<float>& shift) {
+  const int co = (int)w.dims[0], ci = (int)w.dims[1];
+  std::vector<double> tapsum((size_t)9 * co, 0.0);
+  for (int a = 0; a < co; ++a)
+    for (int c = 0; c < ci; ++c)
+      for (int t = 0; t < 9; ++t) tapsum[(size_t)t * co + a] += (double)w.data[((size_t)a * ci + c) * 9 + t] * shift[c];
+  std::vector<float> o((size_t)9 * co);
+  for (int vc = 0; vc < 3; ++vc)
+    for (int hc = 0; hc < 3; ++hc)
+      for (int a = 0; a < co; ++a) {
+        double s = b[a];
+        for (int r = 0; r < 3; ++r) {
+          if ((vc == 0 && r == 0) || (vc == 2 && r == 2)) continue;
+          for (int q = 0; q < 3; ++q) {
+            if ((hc == 0 && q == 0) || (hc == 2 && q == 2)) continue;
+            s += tapsum[(size_t)(r * 3 + q) * co + a];
+          }
+        }
+        o[(size_t)(vc * 3 + hc) * co + a] = (float)s;
+      }
+  return o;
+}
+
+void fill_taps_s1(tc::Params& p, int Wp, int cout, int cin) {
+  p.num_taps = 9;
+  for (int r = 0; r < 3; ++r)
+    for (int s = 0; s < 3; ++s) {
+      tc::Tap& t = p.taps[r * 3 + s];
+      t.a_src = 0; t.b_src = 0;
+      t.a_row_shift = (r - 1) * Wp + (s - 1);
+      t.a_col = 0;
+      t.b_row = (r * 3 + s) * cout;
+      t.nkb = cin / 64;
+    }
+}
+
+// stride-2 3x3 conv over a space-to-depth input (4 phase blocks of `c` channels per cell)
+void fill_taps_s2(tc::Params& p, int Wp2, int cout, int c) {
+  p.num_taps = 9;
+  for (int r = 0; r < 3; ++r)
+    for (int s = 0; s < 3; ++s) {
+      tc::Tap& t = p.taps[r * 3 + s];
+      t.a_src = 0; t.b_src = 0;
+      const int dr = (r == 0) ? -1 : 0, dc = (s == 0) ? -1 : 0;
+      const int pr = (r == 1) ? 0 : 1, pc = (s == 1) ? 0 : 1;
+      t.a_row_shift = dr * Wp2 + dc;
+      t.a_col = (pr * 2 + pc) * c;
+      t.b_row = (r * 3 + s) * cout;
+      t.nkb = c / 64;
+    }
+}
+
+int pick_bn(int cout) { return cout >= 256 ? 256 : cout; }
+
+}  // namespace
+
+// ------------------------------------------------------------------ model create
+int rec_model_create(fr_ctx* ctx, const fr_weights* w) {
+  if (!w || w->model != FR_MODEL_REC) return fr_fail(ctx, FR_ERR_MODEL, "rec weights missing");
+  if (!get_encode_fn()) return fr_fail(ctx, FR_ERR_CUDA, "cuTensorMapEncodeTiled unavailable");
+  std::unique_ptr<RecModel> m(new RecModel());
+  {
+    // stem: OIHW [64,3,3,3] -> [k=(r*3+s)*3+c][64]
+    const fr_tensor& sw = w->at("stem.w");
+    std::vector<float> pw(27 * 64);
+    for (int co = 0; co < 64; ++co)
+      for (int c = 0; c < 3; ++c)
+        for (int r = 0; r < 3; ++r)
+          for (int s = 0; s < 3; ++s)
+            pw[((r * 3 + s) * 3 + c) * 64 + co] = sw.data[((co * 3 + c) * 3 + r) * 3 + s];
+    m->stem_w = dev_upload(ctx, m.get(), pw);
+    m->stem_b = dev_upload(ctx, m.get(), w->at("stem.b").data);
+    m->stem_prelu = dev_upload(ctx, m.get(), w->at("stem.prelu").data);
+  }
+  const int layers[4][2] = {{3, 64}, {4, 128}, {14, 256}, {3, 512}};
+  int cin = 64;
+  for (int l = 0; l < 4; ++l)
+    for (int b = 0; b < layers[l][0]; ++b) {
+      const std::string p = "l" + std::to_string(l) + "." + std::to_string(b);
+      BlockW bw;
+      bw.cin = cin;
+      bw.planes = layers[l][1];
+      bw.stride = b == 0 ? 2 : 1;
+      const fr_tensor& w1 = w->at(p + ".conv1.w");
+      const std::vector<float>& sc = w->at(p + ".bn1.scale").data;
+      const std::vector<float>& sh = w->at(p + ".bn1.shift").data;
+      bw.w1 = dev_upload(ctx, m.get(), pack_conv3(w1, &sc));
+      bw.b1 = dev_upload(ctx, m.get(), border_bias(w1, w->at(p + ".conv1.b").data, sh));
+      bw.prelu = dev_upload(ctx, m.get(), w->at(p + ".prelu").data);
+      bw.w2 = dev_upload(ctx, m.get(), pack_conv3(w->at(p + ".conv2.w"), nullptr));
+      std::vector<float> b2 = w->at(p + ".conv2.b").data;
+      if (b == 0) {
+        const fr_tensor& wd = w->at(p + ".ds.w");
+        bw.wds = dev_upload(ctx, m.get(), to_bf16(wd.data));  // [planes][cin] already K-major
+        const std::vector<float>& bd = w->at(p + ".ds.b").data;
+        for (size_t i = 0; i < b2.size(); ++i) b2[i] += bd[i];
+      }
+      bw.b2 = dev_upload(ctx, m.get(), b2);
+      if (!bw.w1 || !bw.b1 || !bw.prelu || !bw.w2 || !bw.b2)
+        return fr_fail(ctx, FR_ERR_CUDA, "rec weight upload failed");
+      m->blocks.push_back(bw);
+      cin = bw.planes;
+    }
+  {
+    // tail: out = fs * (Wfc * (s2 .* x + t2) + bfc) + ft, x in padded 8x8x512 cell layout
+    const std::vector<float>& s2 = w->at("bn2.scale").data;
+    const std::vector<float>& t2 = w->at("bn2.shift").data;
+    const fr_tensor& fw = w->at("fc.w");
+    const std::vector<float>& fb = w->at("fc.b").data;
+    const std::vector<float>& fs = w->at("feat.scale").data;
+    const std::vector<float>& ft = w->at("feat.shift").data;
+    const int K = 64 * 512;
+    std::vector<bf16> pw((size_t)512 * K, __float2bfloat16_rn(0.f));
+    std::vector<float> pb(512);
+    for (int o = 0; o < 512; ++o) {
+      double acc = fb[o];
+      for (int c = 0; c < 512; ++c)
+        for (int hw = 0; hw < 49; ++hw) {
+          const float wv = fw.data[(size_t)o * 25088 + (size_t)c * 49 + hw];
+          acc += (double)wv * t2[c];
+          const int h = hw / 7, x = hw % 7;
+          pw[(size_t)o * K + (size_t)(h * 8 + x) * 512 + c] = __float2bfloat16_rn(fs[o] * wv * s2[c]);
+        }
+      pb[o] = (float)(fs[o] * acc + ft[o]);
+    }
+    m->fc_w = dev_upload(ctx, m.get(), pw);
+    m->fc_b = dev_upload(ctx, m.get(), pb);
+    if (!m->fc_w || !m->fc_b) return fr_fail(ctx, FR_ERR_CUDA, "fc weight upload failed");
+  }
+  if (cudaMalloc(&m->err_flag, sizeof(int)) != cudaSuccess)
+    return fr_fail(ctx, FR_ERR_CUDA, "err flag alloc failed");
+  cudaMemset(m->err_flag, 0, sizeof(int));
+  ctx->rec = m.release();
+  return FR_OK;
+}
+
+static void rec_free_plan(RecModel* m) {
+  for (void* p : m->plan_allocs) cudaFree(p);
+  m->plan_allocs.clear();
+  m->bufs.clear();
+  m->conv1.clear();
+  m->conv2.clear();
+  m->cap = 0;
+}
+
+void rec_model_destroy(fr_ctx* ctx) {
+  RecModel* m = ctx->rec;
+  if (!m) return;
+  rec_free_plan(m);
+  for (void* p : m->allocs) cudaFree(p);
+  if (m->err_flag) cudaFree(m->err_flag);
+  if (m->chw_stage) cudaFree(m->chw_stage);
+  delete m;
+  ctx->rec = nullptr;
+}
+
+namespace {
+
+bool alloc_act(RecModel* m, Act& a, int cap, int H, int W, int C, cudaStream_t st) {
+  a.H = H; a.W = W; a.C = C; a.Hp = H + 1; a.Wp = W + 1;
+  void* p = nullptr;
+  if (cudaMalloc(&p, a.bytes(cap)) != cudaSuccess) return false;
+  cudaMemsetAsync(p, 0, a.bytes(cap), st);  // halo cells stay zero forever
+  a.p = reinterpret_cast<bf16*>(p);
+  m->plan_allocs.push_back(p);
+  return true;
+}
+
+}  // namespace
+
+// Build buffers, tensor maps and launch parameters for up to `cap` faces per call.
+static int rec_build_plan(fr_ctx* ctx, int cap) {
+  RecModel* m = ctx->rec;
+  if (m->cap >= cap) return FR_OK;
+  FR_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+  rec_free_plan(m);
+  cudaStream_t st = ctx->stream;
+  bool ok = alloc_act(m, m->x0, cap, 112, 112, 64, st) && alloc_act(m, m->x0e, cap, 56, 56, 64, st);
+  const size_t nb = m->blocks.size();
+  m->bufs.resize(nb);
+  m->conv1.resize(nb);
+  m->conv2.resize(nb);
+  int H = 112;  // spatial size of the current residual stream
+  Act x = m->x0, xe = m->x0e;
+  for (size_t i = 0; ok && i < nb; ++i) {
+    const BlockW& bw = m->blocks[i];
+    RecModel::BlockBufs& bb = m->bufs[i];
+    const int Ho = H / bw.stride;
+    const bool next_ds = (i + 1 < nb) && m->blocks[i + 1].stride == 2;
+    if (bw.stride == 2)
+      ok = ok && alloc_act(m, bb.h, cap, Ho, Ho, 4 * bw.planes, st);  // s2d cells
+    else
+      ok = ok && alloc_act(m, bb.h, cap, H, H, bw.planes, st);
+    ok = ok && alloc_act(m, bb.out, cap, Ho, Ho, bw.planes, st);
+    if (next_ds) ok = ok && alloc_act(m, bb.out_even, cap, Ho / 2, Ho / 2, bw.planes, st);
+    if (!ok) break;
+    // ---- conv1: 3x3 s1, x -> h (bias by border class, PReLU)
+    ConvLaunch& c1 = m->conv1[i];
+    memset(&c1.p, 0, sizeof(c1.p));
+    c1.bn = pick_bn(bw.planes);
+    fill_taps_s1(c1.p, x.Wp, bw.planes, bw.cin);
+    c1.p.n_tiles_n = bw.planes / c1.bn;
+    c1.p.H = H; c1.p.W = H; c1.p.Hp = x.Hp; c1.p.Wp = x.Wp;
+    c1.p.cout = bw.planes;
+    c1.p.bias = bw.b1; c1.p.bias_classes = 9;
+    c1.p.prelu = bw.prelu;
+    c1.p.out = bb.h.p;
+    c1.p.err_flag = m->err_flag;
+    c1.rows_per_img = x.Hp * x.Wp;
+    if (bw.stride == 2) {
+      c1.p.out_mode = tc::OUT_S2D;
+      c1.p.Hp2 = bb.h.Hp; c1.p.Wp2 = bb.h.Wp;
+    } else {
+      c1.p.out_mode = tc::OUT_STD;
+    }
+    ok = ok && tc_make_map_2d(&c1.a0, x.p, x.rows(cap), x.C, x.C, tc::BM);
+    c1.a1 = c1.a0;
+    ok = ok && tc_make_map_2d(&c1.b0, bw.w1, (uint64_t)9 * bw.planes, bw.cin, bw.cin, c1.bn);
+    c1.b1 = c1.b0;
+    // ---- conv2: 3x3 stride s (+ fused 1x1 shortcut conv) + residual -> out
+    ConvLaunch& c2 = m->conv2[i];
+    memset(&c2.p, 0, sizeof(c2.p));
+    c2.bn = pick_bn(bw.planes);
+    c2.p.n_tiles_n = bw.planes / c2.bn;
+    c2.p.H = Ho; c2.p.W = Ho; c2.p.Hp = bb.out.Hp; c2.p.Wp = bb.out.Wp;
+    c2.p.cout = bw.planes;
+    c2.p.bias = bw.b2; c2.p.bias_classes = 1;
+    c2.p.out = bb.out.p;
+    c2.p.out_mode = tc::OUT_STD;
+    c2.p.err_flag = m->err_flag;
+    c2.rows_per_img = bb.out.Hp * bb.out.Wp;
+    if (next_ds) {
+      c2.p.out_even = bb.out_even.p;
+      c2.p.Hp2 = bb.out_even.Hp; c2.p.Wp2 = bb.out_even.Wp;
+    }
+    if (bw.stride == 2) {
+      fill_taps_s2(c2.p, bb.h.Wp, bw.planes, bw.planes);
+      tc::Tap& t = c2.p.taps[9];
+      t.a_src = 1; t.b_src = 1; t.a_row_shift = 0; t.a_col = 0; t.b_row = 0; t.nkb = bw.cin / 64;
+      c2.p.num_taps = 10;
+      ok = ok && tc_make_map_2d(&c2.a0, bb.h.p, bb.h.rows(cap), bb.h.C, bb.h.C, tc::BM);
+      ok = ok && tc_make_map_2d(&c2.a1, xe.p, xe.rows(cap), xe.C, xe.C, tc::BM);
+      ok = ok && tc_make_map_2d(&c2.b1, bw.wds, bw.planes, bw.cin, bw.cin, c2.bn);
+    } else {
+      fill_taps_s1(c2.p, bb.h.Wp, bw.planes, bw.planes);
+      c2.p.residual = x.p;
+      ok = ok && tc_make_map_2d(&c2.a0, bb.h.p, bb.h.rows(cap), bb.h.C, bb.h.C, tc::BM);
+      c2.a1 = c2.a0;
+    }
+    ok = ok && tc_make_map_2d(&c2.b0, bw.w2, (uint64_t)9 * bw.planes, bw.planes, bw.planes, c2.bn);
+    if (bw.stride != 2) c2.b1 = c2.b0;
+    x = bb.out;
+    xe = bb.out_even;
+    H = Ho;
+  }
+  if (ok) {
+    void* p = nullptr;
+    ok = cudaMalloc(&p, (size_t)cap * 512 * sizeof(float)) == cudaSuccess;
+    if (ok) { m->fc_out = reinterpret_cast<float*>(p); m->plan_allocs.push_back(p); }
+  }
+  if (ok) {
+    ConvLaunch& f = m->fc;
+    memset(&f.p, 0, sizeof(f.p));
+    f.bn = 256;
+    f.p.num_taps = 1;
+    f.p.taps[0].nkb = 64 * 512 / 64;
+    f.p.n_tiles_n = 2;
+    f.p.H = f.p.W = f.p.Hp = f.p.Wp = 1;
+    f.p.cout = 512;
+    f.p.bias = m->fc_b; f.p.bias_classes = 1;
+    f.p.out_mode = tc::OUT_F32;
+    f.p.out_f32 = m->fc_out;
+    f.p.err_flag = m->err_flag;
+    f.rows_per_img = 1;
+    ok = ok && tc_make_map_2d(&f.a0, x.p, (uint64_t)cap, 64 * 512, 64 * 512, tc::BM);
+    f.a1 = f.a0;
+    ok = ok && tc_make_map_2d(&f.b0, m->fc_w, 512, 64 * 512, 64 * 512, 256);
+    f.b1 = f.b0;
+  }
+  if (!ok) {
+    rec_free_plan(m);
+    return fr_fail(ctx, FR_ERR_CUDA, "rec plan allocation / tensor map encode failed");
+  }
+  m->cap = cap;
+  FR_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+  return FR_OK;
+}
+
+static int rec_run_trunk(fr_ctx* ctx, int n, float* d_out_raw) {
+  RecModel* m = ctx->rec;
+  for (size_t i = 0; i < m->blocks.size(); ++i) {
+    FR_CHECK(tc_launch(ctx, m->conv1[i], n * m->conv1[i].rows_per_img));
+    FR_CHECK(tc_launch(ctx, m->conv2[i], n * m->conv2[i].rows_per_img));
+  }
+  ConvLaunch f = m->fc;
+  f.p.out_f32 = d_out_raw ? d_out_raw : m->fc_out;
+  FR_CHECK(tc_launch(ctx, f, n));
+  return FR_OK;
+}
+
+static int rec_plan_cap(int n) {
+  int cap = 64;
+  while (cap < n) cap *= 2;
+  return cap;
+}
+
+int rec_forward_crops(fr_ctx* ctx, const uint8_t* d_crops, int n, float* d_out_raw,
+                      float* d_out_norm, const int* d_valid) {
+  RecModel* m = ctx->rec;
+  if (!m) return fr_fail(ctx, FR_ERR_NOT_LOADED, "Model not loaded!");
+  if (n <= 0) return FR_OK;
+  FR_CHECK(rec_build_plan(ctx, rec_plan_cap(n)));
+  const long long threads = (long long)n * REC * (REC / 2);
+  stem_kernel<true><<<(unsigned)((threads + 127) / 128), 128, 0, ctx->stream>>>(
+      d_crops, n, m->stem_w, m->stem_b, m->stem_prelu, m->x0.p, m->x0e.p);
+  ctx->launches++;
+  FR_CUDA_OK(ctx, cudaGetLastError());
+  float* raw = d_out_raw ? d_out_raw : m->fc_out;
+  FR_CHECK(rec_run_trunk(ctx, n, raw));
+  if (d_out_norm) FR_CHECK(k_l2_normalize(ctx, raw, n, 512, d_out_norm, d_valid));
+  return FR_OK;
+}
+
+int rec_forward_chw(fr_ctx* ctx, const float* d_chw, int n, float* d_out_raw) {
+  RecModel* m = ctx->rec;
+  if (!m) return fr_fail(ctx, FR_ERR_NOT_LOADED, "Model not loaded!");
+  if (n <= 0) return FR_OK;
+  FR_CHECK(rec_build_plan(ctx, rec_plan_cap(n)));
+  const long long threads = (long long)n * REC * (REC / 2);
+  stem_kernel<false><<<(unsigned)((threads + 127) / 128), 128, 0, ctx->stream>>>(
+      d_chw, n, m->stem_w, m->stem_b, m->stem_prelu, m->x0.p, m->x0e.p);
+  ctx->launches++;
+  FR_CUDA_OK(ctx, cudaGetLastError());
+  return rec_run_trunk(ctx, n, d_out_raw);
+}
+
+// Copy an activation back as fp32 NCHW.  tap 0 = stem; 2*i-1 = h of block i; 2*i = out of block i.
+int rec_tap(fr_ctx* ctx, int tap, int n, float* h_out, size_t out_elems) {
+  RecModel* m = ctx->rec;
+  if (!m || m->cap < n) return fr_fail(ctx, FR_ERR_INVALID_ARG, "rec_tap: no forward has run");
+  Act a;
+  bool s2d = false;
+  if (tap == 0) {
+    a = m->x0;
+  } else {
+    const int blk = (tap - 1) / 2;
+    if (blk < 0 || blk >= (int)m->blocks.size()) return fr_fail(ctx, FR_ERR_INVALID_ARG, "bad tap");
+    if (tap & 1) { a = m->bufs[blk].h; s2d = m->blocks[blk].stride == 2; }
+    else a = m->bufs[blk].out;
+  }
+  const int C = s2d ? a.C / 4 : a.C;
+  const int H = s2d ? a.H * 2 : a.H, W = s2d ? a.W * 2 : a.W;
+  if (out_elems != (size_t)n * C * H * W) return fr_fail(ctx, FR_ERR_CAPACITY, "rec_tap: size mismatch");
+  std::vector<bf16> host(a.rows(n) * a.C);
+  FR_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+  FR_CUDA_OK(ctx, cudaMemcpy(host.data(), a.p, host.size() * 2, cudaMemcpyDeviceToHost));
+  for (int i = 0; i < n; ++i)
+    for (int c = 0; c < C; ++c)
+      for (int y = 0; y < H; ++y)
+        for (int x = 0; x < W; ++x) {
+          size_t src;
+          if (s2d)
+            src = (((size_t)(i * a.Hp + (y >> 1)) * a.Wp + (x >> 1)) * 4 + ((y & 1) * 2 + (x & 1))) * C + c;
+          else
+            src = ((size_t)(i * a.Hp + y) * a.Wp + x) * C + c;
+          h_out[(((size_t)i * C + c) * H + y) * W + x] = __bfloat162float(host[src]);
+        }
+  return FR_OK;
+}
+
+// Unit-test hook: one 3x3 stride-1 (or 1x1) convolution through the tcgen05 kernel.
+int rec_test_conv(fr_ctx* ctx, const float* x, int n, int cin, int h, int w, const float* wgt,
+                  int cout, int ksize, int stride, const float* pre_scale,
+                  const float* pre_shift, const float* bias, const float* prelu,
+                  const float* residual, float* y) {
+  if (stride != 1 || (ksize != 3 && ksize != 1) || cin % 64 || cout % 64 ||
+      (cout > 256 && cout % 256))
+    return fr_fail(ctx, FR_ERR_UNSUPPORTED, "fr_test_conv: unsupported shape");
+  if (!get_encode_fn()) return fr_fail(ctx, FR_ERR_CUDA, "cuTensorMapEncodeTiled unavailable");
+  const int Hp = h + 1, Wp = w + 1;
+  const size_t rows = (size_t)n * Hp * Wp;
+  std::vector<bf16> xin(rows * cin, __float2bfloat16_rn(0.f));
+  for (int i = 0; i < n; ++i)
+    for (int c = 0; c < cin; ++c)
+      for (int yy = 0; yy < h; ++yy)
+        for (int xx = 0; xx < w; ++xx)
+          xin[((size_t)(i * Hp + yy) * Wp + xx) * cin + c] =
+              __float2bfloat16_rn(x[(((size_t)i * cin + c) * h + yy) * w + xx]);
+  fr_tensor wt;
+  wt.dims = {cout, cin, ksize, ksize};
+  wt.data.assign(wgt, wgt + (size_t)cout * cin * ksize * ksize);
+  std::vector<float> sc, sh(cin, 0.f), bs(cout, 0.f);
+  if (pre_scale) sc.assign(pre_scale, pre_scale + cin);
+  if (pre_shift) sh.assign(pre_shift, pre_shift + cin);
+  if (bias) bs.assign(bias, bias + cout);
+  std::vector<bf16> pw = pack_conv3(wt, pre_scale ? &sc : nullptr);
+  std::vector<float> bt;
+  if (ksize == 3) {
+    bt = border_bias(wt, bs, sh);
+  } else {
+    bt = bs;
+    for (int a = 0; a < cout; ++a) {
+      double s = 0;
+      for (int c = 0; c < cin; ++c) s += (double)wgt[(size_t)a * cin + c] * sh[c];
+      bt[a] += (float)s;
+    }
+  }
+  std::vector<bf16> res;
+  if (residual) {
+    res.assign(rows * cout, __float2bfloat16_rn(0.f));
+    for (int i = 0; i < n; ++i)
+      for (int c = 0; c < cout; ++c)
+        for (int yy = 0; yy < h; ++yy)
+          for (int xx = 0; xx < w; ++xx)
+            res[((size_t)(i * Hp + yy) * Wp + xx) * cout + c] =
+                __float2bfloat16_rn(residual[(((size_t)i * cout + c) * h + yy) * w + xx]);
+  }
+  bf16 *d_x = nullptr, *d_w = nullptr, *d_res = nullptr, *d_y = nullptr;
+  float *d_b = nullptr, *d_p = nullptr;
+  int* d_err = nullptr;
+  auto cleanup = [&]() {
+    cudaFree(d_x); cudaFree(d_w); cudaFree(d_res); cudaFree(d_y); cudaFree(d_b); cudaFree(d_p);
+    cudaFree(d_err);
+  };
+  bool ok = cudaMalloc(&d_x, xin.size() * 2) == cudaSuccess &&
+            cudaMalloc(&d_w, pw.size() * 2) == cudaSuccess &&
+            cudaMalloc(&d_y, rows * cout * 2) == cudaSuccess &&
+            cudaMalloc(&d_b, bt.size() * 4) == cudaSuccess &&
+            cudaMalloc(&d_err, 4) == cudaSuccess;
+  if (ok && prelu) ok = cudaMalloc(&d_p, cout * 4) == cudaSuccess;
+  if (ok && residual) ok = cudaMalloc(&d_res, res.size() * 2) == cudaSuccess;
+  if (!ok) { cleanup(); return fr_fail(ctx, FR_ERR_CUDA, "fr_test_conv: alloc failed"); }
+  cudaMemcpy(d_x, xin.data(), xin.size() * 2, cudaMemcpyHostToDevice);
+  cudaMemcpy(d_w, pw.data(), pw.size() * 2, cudaMemcpyHostToDevice);
+  cudaMemcpy(d_b, bt.data(), bt.size() * 4, cudaMemcpyHostToDevice);
+  cudaMemset(d_y, 0, rows * cout * 2);
+  cudaMemset(d_err, 0, 4);
+  if (prelu) cudaMemcpy(d_p, prelu, cout * 4, cudaMemcpyHostToDevice);
+  if (residual) cudaMemcpy(d_res, res.data(), res.size() * 2, cudaMemcpyHostToDevice);
+  ConvLaunch L;
+  memset(&L.p, 0, sizeof(L.p));
+  L.bn = pick_bn(cout);
+  if (ksize == 3) {
+    fill_taps_s1(L.p, Wp, cout, cin);
+    L.p.bias_classes = 9;
+  } else {
+    L.p.num_taps = 1;
+    L.p.taps[0].nkb = cin / 64;
+    L.p.bias_classes = 1;
+  }
+  L.p.n_tiles_n = cout / L.bn;
+  L.p.H = h; L.p.W = w; L.p.Hp = Hp; L.p.Wp = Wp;
+  L.p.cout = cout;
+  L.p.bias = d_b;
+  L.p.prelu = d_p;
+  L.p.residual = d_res;
+  L.p.out = d_y;
+  L.p.out_mode = tc::OUT_STD;
+  L.p.err_flag = d_err;
+  ok = tc_make_map_2d(&L.a0, d_x, rows, cin, cin, tc::BM) &&
+       tc_make_map_2d(&L.b0, d_w, (uint64_t)ksize * ksize * cout, cin, cin, L.bn);
+  L.a1 = L.a0;
+  L.b1 = L.b0;
+  int status = FR_OK;
+  if (!ok) status = fr_fail(ctx, FR_ERR_CUDA, "fr_test_conv: tensor map encode failed");
+  if (status == FR_OK) status = tc_launch(ctx, L, (int)rows);
+  if (status == FR_OK) {
+    cudaError_t e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) status = fr_fail(ctx, FR_ERR_CUDA, std::string("fr_test_conv: ") + cudaGetErrorString(e));
+  }
+  if (status == FR_OK) {
+    std::vector<bf16> yo(rows * cout);
+    cudaMemcpy(yo.data(), d_y, yo.size() * 2, cudaMemcpyDeviceToHost);
+    for (int i = 0; i < n; ++i)
+      for (int c = 0; c < cout; ++c)
+        for (int yy = 0; yy < h; ++yy)
+          for (int xx = 0; xx < w; ++xx)
+            y[(((size_t)i * cout + c) * h + yy) * w + xx] =
+                __bfloat162float(yo[((size_t)(i * Hp + yy) * Wp + xx) * cout + c]);
+  }
+  cleanup();
+  return status;
+}
+
+int k_l2_normalize(fr_ctx* ctx, const float* d_in, int n, int dim, float* d_out,
+                   const int* d_valid) {
+  if (n <= 0) return FR_OK;
+  l2_normalize_kernel<<<ceil_div(n, 8), 256, 0, ctx->stream>>>(d_in, n, dim, d_out, d_valid);
+  ctx->launches++;
+  FR_CUDA_OK(ctx, cudaGetLastError());
+  return FR_OK;
+}
+
+int k_compare_batch(fr_ctx* ctx, const float* d_a, const float* d_b, int n, int dim, float* d_out) {
+  if (n <= 0) return FR_OK;
+  compare_batch_kernel<<<ceil_div(n, 8), 256, 0, ctx->stream>>>(d_a, d_b, n, dim, d_out);
+  ctx->launches++;
+  FR_CUDA_OK(ctx, cudaGetLastError());
+  return FR_OK;
+}

@@ -1,0 +1,404 @@
+// tcgen05 / TMEM / TMA shift-GEMM kernel for sm_100a: the implicit-GEMM engine behind the
+// IResNet-50 convolutions (K6), the FC layer (K7) and the gallery search (K9).
+//
+//   D[m, n] = sum over taps t, k:  A_t[m + shift_t, col_t + k] * B_t[row_t + n, k]
+//
+// Activations are NHWC bf16 with one shared zero halo column per row and one shared zero
+// halo row per image ("padded flat layout": pixel (n,h,w) lives at flat row
+// (n*Hp + h)*Wp + w, Hp = H+1, Wp = W+1).  Every out-of-image neighbour of a 3x3 stencil is
+// then either a halo cell (zero) or an out-of-range row (zero-filled by TMA), so a 3x3
+// convolution is nine row-shifted GEMMs over the same 2-D matrix [rows, C]; a stride-2
+// convolution reads a space-to-depth copy of its input (four phase blocks of C channels per
+// 2x2 cell) so that its nine taps are again plain row shifts, and the 1x1 stride-2 shortcut
+// conv is one more tap accumulating into the same TMEM tile.
+//
+// Warp roles (192 threads, 1 CTA/SM, persistent over output tiles):
+//   warp 0   : TMA producer (one elected lane), 128x64 A tile + BNx64 B tile per stage,
+//              SWIZZLE_128B, mbarrier expect_tx
+//   warp 1   : MMA issuer (one elected lane): tcgen05.mma cta_group::1 kind::f16,
+//              M=128, N=BN, K=16, fp32 accumulators in TMEM (double buffered: 2*BN columns)
+//   warps 2-5: epilogue: tcgen05.ld 32x32b -> bias (per border class) / PReLU / residual ->
+//              bf16 NHWC stores (standard, space-to-depth, + even-pixel copy) or fp32 rows
+#pragma once
+
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+#include <cstdint>
+
+namespace tc {
+
+constexpr int BM = 128;
+constexpr int BK = 64;
+constexpr int A_TILE_BYTES = BM * BK * 2;
+constexpr int MAX_TAPS = 10;
+constexpr int NUM_THREADS = 192;
+
+struct Tap {
+  int a_src;        // 0/1: which A tensor map
+  int b_src;        // 0/1: which B tensor map
+  int a_row_shift;  // added to the tile's first row
+  int a_col;        // first K column in A
+  int b_row;        // first row in B (before adding the N-tile offset)
+  int nkb;          // number of 64-wide K blocks
+};
+
+enum OutMode { OUT_STD = 0, OUT_S2D = 1, OUT_F32 = 2, OUT_TOPK = 3 };
+
+struct Params {
+  Tap taps[MAX_TAPS];
+  int num_taps;
+  int m_rows;       // valid output rows
+  int num_m_tiles;
+  int n_tiles_n;    // Cout / BN
+  int H, W, Hp, Wp; // output geometry (valid extent and padded pitch)
+  int Hp2, Wp2;     // geometry of the s2d / even-copy targets
+  int cout;
+  int bias_classes; // 1, or 9 = (top,mid,bottom) x (left,mid,right)
+  int out_mode;
+  const float* bias;
+  const float* prelu;
+  const __nv_bfloat16* residual;
+  __nv_bfloat16* out;
+  __nv_bfloat16* out_even;
+  float* out_f32;
+  int* err_flag;
+};
+
+template <int BN> struct Cfg {
+  static constexpr int B_TILE_BYTES = BN * BK * 2;
+  static constexpr int STAGE_BYTES = A_TILE_BYTES + B_TILE_BYTES;
+  static constexpr int STAGES = BN == 256 ? 4 : (BN == 128 ? 6 : 8);
+  static constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 256 + 1024;  // barriers + align slack
+};
+
+// ------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
+               "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// Bounded spin: a protocol bug traps (launch failure) instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int* err_flag) {
+  const uint32_t addr = smem_u32(bar);
+  uint32_t ok = 0;
+  long long t0 = 0;
+  for (uint32_t spin = 0;; ++spin) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(addr), "r"(parity)
+        : "memory");
+    if (ok) return;
+    if (spin == 1024) t0 = clock64();
+    if (spin > 1024 && (spin & 1023) == 0 && clock64() - t0 > 4000000000ll) {
+      if (err_flag) atomicExch(err_flag, 1);
+      __trap();
+    }
+  }
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar,
+                                            int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4}], [%2];"
+      :
+      : "r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0),
+        "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() {
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tc_fence_after() {
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
+                   smem_u32(bar))
+               : "memory");
+}
+// K-major, SWIZZLE_128B operand tile: rows of 128 bytes, 8-row swizzle atoms 1024 B apart.
+__device__ __forceinline__ uint64_t make_smem_desc(const void* p) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_u32(p) >> 4) & 0x3FFF);   // start address
+  d |= (uint64_t)1 << 16;                         // leading byte offset (ignored for SW128 K-major)
+  d |= (uint64_t)(1024 >> 4) << 32;               // stride byte offset between 8-row groups
+  d |= (uint64_t)1 << 46;                         // descriptor version (sm_100)
+  d |= (uint64_t)2 << 61;                         // SWIZZLE_128B
+  return d;
+}
+// kind::f16 instruction descriptor: bf16 x bf16 -> fp32, both operands K-major.
+__host__ __device__ constexpr uint32_t make_idesc(int m, int n) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+__device__ __forceinline__ void mma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc,
+                                         uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      :
+      : "r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]),
+        "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]),
+        "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]),
+        "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]),
+        "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+
+// ------------------------------------------------------------------------ kernel
+template <int BN>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+shift_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
+                  const __grid_constant__ CUtensorMap tmB0, const __grid_constant__ CUtensorMap tmB1,
+                  const __grid_constant__ Params p) {
+  using C = Cfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE_BYTES);
+  uint64_t* empty = full + C::STAGES;
+  uint64_t* tfull = empty + C::STAGES;
+  uint64_t* tempty = tfull + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < C::STAGES; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tfull[a], 1);
+      mbar_init(&tempty[a], 4);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    prefetch_tmap(&tmA0);
+    prefetch_tmap(&tmA1);
+    prefetch_tmap(&tmB0);
+    prefetch_tmap(&tmB1);
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                     smem_u32(tmem_slot)),
+                 "r"((uint32_t)C::TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int total_tiles = p.num_m_tiles * p.n_tiles_n;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int m0 = (tile / p.n_tiles_n) * BM;
+        const int n0 = (tile % p.n_tiles_n) * BN;
+        for (int t = 0; t < p.num_taps; ++t) {
+          const Tap tp = p.taps[t];
+          const CUtensorMap* ma = tp.a_src ? &tmA1 : &tmA0;
+          const CUtensorMap* mb = tp.b_src ? &tmB1 : &tmB0;
+          for (int kb = 0; kb < tp.nkb; ++kb) {
+            mbar_wait(&empty[stage], phase ^ 1u, p.err_flag);
+            mbar_expect_tx(&full[stage], C::STAGE_BYTES);
+            uint8_t* sa = smem + stage * C::STAGE_BYTES;
+            tma_load_2d(sa, ma, &full[stage], tp.a_col + kb * BK, m0 + tp.a_row_shift);
+            tma_load_2d(sa + A_TILE_BYTES, mb, &full[stage], kb * BK, tp.b_row + n0);
+            if (++stage == C::STAGES) { stage = 0; phase ^= 1u; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(BM, BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      uint32_t it = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+        const uint32_t acc = it & 1u;
+        const uint32_t acc_phase = (it >> 1) & 1u;
+        mbar_wait(&tempty[acc], acc_phase ^ 1u, p.err_flag);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        uint32_t accumulate = 0;
+        for (int t = 0; t < p.num_taps; ++t) {
+          const int nkb = p.taps[t].nkb;
+          for (int kb = 0; kb < nkb; ++kb) {
+            mbar_wait(&full[stage], phase, p.err_flag);
+            tc_fence_after();
+            const uint8_t* sa = smem + stage * C::STAGE_BYTES;
+            const uint64_t adesc = make_smem_desc(sa);
+            const uint64_t bdesc = make_smem_desc(sa + A_TILE_BYTES);
+#pragma unroll
+            for (int k = 0; k < BK / 16; ++k) {
+              // advance 16 bf16 = 32 bytes inside the 128-byte swizzle row: +2 in 16-byte units
+              mma_bf16(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc,
+                       accumulate);
+              accumulate = 1;
+            }
+            tc_commit(&empty[stage]);
+            if (++stage == C::STAGES) { stage = 0; phase ^= 1u; }
+          }
+        }
+        tc_commit(&tfull[acc]);
+      }
+    }
+  } else {
+    const int q = warp & 3;            // TMEM lane quarter this warp may access
+    const int row = q * 32 + lane;
+    uint32_t it = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      const int m0 = (tile / p.n_tiles_n) * BM;
+      const int n0 = (tile % p.n_tiles_n) * BN;
+      const uint32_t acc = it & 1u;
+      const uint32_t acc_phase = (it >> 1) & 1u;
+      const int m = m0 + row;
+      // geometry of this output row
+      bool valid = m < p.m_rows;
+      int img = 0, hp = 0, wp = 0;
+      if (valid && p.out_mode != OUT_F32) {
+        const int per_img = p.Hp * p.Wp;
+        img = m / per_img;
+        const int rem = m - img * per_img;
+        hp = rem / p.Wp;
+        wp = rem - hp * p.Wp;
+        valid = hp < p.H && wp < p.W;
+      }
+      int cls = 0;
+      if (p.bias_classes == 9)
+        cls = (hp == 0 ? 0 : (hp == p.H - 1 ? 2 : 1)) * 3 + (wp == 0 ? 0 : (wp == p.W - 1 ? 2 : 1));
+      const float* bias = p.bias + (size_t)cls * p.cout + n0;
+      size_t out_off = 0, even_off = 0;
+      bool write_even = false;
+      if (p.out_mode == OUT_STD) {
+        out_off = (size_t)m * p.cout + n0;
+        if (p.out_even && valid && !(hp & 1) && !(wp & 1)) {
+          write_even = true;
+          even_off = ((size_t)(img * p.Hp2 + (hp >> 1)) * p.Wp2 + (wp >> 1)) * p.cout + n0;
+        }
+      } else if (p.out_mode == OUT_S2D) {
+        out_off = (((size_t)(img * p.Hp2 + (hp >> 1)) * p.Wp2 + (wp >> 1)) * 4 +
+                   (size_t)((hp & 1) * 2 + (wp & 1))) * p.cout + n0;
+      } else {
+        out_off = (size_t)m * p.cout + n0;
+      }
+      mbar_wait(&tfull[acc], acc_phase, p.err_flag);
+      tc_fence_after();
+      const uint32_t taddr0 = tmem_base + acc * BN + ((uint32_t)(q * 32) << 16);
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        uint32_t v[32];
+        tmem_ld32(taddr0 + c * 32, v);
+        if (valid) {
+          float f[32];
+#pragma unroll
+          for (int i = 0; i < 32; i += 4) {
+            const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + c * 32 + i));
+            f[i] = __uint_as_float(v[i]) + b4.x;
+            f[i + 1] = __uint_as_float(v[i + 1]) + b4.y;
+            f[i + 2] = __uint_as_float(v[i + 2]) + b4.z;
+            f[i + 3] = __uint_as_float(v[i + 3]) + b4.w;
+          }
+          if (p.prelu) {
+#pragma unroll
+            for (int i = 0; i < 32; i += 4) {
+              const float4 s4 = __ldg(reinterpret_cast<const float4*>(p.prelu + n0 + c * 32 + i));
+              f[i] = f[i] > 0.f ? f[i] : f[i] * s4.x;
+              f[i + 1] = f[i + 1] > 0.f ? f[i + 1] : f[i + 1] * s4.y;
+              f[i + 2] = f[i + 2] > 0.f ? f[i + 2] : f[i + 2] * s4.z;
+              f[i + 3] = f[i + 3] > 0.f ? f[i + 3] : f[i + 3] * s4.w;
+            }
+          }
+          if (p.out_mode == OUT_F32) {
+            float4* o = reinterpret_cast<float4*>(p.out_f32 + out_off + c * 32);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) o[i] = make_float4(f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]);
+          } else {
+            if (p.residual) {
+              const uint4* r = reinterpret_cast<const uint4*>(p.residual + (size_t)m * p.cout + n0 + c * 32);
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const uint4 rv = __ldg(r + i);
+                const uint32_t w[4] = {rv.x, rv.y, rv.z, rv.w};
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  f[i * 8 + 2 * j] += __uint_as_float(w[j] << 16);
+                  f[i * 8 + 2 * j + 1] += __uint_as_float(w[j] & 0xffff0000u);
+                }
+              }
+            }
+            uint4 pk[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              pk[i].x = pack_bf16(f[i * 8 + 0], f[i * 8 + 1]);
+              pk[i].y = pack_bf16(f[i * 8 + 2], f[i * 8 + 3]);
+              pk[i].z = pack_bf16(f[i * 8 + 4], f[i * 8 + 5]);
+              pk[i].w = pack_bf16(f[i * 8 + 6], f[i * 8 + 7]);
+            }
+            uint4* o = reinterpret_cast<uint4*>(p.out + out_off + c * 32);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) o[i] = pk[i];
+            if (write_even) {
+              uint4* oe = reinterpret_cast<uint4*>(p.out_even + even_off + c * 32);
+#pragma unroll
+              for (int i = 0; i < 4; ++i) oe[i] = pk[i];
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[acc]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
+                 "r"((uint32_t)C::TMEM_COLS)
+                 : "memory");
+  }
+}
+
+}  // namespace tc
