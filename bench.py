@@ -1,0 +1,377 @@
+#!/usr/bin/env python
+"""Benchmark of the face-pipeline hot path (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...  # reference-equivalent CPU path
+
+A "step" is one pass of det + align + embed over one batch of synthetic frames per GPU:
+64 frames of 640x640 BGR u8, 8 faces per frame -> 512 aligned faces per GPU per step
+(BASELINE.json configs[3], the configuration the metric "aligned faces/sec end-to-end" is
+quoted on; it fits one GPU).  Frames are independent, so N GPUs run N data-parallel replicas
+of the step with no data-path collective ("scaling": "weak").
+
+value : faces/s with the frames already resident in HBM (CUDA events, max over ranks).
+e2e   : the same metric through the public C-ABI call with HOST (pinned) buffers; the H2D
+        copy of the frames and the D2H read of faces + embeddings are inside the timed region.
+roofline : the dominant kernel family (tcgen05 shift-GEMM = all IResNet-50 convs + FC),
+        algorithmic FLOPs / CUDA-event time, against MEASURED_PEAKS.json.
+cpu_baseline : the oracle (torch-CPU fp32 + cv2 stand-in for ORT-CPU + OpenCV, 4 intra-op
+        threads, batch 1 per call like the reference) on a bounded sample, rank 0, N=1 only.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+FRAMES_PER_STEP = 64
+FACES_PER_FRAME = 8
+FRAME = 640
+SEED = 1
+METRIC = "aligned faces/sec end-to-end (det+align+embed)"
+UNIT = "faces/s"
+# algorithmic work per face (SURVEY 8d / BASELINE.md section 3)
+GFLOP_PER_FACE_TOTAL = 12.6187      # IResNet-50 conv + FC MACs x 2
+GFLOP_PER_FACE_STEM = 2 * 21.6760e-3  # 3->64 3x3 @112^2, runs on the CUDA cores
+TC_LAUNCHES_PER_STEP = 49           # 48 convs (the 4 shortcut 1x1 are fused as taps) + FC
+
+
+def _env_int(name, default):
+    try:
+        return int(os.environ.get(name, default))
+    except ValueError:
+        return default
+
+
+def synth_pad_faces(rng, n_img, k, size=FRAME):
+    """Seeded synthetic landmark sets (template x random similarity), SURVEY 8d config 4."""
+    from facerecognizeonnx_b200 import capi
+    tmpl = np.array([[38.2946, 51.6963], [73.5318, 51.5014], [56.0252, 71.7366],
+                     [41.5493, 92.3655], [70.7299, 92.2041]], np.float32)
+    f = np.zeros((n_img, k), capi.FACE_DTYPE)
+    for i in range(n_img):
+        for j in range(k):
+            s = rng.uniform(0.5, 4.0)
+            th = rng.uniform(-0.6, 0.6)
+            A = np.array([[s * np.cos(th), -s * np.sin(th)], [s * np.sin(th), s * np.cos(th)]])
+            t = np.array([rng.uniform(0, size * 0.5), rng.uniform(0, size * 0.5)])
+            pts = (tmpl @ A.T + t + rng.normal(0, 0.5 * s, (5, 2))).astype(np.float32)
+            x0, y0 = pts.min(0)
+            x1, y1 = pts.max(0)
+            f[i, j]["x"], f[i, j]["y"] = int(x0), int(y0)
+            f[i, j]["w"], f[i, j]["h"] = int(x1 - x0) + 1, int(y1 - y0) + 1
+            f[i, j]["score"] = 0.9
+            f[i, j]["lm"] = pts.reshape(10)
+    return f
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.idx = gpu_index
+        self.lines = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.idx)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for ln in self.proc.stdout:
+            self.lines.append((time.time(), ln.strip()))
+
+    def stop(self, t0, t1):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for t, ln in self.lines:
+            p = [x.strip() for x in ln.split(",")]
+            if len(p) < 8:
+                continue
+            try:
+                c, m = float(p[1]), float(p[2])
+            except ValueError:
+                continue
+            mx.append(m)
+            if t0 - 0.05 <= t <= t1 + 0.05:
+                sm.append(c)
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), p[4:8]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        if not sm:  # region shorter than the sampling period: use the closest samples
+            sm = [float(ln.split(",")[1]) for _, ln in self.lines[-3:] if len(ln.split(",")) > 2]
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {"hbm_gbs": d["hbm_gbs"], "tflops_burst": d["bf16_tflops"],
+                "tflops_sustained": d.get("bf16_tflops_sustained", d["bf16_tflops"]), "source": "measured"}
+    return {"hbm_gbs": 6650.0, "tflops_burst": 1590.0, "tflops_sustained": 1400.0, "source": "fallback"}
+
+
+# --------------------------------------------------------------------------- CPU arm
+class CpuPipeline:
+    """Oracle det + align + embed, batch 1 per call like the reference (built once)."""
+
+    def __init__(self, threads: int, seed: int = SEED):
+        import cv2
+        import torch
+
+        from facerecognizeonnx_b200 import capi   # host-only weight generator (no GPU work)
+        from oracle import detector as odet
+        from oracle import recognizer as orec
+        torch.set_num_threads(threads)
+        cv2.setNumThreads(threads)
+        self.odet = odet
+        self.det = odet.FaceDetector(capi.Weights(capi.FR_MODEL_DET, None, seed).to_dict())
+        self.rec = orec.FaceRecognizer(capi.Weights(capi.FR_MODEL_REC, None, seed).to_dict())
+        # untimed warm-up of both graphs
+        self.det.detect(np.zeros((FRAME, FRAME, 3), np.uint8))
+        self.rec.embed_chw(np.zeros((1, 3, 112, 112), np.float32))
+
+    def run(self, n_frames: int, seed: int):
+        """Returns (faces embedded, seconds) for n_frames fresh synthetic frames."""
+        rng = np.random.default_rng(seed)
+        frames = [rng.integers(0, 256, (FRAME, FRAME, 3), dtype=np.uint8) for _ in range(n_frames)]
+        pad = synth_pad_faces(np.random.default_rng(seed + 1), n_frames, FACES_PER_FRAME)
+        faces_done = 0
+        t0 = time.perf_counter()
+        for i, fr in enumerate(frames):
+            dets = self.det.detect(fr, 0.5, 0.4)
+            sel = dets[:FACES_PER_FRAME]
+            for j in range(FACES_PER_FRAME):
+                if j < len(sel):
+                    fb = sel[j]
+                else:
+                    r = pad[i, j]
+                    fb = self.odet.FaceBox(int(r["x"]), int(r["y"]), int(r["w"]), int(r["h"]), 0.9,
+                                           np.array(r["lm"], np.float32).reshape(5, 2))
+                emb = self.rec.extract_feature(fr, fb)
+                faces_done += int(emb.size == 512)
+        return faces_done, time.perf_counter() - t0
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference-equivalent CPU path with all host threads.  The real
+    reference (ONNX Runtime CPU EP + OpenCV C++) cannot be built or installed in this image
+    (no ORT, no OpenCV headers, no .onnx files), so the oracle port is what runs."""
+    if rank != 0:
+        return
+    cores = len(os.sched_getaffinity(0))
+    pipe = CpuPipeline(cores)
+    frames_per_step = 1
+    faces, secs = 0, 0.0
+    for s in range(args.warmup + args.steps):
+        f, t = pipe.run(frames_per_step, 100 + s)
+        if s >= args.warmup:
+            faces += f
+            secs += t
+    value = faces / secs if secs > 0 else 0.0
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * secs / max(args.steps, 1),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic",
+            "config": {"workload": "det+align+embed, 8 faces/frame, 640x640 frames "
+                                   "(bounded sample: 1 frame + 8 faces per step)",
+                       "frames_per_step": frames_per_step, "faces_per_frame": FACES_PER_FRAME},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                             "sample": f"{args.steps} steps x (1 frame det + 8 faces align+embed); torch-CPU fp32 + cv2 "
+                                       "stand-in for ORT-CPU + OpenCV, batch 1 per call, all host threads"},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------- GPU arm
+def run_gpu(args, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+
+    from facerecognizeonnx_b200 import capi
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    det_w = capi.Weights(capi.FR_MODEL_DET, None, SEED)
+    rec_w = capi.Weights(capi.FR_MODEL_REC, None, SEED)
+    ctx = capi.Context(local_rank, det_w, rec_w)
+    stream = torch.cuda.current_stream()
+    ctx.set_stream(stream.cuda_stream)
+
+    n_img, K = FRAMES_PER_STEP, FACES_PER_FRAME
+    n_faces = n_img * K
+    n_rot = 4  # rotating input batches: 4 x 78.6 MB = 315 MB > 126 MB L2
+    g = torch.Generator(device="cpu").manual_seed(100 + rank)
+    host_frames = [torch.randint(0, 256, (n_img, FRAME, FRAME, 3), dtype=torch.uint8, generator=g).pin_memory()
+                   for _ in range(n_rot)]
+    dev_frames = [h.to(dev) for h in host_frames]
+    pad_np = synth_pad_faces(np.random.default_rng(200 + rank), n_img, K)
+    pad_host = torch.from_numpy(pad_np.view(np.uint8).reshape(n_faces, 60).copy()).pin_memory()
+    pad_dev = pad_host.to(dev)
+    out_faces = torch.empty((n_faces, 60), dtype=torch.uint8, device=dev)
+    out_ndet = torch.empty(n_img, dtype=torch.int32, device=dev)
+    out_emb = torch.empty((n_faces, 512), dtype=torch.float32, device=dev)
+    out_valid = torch.empty(n_faces, dtype=torch.int32, device=dev)
+    frame_bytes = FRAME * FRAME * 3
+
+    def step_dev(i):
+        base = dev_frames[i % n_rot].data_ptr()
+        ctx.pipeline_dev([base + j * frame_bytes for j in range(n_img)], FRAME, FRAME, FRAME * 3, K,
+                         pad_dev.data_ptr(), out_faces.data_ptr(), out_ndet.data_ptr(), out_emb.data_ptr(),
+                         out_valid.data_ptr())
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+
+    # ---- device-resident throughput
+    for i in range(max(args.warmup, 3)):
+        step_dev(i)
+    barrier()
+    ctx.enable_stage_timing(True)
+    ctx.stage_times(reset=True)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    time.sleep(0.25)
+    l0 = ctx.launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_wall0 = time.time()
+    ev0.record(stream)
+    for i in range(args.steps):
+        step_dev(i)
+    ev1.record(stream)
+    torch.cuda.synchronize()
+    t_wall1 = time.time()
+    ms = ev0.elapsed_time(ev1)
+    launches = ctx.launch_count() - l0
+    stage_ms = ctx.stage_times(reset=True)
+    ctx.enable_stage_timing(False)
+    clocks = sampler.stop(t_wall0, t_wall1)
+    if world > 1:
+        dist.barrier()
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    n_det_mean = float(out_ndet.float().mean().item())
+    valid_frac = float(out_valid.float().mean().item())
+    value = world * n_faces * args.steps / (ms / 1e3)
+
+    # ---- end to end through the public API with host (pinned) buffers
+    host_np = [h.numpy() for h in host_frames]
+    pad_view = pad_host.numpy().view(capi.FACE_DTYPE).reshape(n_img, K)
+
+    def step_host(i):
+        fr = host_np[i % n_rot]
+        return ctx.pipeline([fr[j] for j in range(n_img)], K, pad_view)
+
+    for i in range(3):
+        step_host(i)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        res = step_host(i)
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    e2e_value = world * n_faces * args.steps / e2e_s
+    h2d = n_img * frame_bytes + n_faces * 60
+    d2h = n_faces * 512 * 4 + n_faces * 60 + n_faces * 4 + n_img * 4
+
+    # ---- roofline of the dominant kernel family (tcgen05 shift-GEMM)
+    peaks = load_peaks()
+    trunk_s = stage_ms["trunk"] / 1e3
+    tc_flop = n_faces * args.steps * (GFLOP_PER_FACE_TOTAL - GFLOP_PER_FACE_STEM) * 1e9
+    achieved = tc_flop / trunk_s / 1e12 if trunk_s > 0 else 0.0
+    roofline = {"bound": "tensor", "kernel": "tc::shift_gemm_kernel<64|128|256> (IResNet-50 convs + FC)",
+                "achieved": achieved, "peak": peaks["tflops_sustained"], "unit": "TFLOP/s",
+                "frac": achieved / peaks["tflops_sustained"], "peak_source": peaks["source"] + " (sustained bf16)",
+                "traffic": None, "launches_per_step": TC_LAUNCHES_PER_STEP,
+                "avg_launch_ms": stage_ms["trunk"] / (args.steps * TC_LAUNCHES_PER_STEP),
+                "share_of_step": stage_ms["trunk"] / ms if ms > 0 else None}
+    k1_bytes = n_img * args.steps * (FRAME * FRAME * 3 + FRAME * FRAME * 3 * 2)
+    k5_bytes = n_faces * args.steps * (37632 + 37632)
+    stages = {k: v / args.steps for k, v in stage_ms.items()}
+    extra = {"stage_ms_per_step": stages,
+             "k1_preprocess_gbs": k1_bytes / (stage_ms["preprocess"] / 1e3) / 1e9 if stage_ms["preprocess"] > 0 else None,
+             "k5_align_gbs_lower_bound": k5_bytes / (stage_ms["align"] / 1e3) / 1e9 if stage_ms["align"] > 0 else None,
+             "hbm_peak_gbs": peaks["hbm_gbs"], "n_det_per_frame": n_det_mean, "valid_frac": valid_frac}
+
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        frames_sample = 3
+        f, t = CpuPipeline(4).run(frames_sample, 100)
+        cpu_baseline = {"value": f / t, "unit": UNIT, "cores": 4, "kind": "port",
+                        "host_cores_available": len(os.sched_getaffinity(0)),
+                        "sample": f"{frames_sample} frames x (det + 8 faces align+embed) = {f} faces in {t:.1f} s; "
+                                  "oracle = torch-CPU fp32 + cv2 stand-in for ORT-CPU (4 intra-op threads, batch 1) + OpenCV"}
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+                "config": {"workload": "det+align+embed: 64 frames 640x640 per GPU per step, 8 faces/frame "
+                                       "(top post-NMS detections, padded with seeded synthetic landmark sets), "
+                                       "SCRFD det_500m fp32 + IResNet-50 bf16/fp32-accum, random-init weights seed 1",
+                           "frames_per_gpu_per_step": n_img, "faces_per_frame": K,
+                           "l2": "inputs rotate over 4 batches (315 MB > 126 MB L2); activations > 4 GB",
+                           "parallelism": f"dp{world} (independent frame batches, no data-path collective)"},
+                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                        "ms_per_step": 1e3 * e2e_s / args.steps},
+                "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
+                "cpu_baseline": cpu_baseline, "detail": extra}
+        print(json.dumps(line), flush=True)
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = _env_int("RANK", 0)
+    world = _env_int("WORLD_SIZE", 1)
+    local_rank = _env_int("LOCAL_RANK", 0)
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    run_gpu(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

@@ -34,6 +34,7 @@ SYMBOLS = [
     "fr_weights_num_tensors", "fr_weights_tensor_info", "fr_weights_tensor_get",
     "fr_weights_tensor_set", "fr_weights_last_error",
     "fr_create", "fr_destroy", "fr_last_error", "fr_set_stream", "fr_synchronize", "fr_launch_count",
+    "fr_enable_stage_timing", "fr_stage_times",
     "fr_detect", "fr_detect_batch",
     "fr_embed", "fr_embed_faces_batch", "fr_embed_simple", "fr_embed_aligned_batch",
     "fr_compare", "fr_compare_batch", "fr_pipeline_batch",
@@ -87,6 +88,8 @@ def _declare(L: C.CDLL) -> None:
     L.fr_synchronize.argtypes = [vp]
     L.fr_launch_count.argtypes = [vp]
     L.fr_launch_count.restype = u64
+    L.fr_enable_stage_timing.argtypes = [vp, i32]
+    L.fr_stage_times.argtypes = [vp, vp, i32]
     L.fr_detect.argtypes = [vp, vp, i32, i32, sz, f32, f32, vp, i32, C.POINTER(i32)]
     L.fr_detect_batch.argtypes = [vp, vp, vp, vp, vp, i32, i32, f32, f32, vp, i32, vp]
     L.fr_embed.argtypes = [vp, vp, i32, i32, sz, vp, vp]
@@ -241,6 +244,16 @@ class Context:
 
     def launch_count(self) -> int:
         return int(lib().fr_launch_count(self.h))
+
+    STAGES = ("preprocess", "scrfd", "decode_nms", "align", "stem", "trunk", "l2norm", "gallery")
+
+    def enable_stage_timing(self, on: bool = True):
+        self._check(lib().fr_enable_stage_timing(self.h, int(on)))
+
+    def stage_times(self, reset: bool = True) -> dict:
+        ms = (C.c_double * 8)()
+        self._check(lib().fr_stage_times(self.h, ms, int(reset)))
+        return {k: float(ms[i]) for i, k in enumerate(self.STAGES)}
 
     # -- detection
     def detect_batch(self, images: Sequence[np.ndarray], score_thr=0.5, nms_thr=0.4, cap=256):

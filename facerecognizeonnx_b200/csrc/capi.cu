@@ -41,6 +41,19 @@ void* fr_ctx::pin(size_t bytes) {
   return pinned;
 }
 
+void fr_ctx::stage_begin(int stage) {
+  if (!timing) return;
+  cudaEvent_t a, b;
+  cudaEventCreate(&a);
+  cudaEventCreate(&b);
+  cudaEventRecord(a, stream);
+  timing_events.push_back({stage, {a, b}});
+}
+void fr_ctx::stage_end() {
+  if (!timing || timing_events.empty()) return;
+  cudaEventRecord(timing_events.back().second.second, stream);
+}
+
 namespace {
 
 enum {  // indices into ctx->misc
@@ -109,23 +122,30 @@ int prepare_images(fr_ctx* ctx, const uint8_t* const* bgr, const int* rows, cons
       h[i].ptr = dst;
     }
   }
-  if (!ctx->img_desc.reserve(sizeof(ImgDesc) * n_img)) return fr_fail(ctx, FR_ERR_CUDA, "desc allocation failed");
-  // descriptors go through pinned memory so the copy is stream-ordered and the host vector
-  // can die at scope exit
-  // can die at scope exit.  Identical descriptors (a steady-state loop over the same device
-  // buffers) are not re-uploaded, so the device-resident path never synchronises the host.
-  const bool same = ctx->last_desc.size() == h.size() && ctx->last_desc_ptr == ctx->img_desc.p &&
-                    memcmp(ctx->last_desc.data(), h.data(), sizeof(ImgDesc) * n_img) == 0;
-  if (!same) {
+  // Descriptor sets live in a small device-side cache keyed by content, so a steady-state
+  // loop over a few fixed batches never re-uploads and never synchronises the host.
+  fr_ctx::DescSlot* slot = nullptr;
+  for (auto& sl : ctx->desc_cache)
+    if (sl.h.size() == h.size() && memcmp(sl.h.data(), h.data(), sizeof(ImgDesc) * n_img) == 0) slot = &sl;
+  if (!slot) {
+    if (ctx->desc_cache.size() < 16) {
+      ctx->desc_cache.emplace_back();
+      slot = &ctx->desc_cache.back();
+    } else {
+      slot = &ctx->desc_cache[0];
+      for (auto& sl : ctx->desc_cache)
+        if (sl.stamp < slot->stamp) slot = &sl;
+    }
+    FR_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));  // slot and pinned block may be in use
+    if (!slot->d.reserve(sizeof(ImgDesc) * n_img)) return fr_fail(ctx, FR_ERR_CUDA, "desc allocation failed");
     ImgDesc* pin = reinterpret_cast<ImgDesc*>(ctx->pin(sizeof(ImgDesc) * n_img));
     if (!pin) return fr_fail(ctx, FR_ERR_CUDA, "pinned allocation failed");
-    FR_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));  // previous use of the pinned block
     memcpy(pin, h.data(), sizeof(ImgDesc) * n_img);
-    FR_CUDA_OK(ctx, cudaMemcpyAsync(ctx->img_desc.p, pin, sizeof(ImgDesc) * n_img, cudaMemcpyHostToDevice, ctx->stream));
-    ctx->last_desc = h;
-    ctx->last_desc_ptr = ctx->img_desc.p;
+    FR_CUDA_OK(ctx, cudaMemcpyAsync(slot->d.p, pin, sizeof(ImgDesc) * n_img, cudaMemcpyHostToDevice, ctx->stream));
+    slot->h = h;
   }
-  *d_desc_out = ctx->img_desc.as<ImgDesc>();
+  slot->stamp = ++ctx->desc_stamp;
+  *d_desc_out = slot->d.as<ImgDesc>();
   if (h_desc_out) *h_desc_out = h;
   return FR_OK;
 }
@@ -144,10 +164,17 @@ int run_detect(fr_ctx* ctx, const ImgDesc* d_desc, int n_img, float score_thr, f
   const size_t in_elems = (size_t)n_img * 3 * FR_DET_SIZE * FR_DET_SIZE;
   if (!ctx->misc[B_DET_IN].reserve(in_elems * 2)) return fr_fail(ctx, FR_ERR_CUDA, "det input allocation failed");
   __nv_bfloat16* d_in = ctx->misc[B_DET_IN].as<__nv_bfloat16>();
+  ctx->stage_begin(FR_STAGE_PREPROCESS);
   FR_CHECK(k_det_preprocess(ctx, d_desc, n_img, d_in));
+  ctx->stage_end();
   HeadPtrs heads;
+  ctx->stage_begin(FR_STAGE_SCRFD);
   FR_CHECK(det_forward(ctx, d_in, n_img, &heads));
-  return k_scrfd_decode_nms(ctx, ctx->nms, heads, n_img, d_desc, nullptr, score_thr, nms_thr, d_out, cap, d_n_out);
+  ctx->stage_end();
+  ctx->stage_begin(FR_STAGE_DECODE_NMS);
+  const int s = k_scrfd_decode_nms(ctx, ctx->nms, heads, n_img, d_desc, nullptr, score_thr, nms_thr, d_out, cap, d_n_out);
+  ctx->stage_end();
+  return s;
 }
 
 // align + embed for n_faces faces already on the device.
@@ -159,8 +186,10 @@ int run_embed(fr_ctx* ctx, const ImgDesc* d_desc, const fr_face* d_faces, const 
     return fr_fail(ctx, FR_ERR_CUDA, "embed scratch allocation failed");
   AlignRec* d_rec = ctx->misc[B_ALIGN].as<AlignRec>();
   uint8_t* d_crops = ctx->misc[B_CROPS].as<uint8_t>();
+  ctx->stage_begin(FR_STAGE_ALIGN);
   FR_CHECK(k_align_estimate(ctx, d_faces, d_face_img, n_faces, d_desc, d_rec));
   FR_CHECK(k_align_warp(ctx, d_rec, n_faces, d_desc, d_crops, d_valid));
+  ctx->stage_end();
   return rec_forward_crops(ctx, d_crops, n_faces, ctx->misc[B_EMB_RAW].as<float>(), d_emb, d_valid);
 }
 
@@ -208,6 +237,7 @@ void fr_destroy(fr_ctx* ctx) {
   rec_model_destroy(ctx);
   ctx->img_stage.release();
   ctx->img_desc.release();
+  for (auto& sl : ctx->desc_cache) sl.d.release();
   ctx->faces_dev.release();
   for (auto& b : ctx->misc) b.release();
   ctx->nms.keys.release();
@@ -236,6 +266,30 @@ int fr_synchronize(fr_ctx* ctx) {
 }
 
 uint64_t fr_launch_count(const fr_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int fr_enable_stage_timing(fr_ctx* ctx, int on) {
+  if (!ctx) return FR_ERR_INVALID_ARG;
+  Guard g(ctx);
+  ctx->timing = on != 0;
+  return FR_OK;
+}
+
+int fr_stage_times(fr_ctx* ctx, double ms[FR_NUM_STAGES], int reset) {
+  if (!ctx || !ms) return FR_ERR_INVALID_ARG;
+  Guard g(ctx);
+  FR_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+  for (auto& e : ctx->timing_events) {
+    float t = 0.f;
+    if (cudaEventElapsedTime(&t, e.second.first, e.second.second) == cudaSuccess) ctx->stage_ms[e.first] += t;
+    cudaEventDestroy(e.second.first);
+    cudaEventDestroy(e.second.second);
+  }
+  ctx->timing_events.clear();
+  for (int i = 0; i < FR_NUM_STAGES; ++i) ms[i] = ctx->stage_ms[i];
+  if (reset)
+    for (int i = 0; i < FR_NUM_STAGES; ++i) ctx->stage_ms[i] = 0;
+  return FR_OK;
+}
 
 // ------------------------------------------------------------------ detection
 int fr_detect_batch(fr_ctx* ctx, const uint8_t* const* bgr, const int* rows, const int* cols,

@@ -83,8 +83,17 @@ struct fr_ctx {
   DevBuf faces_dev;     // fr_face scratch
   DevBuf misc[12];
   NmsScratch nms;
-  std::vector<ImgDesc> last_desc;   // last uploaded descriptors (upload elision)
-  void* last_desc_ptr = nullptr;
+  // device-side cache of descriptor sets: a steady-state loop over a few fixed batches never
+  // re-uploads (and so never synchronises the host)
+  struct DescSlot { std::vector<ImgDesc> h; DevBuf d; uint64_t stamp = 0; };
+  std::vector<DescSlot> desc_cache;
+  uint64_t desc_stamp = 0;
+  // optional per-stage CUDA-event timing (fr_enable_stage_timing / fr_stage_times)
+  bool timing = false;
+  std::vector<std::pair<int, std::pair<cudaEvent_t, cudaEvent_t>>> timing_events;
+  double stage_ms[FR_NUM_STAGES] = {0};
+  void stage_begin(int stage);
+  void stage_end();
   void* pinned = nullptr;
   size_t pinned_cap = 0;
   void* pin(size_t bytes);

@@ -625,7 +625,7 @@ static int rec_run_trunk(fr_ctx* ctx, int n, float* d_out_raw) {
 }
 
 static int rec_plan_cap(int n) {
-  int cap = 64;
+  int cap = 128;
   while (cap < n) cap *= 2;
   return cap;
 }
@@ -637,13 +637,21 @@ int rec_forward_crops(fr_ctx* ctx, const uint8_t* d_crops, int n, float* d_out_r
   if (n <= 0) return FR_OK;
   FR_CHECK(rec_build_plan(ctx, rec_plan_cap(n)));
   const long long threads = (long long)n * REC * (REC / 2);
+  ctx->stage_begin(FR_STAGE_STEM);
   stem_kernel<true><<<(unsigned)((threads + 127) / 128), 128, 0, ctx->stream>>>(
       d_crops, n, m->stem_w, m->stem_b, m->stem_prelu, m->x0.p, m->x0e.p);
+  ctx->stage_end();
   ctx->launches++;
   FR_CUDA_OK(ctx, cudaGetLastError());
   float* raw = d_out_raw ? d_out_raw : m->fc_out;
+  ctx->stage_begin(FR_STAGE_TRUNK);
   FR_CHECK(rec_run_trunk(ctx, n, raw));
-  if (d_out_norm) FR_CHECK(k_l2_normalize(ctx, raw, n, 512, d_out_norm, d_valid));
+  ctx->stage_end();
+  if (d_out_norm) {
+    ctx->stage_begin(FR_STAGE_L2NORM);
+    FR_CHECK(k_l2_normalize(ctx, raw, n, 512, d_out_norm, d_valid));
+    ctx->stage_end();
+  }
   return FR_OK;
 }
 

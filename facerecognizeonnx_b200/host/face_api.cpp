@@ -1,0 +1,208 @@
+// FaceDetector / FaceRecognizer: the reference's C++ classes (src/face_detector.{h,cpp},
+// src/face_recognizer.{h,cpp}) re-created on top of the C ABI (include/fr_capi.h).  Same
+// public signatures, same guards, same messages on std::cerr, same return conventions
+// (false / empty vector / 0.0f); the arithmetic all happens in libfr_b200.so on the GPU.
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <iostream>
+
+#include "../../include/face_recognizer.h"
+#include "../../include/fr_capi.h"
+
+static_assert(sizeof(FaceBox) == sizeof(fr_face), "FaceBox must be layout-identical to fr_face");
+
+namespace {
+
+int env_int(const char* name, int dflt) {
+  const char* v = std::getenv(name);
+  return v ? std::atoi(v) : dflt;
+}
+bool verbose() { return env_int("FR_VERBOSE", 0) != 0; }
+bool file_exists(const std::string& p) { return std::ifstream(p, std::ios::binary).good(); }
+
+struct Session {
+  fr_weights* w = nullptr;
+  fr_ctx* ctx = nullptr;
+  ~Session() {
+    if (ctx) fr_destroy(ctx);
+    if (w) fr_weights_destroy(w);
+  }
+};
+
+// loadModel (src/face_detector.cpp:20-90): file present -> parse it (failure => false, like the
+// Ort::Exception branch); file absent -> seeded random-init weights of the same architecture
+// (BASELINE.json north_star) with a notice on cerr, returns true.
+bool load(Session& s, int model, const std::string& path, const char* what) {
+  s.~Session();
+  new (&s) Session();
+  const bool have = file_exists(path);
+  int st = fr_weights_create(&s.w, model, have ? path.c_str() : nullptr, (uint64_t)env_int("FR_SEED", 1));
+  if (st != FR_OK) {
+    std::cerr << "Error loading " << what << " model: " << fr_weights_last_error() << std::endl;
+    return false;
+  }
+  if (!have)
+    std::cerr << "Note: " << path << " not found; using seeded random-init " << what
+              << " weights of the same architecture" << std::endl;
+  st = fr_create(&s.ctx, env_int("FR_DEVICE", 0), model == FR_MODEL_DET ? s.w : nullptr,
+                 model == FR_MODEL_REC ? s.w : nullptr);
+  if (st != FR_OK) {
+    std::cerr << "Error loading " << what << " model: CUDA context creation failed (" << st << ")" << std::endl;
+    s.ctx = nullptr;
+    return false;
+  }
+  return true;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------ FaceDetector
+struct FaceDetector::Impl {
+  Session s;
+  int inputWidth = FR_DET_SIZE, inputHeight = FR_DET_SIZE;
+};
+
+FaceDetector::FaceDetector() : impl_(new Impl()) {}
+FaceDetector::~FaceDetector() {}
+
+bool FaceDetector::loadModel(const std::string& modelPath) {
+  if (!load(impl_->s, FR_MODEL_DET, modelPath, "face detector")) return false;
+  std::cout << "Face detector model loaded successfully!" << std::endl;
+  std::cout << "Using input size: " << impl_->inputWidth << "x" << impl_->inputHeight << std::endl;
+  return true;
+}
+
+std::vector<std::vector<FaceBox>> FaceDetector::detectBatch(const std::vector<cv::Mat>& images,
+                                                            float scoreThreshold, float nmsThreshold) {
+  std::vector<std::vector<FaceBox>> out(images.size());
+  if (!impl_->s.ctx) {
+    std::cerr << "Model not loaded!" << std::endl;
+    return out;
+  }
+  const int n = (int)images.size();
+  if (n == 0) return out;
+  std::vector<const uint8_t*> ptr(n);
+  std::vector<int> rows(n), cols(n);
+  std::vector<size_t> step(n);
+  for (int i = 0; i < n; ++i) {
+    if (images[i].empty()) {
+      std::cerr << "Input image is empty!" << std::endl;
+      return out;
+    }
+    ptr[i] = images[i].data;
+    rows[i] = images[i].rows;
+    cols[i] = images[i].cols;
+    step[i] = (size_t)images[i].step;
+  }
+  const int cap = 1024;
+  std::vector<fr_face> faces((size_t)n * cap);
+  std::vector<int> cnt(n, 0);
+  const int st = fr_detect_batch(impl_->s.ctx, ptr.data(), rows.data(), cols.data(), step.data(), n, FR_MEM_HOST,
+                                 scoreThreshold, nmsThreshold, faces.data(), cap, cnt.data());
+  if (st != FR_OK) {
+    std::cerr << "Error during inference: " << fr_last_error(impl_->s.ctx) << std::endl;
+    return out;
+  }
+  for (int i = 0; i < n; ++i) {
+    out[i].resize(cnt[i]);
+    if (cnt[i]) std::memcpy(out[i].data(), faces.data() + (size_t)i * cap, sizeof(fr_face) * cnt[i]);
+    if (verbose()) std::cout << "Found " << cnt[i] << " faces after NMS" << std::endl;
+  }
+  return out;
+}
+
+std::vector<FaceBox> FaceDetector::detect(const cv::Mat& image, float scoreThreshold, float nmsThreshold) {
+  std::vector<FaceBox> faces;
+  if (!impl_->s.ctx) {
+    std::cerr << "Model not loaded!" << std::endl;
+    return faces;
+  }
+  if (image.empty()) {
+    std::cerr << "Input image is empty!" << std::endl;
+    return faces;
+  }
+  if (image.cols <= 0 || image.rows <= 0) {
+    std::cerr << "Invalid image dimensions: " << image.cols << "x" << image.rows << std::endl;
+    return faces;
+  }
+  return detectBatch(std::vector<cv::Mat>{image}, scoreThreshold, nmsThreshold)[0];
+}
+
+// ---------------------------------------------------------------- FaceRecognizer
+struct FaceRecognizer::Impl {
+  Session s;
+  int inputWidth = FR_REC_SIZE, inputHeight = FR_REC_SIZE, featureDim = FR_FEAT_DIM;
+};
+
+FaceRecognizer::FaceRecognizer() : impl_(new Impl()) {}
+FaceRecognizer::~FaceRecognizer() {}
+
+bool FaceRecognizer::loadModel(const std::string& modelPath) {
+  if (!load(impl_->s, FR_MODEL_REC, modelPath, "face recognizer")) return false;
+  std::cout << "Face recognizer model loaded successfully!" << std::endl;
+  std::cout << "Using input size: " << impl_->inputWidth << "x" << impl_->inputHeight << std::endl;
+  return true;
+}
+
+std::vector<std::vector<float>> FaceRecognizer::extractFeatures(const cv::Mat& image,
+                                                                const std::vector<FaceBox>& faces) {
+  std::vector<std::vector<float>> out(faces.size());
+  if (!impl_->s.ctx) {
+    std::cerr << "Model not loaded!" << std::endl;
+    return out;
+  }
+  if (image.empty()) {
+    std::cerr << "Input image is empty!" << std::endl;
+    return out;
+  }
+  const int n = (int)faces.size();
+  if (n == 0) return out;
+  const uint8_t* ptr[1] = {image.data};
+  const int rows = image.rows, cols = image.cols;
+  const size_t step = (size_t)image.step;
+  std::vector<int> fimg(n, 0), valid(n, 0);
+  std::vector<float> emb((size_t)n * FR_FEAT_DIM);
+  const int st = fr_embed_faces_batch(impl_->s.ctx, ptr, &rows, &cols, &step, 1, FR_MEM_HOST,
+                                      reinterpret_cast<const fr_face*>(faces.data()), fimg.data(), n, emb.data(),
+                                      valid.data());
+  if (st != FR_OK) {
+    std::cerr << "Error during feature extraction: " << fr_last_error(impl_->s.ctx) << std::endl;
+    return out;
+  }
+  for (int i = 0; i < n; ++i) {
+    if (!valid[i]) {
+      std::cerr << "Face alignment failed!" << std::endl;
+      continue;
+    }
+    out[i].assign(emb.begin() + (size_t)i * FR_FEAT_DIM, emb.begin() + (size_t)(i + 1) * FR_FEAT_DIM);
+  }
+  return out;
+}
+
+std::vector<float> FaceRecognizer::extractFeature(const cv::Mat& image, const FaceBox& face) {
+  return extractFeatures(image, std::vector<FaceBox>{face})[0];
+}
+
+std::vector<float> FaceRecognizer::extractFeatureSimple(const cv::Mat& image) {
+  std::vector<float> feature;
+  if (!impl_->s.ctx) {
+    std::cerr << "Model not loaded!" << std::endl;
+    return feature;
+  }
+  if (image.empty()) {
+    std::cerr << "Input image is empty!" << std::endl;
+    return feature;
+  }
+  feature.resize(FR_FEAT_DIM);
+  const int st = fr_embed_simple(impl_->s.ctx, image.data, image.rows, image.cols, (size_t)image.step, feature.data());
+  if (st != FR_OK) {
+    std::cerr << "Error during feature extraction: " << fr_last_error(impl_->s.ctx) << std::endl;
+    feature.clear();
+  }
+  return feature;
+}
+
+float FaceRecognizer::compareFaces(const std::vector<float>& feature1, const std::vector<float>& feature2) {
+  return fr_compare(feature1.data(), (int)feature1.size(), feature2.data(), (int)feature2.size());
+}

@@ -157,6 +157,24 @@ FR_API int fr_gallery_search(fr_gallery* g, const float* queries, int nq, int k,
 FR_API int fr_topk_merge(fr_ctx* ctx, const float* scores, const int64_t* idx, int parts, int nq,
                          int k, int memspace, float* out_scores, int64_t* out_idx);
 
+/* -------------------------------------------------------- instrumentation --
+ * CUDA-event timing of each stage on the ctx stream (what bench.py's roofline block uses).
+ * fr_stage_times synchronises, adds the elapsed ms of every recorded interval to ms[stage]
+ * (accumulating since the last reset) and clears the interval list. */
+enum {
+  FR_STAGE_PREPROCESS = 0, /* K1 */
+  FR_STAGE_SCRFD = 1,      /* K2 */
+  FR_STAGE_DECODE_NMS = 2, /* K3+K4 */
+  FR_STAGE_ALIGN = 3,      /* K5 */
+  FR_STAGE_STEM = 4,       /* K6 stem (SIMT) */
+  FR_STAGE_TRUNK = 5,      /* K6/K7 tcgen05 shift-GEMM launches */
+  FR_STAGE_L2NORM = 6,     /* R4 */
+  FR_STAGE_GALLERY = 7,    /* K9 */
+  FR_NUM_STAGES = 8
+};
+FR_API int fr_enable_stage_timing(fr_ctx* ctx, int on);
+FR_API int fr_stage_times(fr_ctx* ctx, double ms[FR_NUM_STAGES], int reset);
+
 /* ------------------------------------------------------ stage-level hooks --
  * Each stage of the hot path, callable alone, for the parity tests. */
 /* K1: FaceDetector::preprocess (src/face_detector.cpp:92-137). out_chw fp32 [n,3,640,640]. */

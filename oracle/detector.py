@@ -126,20 +126,32 @@ def iou(a: FaceBox, b: FaceBox) -> float:
 def nms(boxes: List[FaceBox], threshold: float) -> List[FaceBox]:
     """FaceDetector::nms, src/face_detector.cpp:356-384.  std::sort is
     unstable; the canonical tie order is score desc, then
-    candidate (anchor) index asc."""
+    candidate (anchor) index asc.  The inner j-loop is vectorised with numpy
+    int32 / float32 arrays (same arithmetic as ``iou`` element-wise)."""
     order = sorted(range(len(boxes)), key=lambda i: (-float(boxes[i].score), boxes[i].anchor, i))
     bs = [boxes[i] for i in order]
+    n = len(bs)
+    if n == 0:
+        return []
     thr = np.float32(threshold)
-    suppressed = [False] * len(bs)
-    for i in range(len(bs)):
-        if suppressed[i]:
-            continue
-        for j in range(i + 1, len(bs)):
-            if suppressed[j]:
+    X = np.array([b.x for b in bs], np.int32)
+    Y = np.array([b.y for b in bs], np.int32)
+    W = np.array([b.w for b in bs], np.int32)
+    H = np.array([b.h for b in bs], np.int32)
+    with np.errstate(all="ignore"):
+        X2, Y2, A = X + W, Y + H, W * H
+        suppressed = np.zeros(n, bool)
+        for i in range(n):
+            if suppressed[i]:
                 continue
-            if iou(bs[i], bs[j]) > thr:  # strict, :370
-                suppressed[j] = True
-    return [b for b, s in zip(bs, suppressed) if not s]
+            j = slice(i + 1, n)
+            w = np.maximum(np.int32(0), np.minimum(X2[i], X2[j]) - np.maximum(X[i], X[j]))
+            h = np.maximum(np.int32(0), np.minimum(Y2[i], Y2[j]) - np.maximum(Y[i], Y[j]))
+            inter = (w * h).astype(np.int32)
+            den = (A[i] + A[j] - inter).astype(np.int32)
+            v = inter.astype(np.float32) / den.astype(np.float32)
+            suppressed[j] |= v > thr  # strict, :370; NaN (0/0) compares false
+    return [b for b, s_ in zip(bs, suppressed) if not s_]
 
 
 def postprocess(out15: np.ndarray, scale, score_thr: float = 0.5, nms_thr: float = 0.4) -> List[FaceBox]:

@@ -1,0 +1,103 @@
+"""End-to-end GPU parity: detect / extractFeature / fused pipeline / API mirror vs the oracle."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import SEED, faces_from_landmarks, synth_landmarks
+from oracle import detector as odet
+from oracle import recognizer as orec
+
+pytestmark = pytest.mark.gpu
+
+
+def _frames(rng, n, h=640, w=640):
+    return [rng.integers(0, 256, (h, w, 3), dtype=np.uint8) for _ in range(n)]
+
+
+def _match_dets(got, exp, thr):
+    """Kept detections must agree except for candidates whose score is within 1e-4 of the
+    threshold (fp32 summation order differs between the CUDA cores and oneDNN)."""
+    e = {(f.x, f.y, f.w, f.h): f for f in exp}
+    g = {(int(r["x"]), int(r["y"]), int(r["w"]), int(r["h"])): r for r in got}
+    common = set(e) & set(g)
+    assert len(common) >= 0.9 * max(len(e), 1), (len(common), len(e), len(g))
+    for k in common:
+        assert abs(float(g[k]["score"]) - float(e[k].score)) < 1e-4
+        assert np.abs(np.array(g[k]["lm"]) - e[k].landmarks.reshape(10)).max() < 1e-3
+
+
+def test_detect_end_to_end_vs_oracle(ctx, det_wdict):
+    rng = np.random.default_rng(41)
+    det = odet.FaceDetector(det_wdict)
+    for im in _frames(rng, 2) + _frames(rng, 1, 480, 640):
+        got = ctx.detect(im, 0.5, 0.4, cap=1024)
+        exp = det.detect(im, 0.5, 0.4)
+        _match_dets(got, exp, 0.5)
+        sc = got["score"]
+        assert np.all(sc[:-1] >= sc[1:])   # sorted by score, descending (nms() output order)
+
+
+def test_detect_batch_equals_single(ctx):
+    rng = np.random.default_rng(42)
+    ims = _frames(rng, 3) + _frames(rng, 1, 360, 640)
+    batch = ctx.detect_batch(ims, 0.5, 0.4, cap=512)
+    for im, b in zip(ims, batch):
+        assert np.array_equal(ctx.detect(im, 0.5, 0.4, cap=512), b)
+
+
+def test_extract_feature_end_to_end_vs_oracle(ctx, capi, rec_wdict):
+    import cv2
+    rng = np.random.default_rng(43)
+    img = cv2.GaussianBlur(rng.integers(0, 256, (480, 640, 3), dtype=np.uint8), (0, 0), 1.2)
+    lms = synth_landmarks(rng, 6, 640, 480)
+    faces = faces_from_landmarks(capi, lms)
+    emb, valid = ctx.embed_faces([img], faces, [0] * 6)
+    assert valid.all()
+    rec = orec.FaceRecognizer(rec_wdict)
+    for i in range(6):
+        fb = odet.FaceBox(int(faces[i]["x"]), int(faces[i]["y"]), int(faces[i]["w"]), int(faces[i]["h"]), 0.9, lms[i])
+        ref = rec.extract_feature(img, fb)
+        assert float((emb[i] * ref).sum()) >= 0.999
+
+
+def test_pipeline_matches_staged_calls(ctx, capi):
+    rng = np.random.default_rng(44)
+    ims = _frames(rng, 4)
+    K = 8
+    pad = faces_from_landmarks(capi, synth_landmarks(rng, 4 * K, 640, 640)).reshape(4, K)
+    faces, n_det, emb, valid = ctx.pipeline(ims, K, pad)
+    dets = ctx.detect_batch(ims, 0.5, 0.4, cap=64)
+    for i in range(4):
+        assert n_det[i] == len(dets[i])
+        sel = np.concatenate([dets[i][:K], pad[i][min(len(dets[i]), K):]])
+        assert np.array_equal(faces[i], sel)
+        e2, v2 = ctx.embed_faces([ims[i]], sel, [0] * K)
+        assert np.array_equal(v2, valid[i])
+        assert np.allclose(emb[i], e2, atol=1e-6)
+    assert valid.all()
+
+
+def test_api_mirror_compare_mode(capi, tmp_path):
+    """compare-mode flow of src/main.cpp:67-123 through the reference-named classes."""
+    from facerecognizeonnx_b200 import api
+    api._Shared.seed = SEED
+    det, rec = api.FaceDetector(), api.FaceRecognizer()
+    assert det.detect(np.zeros((10, 10, 3), np.uint8)) == []          # "Model not loaded!"
+    assert det.loadModel(str(tmp_path / "det_500m.onnx"))               # absent -> random init, True
+    assert rec.loadModel(str(tmp_path / "w600k_r50.onnx"))
+    assert det.detect(np.zeros((0, 0, 3), np.uint8)) == []             # "Input image is empty!"
+    rng = np.random.default_rng(45)
+    im = rng.integers(0, 256, (640, 640, 3), dtype=np.uint8)
+    faces = det.detect(im)
+    assert all(isinstance(f, api.FaceBox) for f in faces)
+    lm = synth_landmarks(rng, 2, 640, 640)
+    f1 = api.FaceBox((10, 10, 100, 100), 0.9, lm[0])
+    f2 = api.FaceBox((10, 10, 100, 100), 0.9, lm[1])
+    e1, e2 = rec.extractFeature(im, f1), rec.extractFeature(im, f2)
+    assert e1.shape == (512,) and abs(float(np.linalg.norm(e1)) - 1) < 1e-5
+    s = rec.compareFaces(e1, e2)
+    assert 0.0 <= s <= 1.0 and rec.compareFaces(e1, e1) > 0.999
+    assert rec.compareFaces(e1, e2[:100]) == 0.0                       # size mismatch -> 0.0f
+    bad = api.FaceBox((900, 900, 5, 5), 0.9, np.zeros((5, 2), np.float32))
+    assert rec.extractFeature(im, bad).size == 0                       # alignment failed -> empty
+    assert rec.extractFeatureSimple(im).shape == (512,)
