@@ -222,7 +222,12 @@ def run_gpu(args, rank, world, local_rank):
     det_w = capi.Weights(capi.FR_MODEL_DET, None, SEED)
     rec_w = capi.Weights(capi.FR_MODEL_REC, None, SEED)
     ctx = capi.Context(local_rank, det_w, rec_w)
-    stream = torch.cuda.current_stream()
+    # a dedicated non-default stream: the library launches on it and the CUDA events that
+    # time the region are recorded on it (the legacy default stream has handle 0, which
+    # fr_set_stream treats as "use the ctx-owned stream")
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
+    assert stream.cuda_stream != 0
     ctx.set_stream(stream.cuda_stream)
 
     n_img, K = FRAMES_PER_STEP, FACES_PER_FRAME

@@ -428,3 +428,65 @@ def compare(a: np.ndarray, b: np.ndarray) -> float:
     a = np.ascontiguousarray(a, np.float32).reshape(-1)
     b = np.ascontiguousarray(b, np.float32).reshape(-1)
     return float(lib().fr_compare(a.ctypes.data, a.size, b.ctypes.data, b.size))
+
+
+# ---------------------------------------------------------------- gallery --
+class Gallery:
+    """1:N gallery shard on one GPU (fr_gallery_*).  index_base is the global index of local
+    row 0, so search results carry global indices."""
+
+    def __init__(self, ctx: Context, capacity_rows: int, index_base: int = 0):
+        h = C.c_void_p()
+        ctx._check(lib().fr_gallery_create(ctx.h, C.byref(h), capacity_rows, index_base))
+        self.h, self.ctx, self.index_base = h, ctx, index_base
+
+    def close(self):
+        if getattr(self, "h", None):
+            lib().fr_gallery_destroy(self.h)
+            self.h = None
+
+    __del__ = close
+
+    def __len__(self):
+        return int(lib().fr_gallery_size(self.h))
+
+    def add(self, rows: np.ndarray):
+        rows = np.ascontiguousarray(rows, np.float32)
+        assert rows.ndim == 2 and rows.shape[1] == FEAT_DIM
+        self.ctx._check(lib().fr_gallery_add(self.h, rows.ctypes.data, rows.shape[0], FR_MEM_HOST))
+
+    def fill_synthetic(self, n: int, seed: int):
+        self.ctx._check(lib().fr_gallery_fill_synthetic(self.h, n, seed))
+
+    def get_rows(self, first: int, n: int) -> np.ndarray:
+        out = np.zeros((n, FEAT_DIM), np.float32)
+        self.ctx._check(lib().fr_gallery_get_rows(self.h, first, n, out.ctypes.data))
+        return out
+
+    def search(self, queries: np.ndarray, k: int = 10):
+        q = np.ascontiguousarray(queries, np.float32)
+        nq = q.shape[0]
+        s = np.zeros((nq, k), np.float32)
+        i = np.zeros((nq, k), np.int64)
+        self.ctx._check(lib().fr_gallery_search(self.h, q.ctypes.data, nq, k, FR_MEM_HOST, s.ctypes.data, i.ctypes.data))
+        return s, i
+
+    def search_dev(self, q_ptr: int, nq: int, k: int, out_s_ptr: int, out_i_ptr: int):
+        self.ctx._check(lib().fr_gallery_search(self.h, q_ptr, nq, k, FR_MEM_DEVICE, out_s_ptr, out_i_ptr))
+
+
+def topk_merge(ctx: Context, scores: np.ndarray, idx: np.ndarray, k: int):
+    """scores/idx: [parts, nq, k] host arrays -> merged [nq, k]."""
+    s = np.ascontiguousarray(scores, np.float32)
+    i = np.ascontiguousarray(idx, np.int64)
+    parts, nq, kk = s.shape
+    assert kk == k
+    os_ = np.zeros((nq, k), np.float32)
+    oi = np.zeros((nq, k), np.int64)
+    ctx._check(lib().fr_topk_merge(ctx.h, s.ctypes.data, i.ctypes.data, parts, nq, k, FR_MEM_HOST,
+                                   os_.ctypes.data, oi.ctypes.data))
+    return os_, oi
+
+
+def topk_merge_dev(ctx: Context, s_ptr: int, i_ptr: int, parts: int, nq: int, k: int, os_ptr: int, oi_ptr: int):
+    ctx._check(lib().fr_topk_merge(ctx.h, s_ptr, i_ptr, parts, nq, k, FR_MEM_DEVICE, os_ptr, oi_ptr))

@@ -1,26 +1,469 @@
-// K9: 1:N cosine search (north_star extension; the reference only has 1:1 compareFaces,
-// src/face_recognizer.cpp:320-334).
+// K9: 1:N cosine search with fused top-k (north_star extension; the reference only has the
+// 1:1 FaceRecognizer::compareFaces, src/face_recognizer.cpp:320-334, whose batched
+// generalisation this is: S = Q . G^T on L2-normalised rows, top-k per query, ties -> lower
+// index; mapped score (S+1)/2 and the 0.6 rule are applied by the caller).
+//
+// One tcgen05 kernel does GEMM and selection; the 4096 x N score matrix never exists:
+//   * a CTA owns one tile of 128 queries (A operand: 128 x 512 bf16 = 128 KB, loaded once by
+//     TMA and kept resident in shared memory) and sweeps a contiguous range of gallery tiles
+//   * gallery tiles (256 rows x 64 K-columns, SWIZZLE_128B) stream through a 3-stage TMA ring
+//   * tcgen05.mma M=128 N=256 K=16, fp32 accumulators double-buffered in TMEM (2 x 256 cols)
+//   * epilogue warps read the accumulator with tcgen05.ld; each thread owns one query row and
+//     keeps its running top-k in registers across all tiles of the sweep
+// Partial lists of the splits (and, multi-GPU, of the ranks after the NCCL all-gather) are
+// merged by topk_merge_kernel with the (score desc, global index asc) order, so the result
+// does not depend on the number of splits or ranks.
+#include <cmath>
+#include <cstring>
+
 #include "common.h"
+#include "tc_gemm.cuh"
+
+bool tc_make_map_2d(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols,
+                    uint64_t pitch_elems, uint32_t box_rows);
+
+namespace {
+
+typedef __nv_bfloat16 bf16;
+constexpr int DIM = FR_FEAT_DIM;        // 512
+constexpr int KB = DIM / tc::BK;        // 8 K blocks
+constexpr int GN = 256;                 // gallery rows per tile
+constexpr int TOPK = 16;                // list capacity (k <= 16)
+constexpr int G_STAGES = 3;
+constexpr int G_B_BYTES = GN * tc::BK * 2;             // 32 KB
+constexpr int G_A_BYTES = KB * tc::A_TILE_BYTES;       // 128 KB
+constexpr int G_SMEM = G_A_BYTES + G_STAGES * G_B_BYTES + 256 + 1024;
+
+struct GParams {
+  int n_rows;           // gallery rows in this shard
+  int nq;               // valid queries
+  int num_m_tiles;
+  int n_tiles;          // ceil(n_rows / GN)
+  int tiles_per_split;
+  int nq_pad;
+  float* out_s;         // [splits][nq_pad][TOPK]
+  int* out_i;           // [splits][nq_pad][TOPK]
+  int* err_flag;
+};
+
+__global__ void __launch_bounds__(tc::NUM_THREADS, 1)
+gallery_topk_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmG,
+                    const __grid_constant__ GParams p) {
+  using namespace tc;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + G_A_BYTES;
+  uint64_t* full = reinterpret_cast<uint64_t*>(sB + G_STAGES * G_B_BYTES);
+  uint64_t* empty = full + G_STAGES;
+  uint64_t* tfull = empty + G_STAGES;
+  uint64_t* tempty = tfull + 2;
+  uint64_t* afull = tempty + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(afull + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m_tile = blockIdx.x % p.num_m_tiles;
+  const int split = blockIdx.x / p.num_m_tiles;
+  const int t_begin = split * p.tiles_per_split;
+  const int t_end = min(t_begin + p.tiles_per_split, p.n_tiles);
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < G_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 4); }
+    mbar_init(afull, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    prefetch_tmap(&tmQ);
+    prefetch_tmap(&tmG);
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"(512u)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_expect_tx(afull, G_A_BYTES);
+      for (int kb = 0; kb < KB; ++kb) tma_load_2d(sA + kb * A_TILE_BYTES, &tmQ, afull, kb * BK, m_tile * BM);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = t_begin; t < t_end; ++t)
+        for (int kb = 0; kb < KB; ++kb) {
+          mbar_wait(&empty[stage], phase ^ 1u, p.err_flag);
+          mbar_expect_tx(&full[stage], G_B_BYTES);
+          tma_load_2d(sB + stage * G_B_BYTES, &tmG, &full[stage], kb * BK, t * GN);
+          if (++stage == G_STAGES) { stage = 0; phase ^= 1u; }
+        }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(BM, GN);
+      mbar_wait(afull, 0, p.err_flag);
+      tc_fence_after();
+      int stage = 0;
+      uint32_t phase = 0, it = 0;
+      for (int t = t_begin; t < t_end; ++t, ++it) {
+        const uint32_t acc = it & 1u, acc_phase = (it >> 1) & 1u;
+        mbar_wait(&tempty[acc], acc_phase ^ 1u, p.err_flag);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * GN;
+        for (int kb = 0; kb < KB; ++kb) {
+          mbar_wait(&full[stage], phase, p.err_flag);
+          tc_fence_after();
+          const uint64_t adesc = make_smem_desc(sA + kb * A_TILE_BYTES);
+          const uint64_t bdesc = make_smem_desc(sB + stage * G_B_BYTES);
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k)
+            mma_bf16(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | k) ? 1u : 0u);
+          tc_commit(&empty[stage]);
+          if (++stage == G_STAGES) { stage = 0; phase ^= 1u; }
+        }
+        tc_commit(&tfull[acc]);
+      }
+    }
+  } else {
+    const int q = warp & 3;
+    const int row = m_tile * BM + q * 32 + lane;
+    float ts[TOPK];
+    int ti[TOPK];
+#pragma unroll
+    for (int j = 0; j < TOPK; ++j) { ts[j] = -INFINITY; ti[j] = -1; }
+    uint32_t it = 0;
+    for (int t = t_begin; t < t_end; ++t, ++it) {
+      const uint32_t acc = it & 1u, acc_phase = (it >> 1) & 1u;
+      mbar_wait(&tfull[acc], acc_phase, p.err_flag);
+      tc_fence_after();
+      const uint32_t taddr0 = tmem_base + acc * GN + ((uint32_t)(q * 32) << 16);
+      const int col0 = t * GN;
+#pragma unroll 1
+      for (int c = 0; c < GN / 32; ++c) {
+        uint32_t v[32];
+        tmem_ld32(taddr0 + c * 32, v);
+        const int cb = col0 + c * 32;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const float s = __uint_as_float(v[i]);
+          if (s > ts[TOPK - 1] && cb + i < p.n_rows) {
+            float cs = s;
+            int ci = cb + i;
+            bool ins = false;   // once inserted, everything below shifts down by one
+#pragma unroll
+            for (int j = 0; j < TOPK; ++j)
+              if (ins || cs > ts[j]) {   // increasing-index sweep: strict '>' keeps ties stable
+                const float fs = ts[j]; ts[j] = cs; cs = fs;
+                const int fi = ti[j]; ti[j] = ci; ci = fi;
+                ins = true;
+              }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[acc]);
+    }
+    if (row < p.nq) {
+      float* os = p.out_s + ((size_t)split * p.nq_pad + row) * TOPK;
+      int* oi = p.out_i + ((size_t)split * p.nq_pad + row) * TOPK;
+#pragma unroll
+      for (int j = 0; j < TOPK; ++j) { os[j] = ts[j]; oi[j] = ti[j]; }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  }
+}
+
+// Merge `parts` sorted lists of `kin` candidates per query into the top `kout`
+// (score desc, global index asc).  idx32 (local, + base) or idx64 (already global) input.
+__global__ void topk_merge_kernel(const float* __restrict__ s_in, const int* __restrict__ i32_in,
+                                  const long long* __restrict__ i64_in, int parts, int nq, int part_stride,
+                                  int kin, int kout, long long base, float* __restrict__ s_out,
+                                  long long* __restrict__ i_out) {
+  const int qi = blockIdx.x * blockDim.x + threadIdx.x;
+  if (qi >= nq) return;
+  float ts[TOPK];
+  long long ti[TOPK];
+#pragma unroll
+  for (int j = 0; j < TOPK; ++j) { ts[j] = -INFINITY; ti[j] = -1; }
+  for (int pt = 0; pt < parts; ++pt)
+    for (int c = 0; c < kin; ++c) {
+      const size_t o = ((size_t)pt * part_stride + qi) * kin + c;
+      float cs = s_in[o];
+      long long ci;
+      if (i64_in) ci = i64_in[o];
+      else { const int l = i32_in[o]; ci = l < 0 ? -1 : base + l; }
+      if (ci < 0) continue;
+      bool ins = false;
+#pragma unroll
+      for (int j = 0; j < TOPK; ++j) {
+        const bool better = ins || ti[j] < 0 || cs > ts[j] || (cs == ts[j] && ci < ti[j]);
+        if (better) {
+          const float fs = ts[j]; ts[j] = cs; cs = fs;
+          const long long fi = ti[j]; ti[j] = ci; ci = fi;
+          ins = true;
+        }
+      }
+    }
+  for (int j = 0; j < kout; ++j) {
+    s_out[(size_t)qi * kout + j] = ts[j];
+    i_out[(size_t)qi * kout + j] = ti[j];
+  }
+}
+
+__global__ void rows_to_bf16_kernel(const float* __restrict__ in, bf16* __restrict__ out, size_t n) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) out[i] = __float2bfloat16_rn(in[i]);
+}
+
+__device__ __forceinline__ uint64_t mix64(uint64_t x) {
+  x += 0x9E3779B97F4A7C15ull;
+  x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+  x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+  return x ^ (x >> 31);
+}
+
+// One warp per row: 512 hashed values in (-1,1), L2-normalised, stored bf16.
+__global__ void fill_synthetic_kernel(bf16* __restrict__ g, long long first, long long n, uint64_t seed,
+                                      long long global_base) {
+  const long long r = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (r >= n) return;
+  const uint64_t rowkey = mix64(seed ^ (uint64_t)(global_base + first + r) * 0xD1B54A32D192ED03ull);
+  float v[DIM / 32];
+  float ss = 0.f;
+#pragma unroll
+  for (int j = 0; j < DIM / 32; ++j) {
+    const uint64_t h = mix64(rowkey + (uint64_t)(j * 32 + lane));
+    v[j] = (float)(h >> 40) * (2.0f / 16777216.0f) - 1.0f;
+    ss = fmaf(v[j], v[j], ss);
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, off);
+  const float inv = rsqrtf(ss);
+#pragma unroll
+  for (int j = 0; j < DIM / 32; ++j) g[(size_t)(first + r) * DIM + j * 32 + lane] = __float2bfloat16_rn(v[j] * inv);
+}
+
+__global__ void bf16_rows_to_f32_kernel(const bf16* __restrict__ in, float* __restrict__ out, size_t n) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) out[i] = __bfloat162float(in[i]);
+}
+
+}  // namespace
 
 struct fr_gallery {
   fr_ctx* ctx = nullptr;
+  bf16* rows = nullptr;
+  int64_t cap = 0, size = 0, base = 0;
+  DevBuf q_bf16, q_f32, part_s, part_i, out_s, out_i;
+  int* err_flag = nullptr;
 };
 
+namespace {
+struct GGuard {
+  fr_ctx* c;
+  explicit GGuard(fr_ctx* ctx) : c(ctx) { c->mu.lock(); cudaSetDevice(c->device); }
+  ~GGuard() { c->mu.unlock(); }
+};
+}  // namespace
+
 extern "C" {
+
 int fr_gallery_create(fr_ctx* ctx, fr_gallery** out, int64_t capacity_rows, int64_t index_base) {
-  (void)out; (void)capacity_rows; (void)index_base;
-  return fr_fail(ctx, FR_ERR_UNSUPPORTED, "gallery not built yet");
+  if (!ctx || !out || capacity_rows <= 0) return fr_fail(ctx, FR_ERR_INVALID_ARG, "bad gallery arguments");
+  GGuard g(ctx);
+  std::unique_ptr<fr_gallery> G(new fr_gallery());
+  G->ctx = ctx;
+  G->cap = capacity_rows;
+  G->base = index_base;
+  // round the allocation up to a whole tile so TMA boxes never leave the allocation
+  const size_t alloc_rows = ((size_t)capacity_rows + GN - 1) / GN * GN;
+  if (cudaMalloc(&G->rows, alloc_rows * DIM * 2) != cudaSuccess || cudaMalloc(&G->err_flag, 4) != cudaSuccess)
+    return fr_fail(ctx, FR_ERR_CUDA, "gallery allocation failed");
+  cudaMemsetAsync(G->rows, 0, alloc_rows * DIM * 2, ctx->stream);
+  cudaMemsetAsync(G->err_flag, 0, 4, ctx->stream);
+  *out = G.release();
+  return FR_OK;
 }
-void fr_gallery_destroy(fr_gallery* g) { delete g; }
-int fr_gallery_add(fr_gallery* g, const float* rows, int64_t n, int memspace) { (void)g; (void)rows; (void)n; (void)memspace; return FR_ERR_UNSUPPORTED; }
-int fr_gallery_fill_synthetic(fr_gallery* g, int64_t n, uint64_t seed) { (void)g; (void)n; (void)seed; return FR_ERR_UNSUPPORTED; }
-int fr_gallery_get_rows(fr_gallery* g, int64_t first, int64_t n, float* out_host) { (void)g; (void)first; (void)n; (void)out_host; return FR_ERR_UNSUPPORTED; }
-int64_t fr_gallery_size(const fr_gallery* g) { (void)g; return 0; }
-int fr_gallery_search(fr_gallery* g, const float* queries, int nq, int k, int memspace, float* out_scores, int64_t* out_idx) {
-  (void)g; (void)queries; (void)nq; (void)k; (void)memspace; (void)out_scores; (void)out_idx; return FR_ERR_UNSUPPORTED;
+
+void fr_gallery_destroy(fr_gallery* g) {
+  if (!g) return;
+  {
+    GGuard gg(g->ctx);
+    cudaStreamSynchronize(g->ctx->stream);
+    cudaFree(g->rows);
+    cudaFree(g->err_flag);
+    g->q_bf16.release(); g->q_f32.release(); g->part_s.release(); g->part_i.release();
+    g->out_s.release(); g->out_i.release();
+  }
+  delete g;
 }
-int fr_topk_merge(fr_ctx* ctx, const float* scores, const int64_t* idx, int parts, int nq, int k, int memspace, float* out_scores, int64_t* out_idx) {
-  (void)scores; (void)idx; (void)parts; (void)nq; (void)k; (void)memspace; (void)out_scores; (void)out_idx;
-  return fr_fail(ctx, FR_ERR_UNSUPPORTED, "gallery not built yet");
+
+int64_t fr_gallery_size(const fr_gallery* g) { return g ? g->size : 0; }
+
+int fr_gallery_add(fr_gallery* g, const float* rows, int64_t n, int memspace) {
+  if (!g || !rows || n <= 0) return FR_ERR_INVALID_ARG;
+  fr_ctx* ctx = g->ctx;
+  GGuard gg(ctx);
+  if (g->size + n > g->cap) return fr_fail(ctx, FR_ERR_CAPACITY, "gallery full");
+  const size_t elems = (size_t)n * DIM;
+  const float* d_rows = rows;
+  if (memspace != FR_MEM_DEVICE) {
+    if (!g->q_f32.reserve(elems * 4)) return fr_fail(ctx, FR_ERR_CUDA, "gallery staging allocation failed");
+    FR_CUDA_OK(ctx, cudaMemcpyAsync(g->q_f32.p, rows, elems * 4, cudaMemcpyHostToDevice, ctx->stream));
+    d_rows = g->q_f32.as<float>();
+  }
+  rows_to_bf16_kernel<<<148 * 4, 256, 0, ctx->stream>>>(d_rows, g->rows + (size_t)g->size * DIM, elems);
+  ctx->launches++;
+  FR_CUDA_OK(ctx, cudaGetLastError());
+  if (memspace != FR_MEM_DEVICE) FR_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+  g->size += n;
+  return FR_OK;
 }
+
+int fr_gallery_fill_synthetic(fr_gallery* g, int64_t n, uint64_t seed) {
+  if (!g || n <= 0) return FR_ERR_INVALID_ARG;
+  fr_ctx* ctx = g->ctx;
+  GGuard gg(ctx);
+  if (g->size + n > g->cap) return fr_fail(ctx, FR_ERR_CAPACITY, "gallery full");
+  const unsigned blocks = (unsigned)((n + 7) / 8);
+  fill_synthetic_kernel<<<blocks, 256, 0, ctx->stream>>>(g->rows, g->size, n, seed, g->base);
+  ctx->launches++;
+  FR_CUDA_OK(ctx, cudaGetLastError());
+  g->size += n;
+  return FR_OK;
 }
+
+int fr_gallery_get_rows(fr_gallery* g, int64_t first, int64_t n, float* out_host) {
+  if (!g || !out_host || first < 0 || n <= 0 || first + n > g->size) return FR_ERR_INVALID_ARG;
+  fr_ctx* ctx = g->ctx;
+  GGuard gg(ctx);
+  const size_t elems = (size_t)n * DIM;
+  if (!g->q_f32.reserve(elems * 4)) return fr_fail(ctx, FR_ERR_CUDA, "gallery staging allocation failed");
+  bf16_rows_to_f32_kernel<<<148 * 4, 256, 0, ctx->stream>>>(g->rows + (size_t)first * DIM, g->q_f32.as<float>(), elems);
+  ctx->launches++;
+  FR_CUDA_OK(ctx, cudaMemcpyAsync(out_host, g->q_f32.p, elems * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  FR_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+  return FR_OK;
+}
+
+int fr_gallery_search(fr_gallery* g, const float* queries, int nq, int k, int memspace, float* out_scores,
+                      int64_t* out_idx) {
+  if (!g || !queries || !out_scores || !out_idx || nq <= 0 || k <= 0 || k > TOPK) return FR_ERR_INVALID_ARG;
+  fr_ctx* ctx = g->ctx;
+  GGuard gg(ctx);
+  static bool attr = false;
+  static int num_sms = 148;
+  if (!attr) {
+    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, ctx->device);
+    FR_CUDA_OK(ctx, cudaFuncSetAttribute(gallery_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, G_SMEM));
+    attr = true;
+  }
+  const int num_m_tiles = ceil_div(nq, tc::BM);
+  const int nq_pad = num_m_tiles * tc::BM;
+  const int n_tiles = (int)((g->size + GN - 1) / GN);
+  int splits = std::max(1, num_sms / num_m_tiles);
+  if (n_tiles > 0) splits = std::min(splits, n_tiles); else splits = 1;
+  const int tps = n_tiles > 0 ? ceil_div(n_tiles, splits) : 0;
+  if (n_tiles > 0) splits = ceil_div(n_tiles, tps);
+  const size_t qelems = (size_t)nq_pad * DIM;
+  if (!g->q_bf16.reserve(qelems * 2) || !g->part_s.reserve((size_t)splits * nq_pad * TOPK * 4) ||
+      !g->part_i.reserve((size_t)splits * nq_pad * TOPK * 4))
+    return fr_fail(ctx, FR_ERR_CUDA, "search allocation failed");
+  const float* d_q = queries;
+  if (memspace != FR_MEM_DEVICE) {
+    if (!g->q_f32.reserve((size_t)nq * DIM * 4)) return fr_fail(ctx, FR_ERR_CUDA, "search allocation failed");
+    FR_CUDA_OK(ctx, cudaMemcpyAsync(g->q_f32.p, queries, (size_t)nq * DIM * 4, cudaMemcpyHostToDevice, ctx->stream));
+    d_q = g->q_f32.as<float>();
+  }
+  ctx->stage_begin(FR_STAGE_GALLERY);
+  if (nq_pad > nq)
+    FR_CUDA_OK(ctx, cudaMemsetAsync(g->q_bf16.as<bf16>() + (size_t)nq * DIM, 0, (size_t)(nq_pad - nq) * DIM * 2, ctx->stream));
+  rows_to_bf16_kernel<<<148 * 2, 256, 0, ctx->stream>>>(d_q, g->q_bf16.as<bf16>(), (size_t)nq * DIM);
+  ctx->launches++;
+  float* d_os = out_scores;
+  long long* d_oi = reinterpret_cast<long long*>(out_idx);
+  if (memspace != FR_MEM_DEVICE) {
+    if (!g->out_s.reserve((size_t)nq * k * 4) || !g->out_i.reserve((size_t)nq * k * 8))
+      return fr_fail(ctx, FR_ERR_CUDA, "search allocation failed");
+    d_os = g->out_s.as<float>();
+    d_oi = g->out_i.as<long long>();
+  }
+  if (n_tiles > 0) {
+    CUtensorMap tmQ, tmG;
+    const uint64_t g_rows = (uint64_t)((g->cap + GN - 1) / GN * GN);
+    if (!tc_make_map_2d(&tmQ, g->q_bf16.p, nq_pad, DIM, DIM, tc::BM) ||
+        !tc_make_map_2d(&tmG, g->rows, g_rows, DIM, DIM, GN))
+      return fr_fail(ctx, FR_ERR_CUDA, "gallery tensor map encode failed");
+    GParams p;
+    p.n_rows = (int)g->size;
+    p.nq = nq;
+    p.num_m_tiles = num_m_tiles;
+    p.n_tiles = n_tiles;
+    p.tiles_per_split = tps;
+    p.nq_pad = nq_pad;
+    p.out_s = g->part_s.as<float>();
+    p.out_i = g->part_i.as<int>();
+    p.err_flag = g->err_flag;
+    gallery_topk_kernel<<<num_m_tiles * splits, tc::NUM_THREADS, G_SMEM, ctx->stream>>>(tmQ, tmG, p);
+    ctx->launches++;
+    FR_CUDA_OK(ctx, cudaGetLastError());
+  }
+  topk_merge_kernel<<<ceil_div(nq, 128), 128, 0, ctx->stream>>>(
+      g->part_s.as<float>(), g->part_i.as<int>(), nullptr, n_tiles > 0 ? splits : 0, nq, nq_pad, TOPK, k,
+      (long long)g->base, d_os, d_oi);
+  ctx->launches++;
+  FR_CUDA_OK(ctx, cudaGetLastError());
+  ctx->stage_end();
+  if (memspace != FR_MEM_DEVICE) {
+    FR_CUDA_OK(ctx, cudaMemcpyAsync(out_scores, d_os, (size_t)nq * k * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    FR_CUDA_OK(ctx, cudaMemcpyAsync(out_idx, d_oi, (size_t)nq * k * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    FR_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+  }
+  return FR_OK;
+}
+
+int fr_topk_merge(fr_ctx* ctx, const float* scores, const int64_t* idx, int parts, int nq, int k, int memspace,
+                  float* out_scores, int64_t* out_idx) {
+  if (!ctx || !scores || !idx || !out_scores || !out_idx || parts <= 0 || nq <= 0 || k <= 0 || k > TOPK)
+    return fr_fail(ctx, FR_ERR_INVALID_ARG, "bad merge arguments");
+  GGuard gg(ctx);
+  const size_t n_in = (size_t)parts * nq * k;
+  const float* d_s = scores;
+  const long long* d_i = reinterpret_cast<const long long*>(idx);
+  float* d_os = out_scores;
+  long long* d_oi = reinterpret_cast<long long*>(out_idx);
+  if (memspace != FR_MEM_DEVICE) {
+    if (!ctx->misc[10].reserve(n_in * 4) || !ctx->misc[11].reserve(n_in * 8) ||
+        !ctx->misc[8].reserve((size_t)nq * k * 4) || !ctx->misc[9].reserve((size_t)nq * k * 8))
+      return fr_fail(ctx, FR_ERR_CUDA, "merge allocation failed");
+    FR_CUDA_OK(ctx, cudaMemcpyAsync(ctx->misc[10].p, scores, n_in * 4, cudaMemcpyHostToDevice, ctx->stream));
+    FR_CUDA_OK(ctx, cudaMemcpyAsync(ctx->misc[11].p, idx, n_in * 8, cudaMemcpyHostToDevice, ctx->stream));
+    d_s = ctx->misc[10].as<float>();
+    d_i = ctx->misc[11].as<long long>();
+    d_os = ctx->misc[8].as<float>();
+    d_oi = ctx->misc[9].as<long long>();
+  }
+  topk_merge_kernel<<<ceil_div(nq, 128), 128, 0, ctx->stream>>>(d_s, nullptr, d_i, parts, nq, nq, k, k, 0, d_os, d_oi);
+  ctx->launches++;
+  FR_CUDA_OK(ctx, cudaGetLastError());
+  if (memspace != FR_MEM_DEVICE) {
+    FR_CUDA_OK(ctx, cudaMemcpyAsync(out_scores, d_os, (size_t)nq * k * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    FR_CUDA_OK(ctx, cudaMemcpyAsync(out_idx, d_oi, (size_t)nq * k * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    FR_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+  }
+  return FR_OK;
+}
+
+}  // extern "C"
