@@ -59,15 +59,35 @@ bool tc_make_map_2d(CUtensorMap* map, const void* base, uint64_t rows, uint64_t 
 
 struct ConvLaunch {
   CUtensorMap a0, a1, b0, b1;
+  CUtensorMap a_halo;      // halo mode: box = (a_rows / a_boxes) x 64
   tc::Params p;
   int bn = 64;
   int rows_per_img = 1;  // Hp*Wp of the output geometry
+  bool halo = false;
 };
+
+static int env_flag(const char* name, int dflt) {
+  const char* v = getenv(name);
+  return v ? atoi(v) : dflt;
+}
+
+// Configure halo mode for a 3x3 stride-1 conv whose A operand is `base` ([rows, cin], pitch cin).
+static bool tc_setup_halo(ConvLaunch& L, const void* base, uint64_t rows, int cin, int Wp) {
+  if (!env_flag("FR_TC_HALO", 1)) return true;   // default on (FR_TC_HALO=0 selects the per-tap loader)
+  int a_rows = (tc::BM + 2 * Wp + 2 + 7) / 8 * 8;
+  int boxes = 1;
+  if (a_rows > 256) { boxes = 2; a_rows = (a_rows + 15) / 16 * 16; }
+  L.p.a_rows = a_rows;
+  L.p.a_boxes = boxes;
+  L.p.base_off_mode = env_flag("FR_TC_BASEOFF", 0);
+  L.halo = true;
+  return tc_make_map_2d(&L.a_halo, base, rows, cin, cin, a_rows / boxes);
+}
 
 int tc_launch(fr_ctx* ctx, ConvLaunch& L, int m_rows) {
   L.p.m_rows = m_rows;
   L.p.num_m_tiles = ceil_div(m_rows, tc::BM);
-  const int total = L.p.num_m_tiles * L.p.n_tiles_n;
+  const int total = L.p.num_m_tiles * L.p.n_tiles_n * (L.p.k_splits > 1 ? L.p.k_splits : 1);
   if (total <= 0) return FR_OK;
   static int num_sms = 0;
   static bool attrs = false;
@@ -82,9 +102,28 @@ int tc_launch(fr_ctx* ctx, ConvLaunch& L, int m_rows) {
     FR_CUDA_OK(ctx, cudaFuncSetAttribute(tc::shift_gemm_kernel<256>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          tc::Cfg<256>::SMEM_BYTES));
+    FR_CUDA_OK(ctx, cudaFuncSetAttribute(tc::halo_gemm_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    FR_CUDA_OK(ctx, cudaFuncSetAttribute(tc::halo_gemm_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    FR_CUDA_OK(ctx, cudaFuncSetAttribute(tc::halo_gemm_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     attrs = true;
   }
   const int grid = std::min(total, num_sms);
+  if (L.halo) {
+    switch (L.bn) {
+      case 64:
+        tc::halo_gemm_kernel<64><<<grid, tc::NUM_THREADS, tc::HaloCfg<64>::smem_bytes(L.p.a_rows), ctx->stream>>>(L.a_halo, L.b0, L.p);
+        break;
+      case 128:
+        tc::halo_gemm_kernel<128><<<grid, tc::NUM_THREADS, tc::HaloCfg<128>::smem_bytes(L.p.a_rows), ctx->stream>>>(L.a_halo, L.b0, L.p);
+        break;
+      default:
+        tc::halo_gemm_kernel<256><<<grid, tc::NUM_THREADS, tc::HaloCfg<256>::smem_bytes(L.p.a_rows), ctx->stream>>>(L.a_halo, L.b0, L.p);
+        break;
+    }
+    ctx->launches++;
+    FR_CUDA_OK(ctx, cudaGetLastError());
+    return FR_OK;
+  }
   switch (L.bn) {
     case 64:
       tc::shift_gemm_kernel<64><<<grid, tc::NUM_THREADS, tc::Cfg<64>::SMEM_BYTES, ctx->stream>>>(
@@ -148,6 +187,7 @@ struct RecModel {
   std::vector<ConvLaunch> conv1, conv2;
   ConvLaunch fc;
   float* fc_out = nullptr;   // [cap,512] raw
+  float* fc_part = nullptr;  // [FC_SPLITS][cap,512] split-K partial sums
   float* chw_stage = nullptr;
   size_t chw_stage_cap = 0;
 };
@@ -271,6 +311,19 @@ stem_kernel(const void* __restrict__ in_, int n, const float* __restrict__ w,
       reinterpret_cast<uint4*>(oe + cg)[1] = p0[1];
     }
   }
+}
+
+constexpr int FC_SPLITS = 16;
+
+// sum of the split-K partial products of the FC (bias was added by split 0)
+__global__ void fc_reduce_kernel(const float* __restrict__ part, size_t n_elems, size_t stride,
+                                 float* __restrict__ out) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_elems) return;
+  float s = 0.f;
+#pragma unroll
+  for (int k = 0; k < FC_SPLITS; ++k) s += part[(size_t)k * stride + i];
+  out[i] = s;
 }
 
 // R4: FaceRecognizer::normalize (src/face_recognizer.cpp:306-318): one warp per row.
@@ -541,6 +594,7 @@ static int rec_build_plan(fr_ctx* ctx, int cap) {
     }
     ok = ok && tc_make_map_2d(&c1.a0, x.p, x.rows(cap), x.C, x.C, tc::BM);
     c1.a1 = c1.a0;
+    ok = ok && tc_setup_halo(c1, x.p, x.rows(cap), x.C, x.Wp);
     ok = ok && tc_make_map_2d(&c1.b0, bw.w1, (uint64_t)9 * bw.planes, bw.cin, bw.cin, c1.bn);
     c1.b1 = c1.b0;
     // ---- conv2: 3x3 stride s (+ fused 1x1 shortcut conv) + residual -> out
@@ -572,6 +626,7 @@ static int rec_build_plan(fr_ctx* ctx, int cap) {
       c2.p.residual = x.p;
       ok = ok && tc_make_map_2d(&c2.a0, bb.h.p, bb.h.rows(cap), bb.h.C, bb.h.C, tc::BM);
       c2.a1 = c2.a0;
+      ok = ok && tc_setup_halo(c2, bb.h.p, bb.h.rows(cap), bb.h.C, bb.h.Wp);
     }
     ok = ok && tc_make_map_2d(&c2.b0, bw.w2, (uint64_t)9 * bw.planes, bw.planes, bw.planes, c2.bn);
     if (bw.stride != 2) c2.b1 = c2.b0;
@@ -583,6 +638,9 @@ static int rec_build_plan(fr_ctx* ctx, int cap) {
     void* p = nullptr;
     ok = cudaMalloc(&p, (size_t)cap * 512 * sizeof(float)) == cudaSuccess;
     if (ok) { m->fc_out = reinterpret_cast<float*>(p); m->plan_allocs.push_back(p); }
+    void* q = nullptr;
+    ok = ok && cudaMalloc(&q, (size_t)FC_SPLITS * cap * 512 * sizeof(float)) == cudaSuccess;
+    if (ok) { m->fc_part = reinterpret_cast<float*>(q); m->plan_allocs.push_back(q); }
   }
   if (ok) {
     ConvLaunch& f = m->fc;
@@ -595,7 +653,10 @@ static int rec_build_plan(fr_ctx* ctx, int cap) {
     f.p.cout = 512;
     f.p.bias = m->fc_b; f.p.bias_classes = 1;
     f.p.out_mode = tc::OUT_F32;
-    f.p.out_f32 = m->fc_out;
+    f.p.out_f32 = m->fc_part;
+    f.p.k_splits = FC_SPLITS;
+    f.p.k_split_len = (64 * 512 / 64) / FC_SPLITS;
+    f.p.split_stride = (long long)cap * 512;
     f.p.err_flag = m->err_flag;
     f.rows_per_img = 1;
     ok = ok && tc_make_map_2d(&f.a0, x.p, (uint64_t)cap, 64 * 512, 64 * 512, tc::BM);
@@ -618,9 +679,12 @@ static int rec_run_trunk(fr_ctx* ctx, int n, float* d_out_raw) {
     FR_CHECK(tc_launch(ctx, m->conv1[i], n * m->conv1[i].rows_per_img));
     FR_CHECK(tc_launch(ctx, m->conv2[i], n * m->conv2[i].rows_per_img));
   }
-  ConvLaunch f = m->fc;
-  f.p.out_f32 = d_out_raw ? d_out_raw : m->fc_out;
-  FR_CHECK(tc_launch(ctx, f, n));
+  FR_CHECK(tc_launch(ctx, m->fc, n));
+  float* raw = d_out_raw ? d_out_raw : m->fc_out;
+  const size_t elems = (size_t)n * 512;
+  fc_reduce_kernel<<<(unsigned)((elems + 255) / 256), 256, 0, ctx->stream>>>(m->fc_part, elems, (size_t)m->cap * 512, raw);
+  ctx->launches++;
+  FR_CUDA_OK(ctx, cudaGetLastError());
   return FR_OK;
 }
 
@@ -795,6 +859,7 @@ int rec_test_conv(fr_ctx* ctx, const float* x, int n, int cin, int h, int w, con
        tc_make_map_2d(&L.b0, d_w, (uint64_t)ksize * ksize * cout, cin, cin, L.bn);
   L.a1 = L.a0;
   L.b1 = L.b0;
+  if (ok && ksize == 3) ok = tc_setup_halo(L, d_x, rows, cin, Wp);
   int status = FR_OK;
   if (!ok) status = fr_fail(ctx, FR_ERR_CUDA, "fr_test_conv: tensor map encode failed");
   if (status == FR_OK) status = tc_launch(ctx, L, (int)rows);

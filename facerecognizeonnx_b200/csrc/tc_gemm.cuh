@@ -64,6 +64,15 @@ struct Params {
   __nv_bfloat16* out_even;
   float* out_f32;
   int* err_flag;
+  // split-K (FC): tile index -> (m, n, split); each split covers k_split_len K blocks and
+  // writes its partial sums to out_f32 + split * split_stride (bias only in split 0)
+  int k_splits;
+  int k_split_len;
+  long long split_stride;
+  // halo mode (halo_gemm_kernel): one A block of a_rows rows per K block serves all 9 taps
+  int a_rows;        // multiple of 8 (and of 16 when loaded as two boxes)
+  int a_boxes;       // 1 or 2 TMA boxes per A block
+  int base_off_mode; // 0: descriptor base_offset = 0; 1: base_offset = (addr >> 7) & 7
 };
 
 template <int BN> struct Cfg {
@@ -178,6 +187,111 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
   return *reinterpret_cast<uint32_t*>(&h);
 }
 
+// Epilogue of one output tile for one thread (= one accumulator row): TMEM -> registers ->
+// bias / PReLU / residual -> global.  All 32 lanes of the warp must call it (tcgen05.ld).
+template <int BN>
+__device__ __forceinline__ void epilogue_tile(const Params& p, uint32_t taddr0, int m, int n0, int split) {
+  bool valid = m < p.m_rows;
+  int img = 0, hp = 0, wp = 0;
+  if (valid && p.out_mode != OUT_F32) {
+    const int per_img = p.Hp * p.Wp;
+    img = m / per_img;
+    const int rem = m - img * per_img;
+    hp = rem / p.Wp;
+    wp = rem - hp * p.Wp;
+    valid = hp < p.H && wp < p.W;
+  }
+  int cls = 0;
+  if (p.bias_classes == 9)
+    cls = (hp == 0 ? 0 : (hp == p.H - 1 ? 2 : 1)) * 3 + (wp == 0 ? 0 : (wp == p.W - 1 ? 2 : 1));
+  const float* bias = p.bias + (size_t)cls * p.cout + n0;
+  const float bias_on = split == 0 ? 1.f : 0.f;
+  size_t out_off = 0, even_off = 0;
+  bool write_even = false;
+  if (p.out_mode == OUT_STD) {
+    out_off = (size_t)m * p.cout + n0;
+    if (p.out_even && valid && !(hp & 1) && !(wp & 1)) {
+      write_even = true;
+      even_off = ((size_t)(img * p.Hp2 + (hp >> 1)) * p.Wp2 + (wp >> 1)) * p.cout + n0;
+    }
+  } else if (p.out_mode == OUT_S2D) {
+    out_off = (((size_t)(img * p.Hp2 + (hp >> 1)) * p.Wp2 + (wp >> 1)) * 4 +
+               (size_t)((hp & 1) * 2 + (wp & 1))) * p.cout + n0;
+  } else {
+    out_off = (size_t)split * p.split_stride + (size_t)m * p.cout + n0;
+  }
+#pragma unroll 1
+  for (int c = 0; c < BN / 32; ++c) {
+    uint32_t v[32];
+    tmem_ld32(taddr0 + c * 32, v);
+    if (valid) {
+      float f[32];
+#pragma unroll
+      for (int i = 0; i < 32; i += 4) {
+        const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + c * 32 + i));
+        f[i] = __uint_as_float(v[i]) + b4.x * bias_on;
+        f[i + 1] = __uint_as_float(v[i + 1]) + b4.y * bias_on;
+        f[i + 2] = __uint_as_float(v[i + 2]) + b4.z * bias_on;
+        f[i + 3] = __uint_as_float(v[i + 3]) + b4.w * bias_on;
+      }
+      if (p.prelu) {
+#pragma unroll
+        for (int i = 0; i < 32; i += 4) {
+          const float4 s4 = __ldg(reinterpret_cast<const float4*>(p.prelu + n0 + c * 32 + i));
+          f[i] = f[i] > 0.f ? f[i] : f[i] * s4.x;
+          f[i + 1] = f[i + 1] > 0.f ? f[i + 1] : f[i + 1] * s4.y;
+          f[i + 2] = f[i + 2] > 0.f ? f[i + 2] : f[i + 2] * s4.z;
+          f[i + 3] = f[i + 3] > 0.f ? f[i + 3] : f[i + 3] * s4.w;
+        }
+      }
+      if (p.out_mode == OUT_F32) {
+        float4* o = reinterpret_cast<float4*>(p.out_f32 + out_off + c * 32);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) o[i] = make_float4(f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]);
+      } else {
+        if (p.residual) {
+          const uint4* r = reinterpret_cast<const uint4*>(p.residual + (size_t)m * p.cout + n0 + c * 32);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const uint4 rv = __ldg(r + i);
+            const uint32_t w[4] = {rv.x, rv.y, rv.z, rv.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              f[i * 8 + 2 * j] += __uint_as_float(w[j] << 16);
+              f[i * 8 + 2 * j + 1] += __uint_as_float(w[j] & 0xffff0000u);
+            }
+          }
+        }
+        uint4 pk[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          pk[i].x = pack_bf16(f[i * 8 + 0], f[i * 8 + 1]);
+          pk[i].y = pack_bf16(f[i * 8 + 2], f[i * 8 + 3]);
+          pk[i].z = pack_bf16(f[i * 8 + 4], f[i * 8 + 5]);
+          pk[i].w = pack_bf16(f[i * 8 + 6], f[i * 8 + 7]);
+        }
+        uint4* o = reinterpret_cast<uint4*>(p.out + out_off + c * 32);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) o[i] = pk[i];
+        if (write_even) {
+          uint4* oe = reinterpret_cast<uint4*>(p.out_even + even_off + c * 32);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) oe[i] = pk[i];
+        }
+      }
+    }
+  }
+}
+
+// tile index -> (m tile, n tile, K split)
+__device__ __forceinline__ void tile_coords(const Params& p, int tile, int& m_tile, int& n_tile, int& split) {
+  const int ks = p.k_splits > 1 ? p.k_splits : 1;
+  split = tile % ks;
+  const int t2 = tile / ks;
+  n_tile = t2 % p.n_tiles_n;
+  m_tile = t2 / p.n_tiles_n;
+}
+
 // ------------------------------------------------------------------------ kernel
 template <int BN>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
@@ -224,20 +338,23 @@ shift_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  const int total_tiles = p.num_m_tiles * p.n_tiles_n;
+  const int total_tiles = p.num_m_tiles * p.n_tiles_n * (p.k_splits > 1 ? p.k_splits : 1);
 
   if (warp == 0) {
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int m0 = (tile / p.n_tiles_n) * BM;
-        const int n0 = (tile % p.n_tiles_n) * BN;
+        int m_tile, n_tile, split;
+        tile_coords(p, tile, m_tile, n_tile, split);
+        const int m0 = m_tile * BM, n0 = n_tile * BN;
         for (int t = 0; t < p.num_taps; ++t) {
           const Tap tp = p.taps[t];
           const CUtensorMap* ma = tp.a_src ? &tmA1 : &tmA0;
           const CUtensorMap* mb = tp.b_src ? &tmB1 : &tmB0;
-          for (int kb = 0; kb < tp.nkb; ++kb) {
+          const int kb0 = p.k_splits > 1 ? split * p.k_split_len : 0;
+          const int nkb = p.k_splits > 1 ? p.k_split_len : tp.nkb;
+          for (int kb = kb0; kb < kb0 + nkb; ++kb) {
             mbar_wait(&empty[stage], phase ^ 1u, p.err_flag);
             mbar_expect_tx(&full[stage], C::STAGE_BYTES);
             uint8_t* sa = smem + stage * C::STAGE_BYTES;
@@ -262,7 +379,7 @@ shift_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
         const uint32_t d_tmem = tmem_base + acc * BN;
         uint32_t accumulate = 0;
         for (int t = 0; t < p.num_taps; ++t) {
-          const int nkb = p.taps[t].nkb;
+          const int nkb = p.k_splits > 1 ? p.k_split_len : p.taps[t].nkb;
           for (int kb = 0; kb < nkb; ++kb) {
             mbar_wait(&full[stage], phase, p.err_flag);
             tc_fence_after();
@@ -288,104 +405,168 @@ shift_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
     const int row = q * 32 + lane;
     uint32_t it = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      int m_tile, n_tile, split;
+      tile_coords(p, tile, m_tile, n_tile, split);
+      const uint32_t acc = it & 1u;
+      const uint32_t acc_phase = (it >> 1) & 1u;
+      mbar_wait(&tfull[acc], acc_phase, p.err_flag);
+      tc_fence_after();
+      const uint32_t taddr0 = tmem_base + acc * BN + ((uint32_t)(q * 32) << 16);
+      epilogue_tile<BN>(p, taddr0, m_tile * BM + row, n_tile * BN, split);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[acc]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
+                 "r"((uint32_t)C::TMEM_COLS)
+                 : "memory");
+  }
+}
+
+// ---------------------------------------------------------------- halo-mode kernel
+// 3x3 stride-1 convolutions only.  Instead of re-loading the 128-row A tile once per tap
+// (9 x 16 KB per K block), ONE block of a_rows = 128 + 2*Wp + 2 (rounded up to 8) rows is
+// loaded per K block and the nine taps address it through row-shifted shared-memory
+// descriptors (start address + (r*Wp + s) * 128 B; SWIZZLE_128B is a function of the
+// shared-memory address bits, which TMA used when it wrote the block; verified on B200: the
+// descriptor base_offset field must stay 0).  Weights stream
+// through their own ring.  Cuts the L2->SMEM traffic of the feed-bound layers 1.4-2.1x.
+template <int BN> struct HaloCfg {
+  static constexpr int B_TILE_BYTES = BN * BK * 2;
+  static constexpr int A_STAGES = 2;
+  static constexpr int B_STAGES = BN == 256 ? 4 : 8;
+  static constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;
+  static int smem_bytes(int a_rows) { return A_STAGES * a_rows * 128 + B_STAGES * B_TILE_BYTES + 256 + 1024; }
+};
+
+__device__ __forceinline__ uint64_t make_smem_desc_off(const void* p, int base_off_mode) {
+  uint64_t d = make_smem_desc(p);
+  if (base_off_mode) d |= (uint64_t)((smem_u32(p) >> 7) & 7u) << 49;
+  return d;
+}
+
+template <int BN>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+halo_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                 const __grid_constant__ Params p) {
+  using C = HaloCfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  const int a_bytes = p.a_rows * 128;              // multiple of 1024
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + C::A_STAGES * a_bytes;
+  uint64_t* afull = reinterpret_cast<uint64_t*>(sB + C::B_STAGES * C::B_TILE_BYTES);
+  uint64_t* aempty = afull + C::A_STAGES;
+  uint64_t* bfull = aempty + C::A_STAGES;
+  uint64_t* bempty = bfull + C::B_STAGES;
+  uint64_t* tfull = bempty + C::B_STAGES;
+  uint64_t* tempty = tfull + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < C::A_STAGES; ++s) { mbar_init(&afull[s], 1); mbar_init(&aempty[s], 1); }
+    for (int s = 0; s < C::B_STAGES; ++s) { mbar_init(&bfull[s], 1); mbar_init(&bempty[s], 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 4); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    prefetch_tmap(&tmA);
+    prefetch_tmap(&tmB);
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"((uint32_t)C::TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int total_tiles = p.num_m_tiles * p.n_tiles_n;
+  const int nkb = p.taps[0].nkb;
+  const int wp = p.Wp;
+  const int box_rows = p.a_rows / p.a_boxes;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int sa = 0, sb = 0;
+      uint32_t pa = 0, pb = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int m0 = (tile / p.n_tiles_n) * BM;
+        const int n0 = (tile % p.n_tiles_n) * BN;
+        for (int kb = 0; kb < nkb; ++kb) {
+          mbar_wait(&aempty[sa], pa ^ 1u, p.err_flag);
+          mbar_expect_tx(&afull[sa], (uint32_t)a_bytes);
+          for (int bx = 0; bx < p.a_boxes; ++bx)
+            tma_load_2d(sA + sa * a_bytes + bx * box_rows * 128, &tmA, &afull[sa], kb * BK,
+                        m0 - wp - 1 + bx * box_rows);
+          if (++sa == C::A_STAGES) { sa = 0; pa ^= 1u; }
+          for (int t = 0; t < 9; ++t) {
+            mbar_wait(&bempty[sb], pb ^ 1u, p.err_flag);
+            mbar_expect_tx(&bfull[sb], C::B_TILE_BYTES);
+            tma_load_2d(sB + sb * C::B_TILE_BYTES, &tmB, &bfull[sb], kb * BK, t * p.cout + n0);
+            if (++sb == C::B_STAGES) { sb = 0; pb ^= 1u; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(BM, BN);
+      int sa = 0, sb = 0;
+      uint32_t pa = 0, pb = 0, it = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+        const uint32_t acc = it & 1u;
+        const uint32_t acc_phase = (it >> 1) & 1u;
+        mbar_wait(&tempty[acc], acc_phase ^ 1u, p.err_flag);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        uint32_t accumulate = 0;
+        for (int kb = 0; kb < nkb; ++kb) {
+          mbar_wait(&afull[sa], pa, p.err_flag);
+          tc_fence_after();
+          const uint8_t* ablk = sA + sa * a_bytes;
+          for (int t = 0; t < 9; ++t) {
+            mbar_wait(&bfull[sb], pb, p.err_flag);
+            tc_fence_after();
+            const int off_rows = (t / 3) * wp + (t % 3);
+            const uint64_t adesc = make_smem_desc_off(ablk + off_rows * 128, p.base_off_mode);
+            const uint64_t bdesc = make_smem_desc(sB + sb * C::B_TILE_BYTES);
+#pragma unroll
+            for (int k = 0; k < BK / 16; ++k) {
+              mma_bf16(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, accumulate);
+              accumulate = 1;
+            }
+            tc_commit(&bempty[sb]);
+            if (++sb == C::B_STAGES) { sb = 0; pb ^= 1u; }
+          }
+          tc_commit(&aempty[sa]);
+          if (++sa == C::A_STAGES) { sa = 0; pa ^= 1u; }
+        }
+        tc_commit(&tfull[acc]);
+      }
+    }
+  } else {
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    uint32_t it = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
       const int m0 = (tile / p.n_tiles_n) * BM;
       const int n0 = (tile % p.n_tiles_n) * BN;
       const uint32_t acc = it & 1u;
       const uint32_t acc_phase = (it >> 1) & 1u;
-      const int m = m0 + row;
-      // geometry of this output row
-      bool valid = m < p.m_rows;
-      int img = 0, hp = 0, wp = 0;
-      if (valid && p.out_mode != OUT_F32) {
-        const int per_img = p.Hp * p.Wp;
-        img = m / per_img;
-        const int rem = m - img * per_img;
-        hp = rem / p.Wp;
-        wp = rem - hp * p.Wp;
-        valid = hp < p.H && wp < p.W;
-      }
-      int cls = 0;
-      if (p.bias_classes == 9)
-        cls = (hp == 0 ? 0 : (hp == p.H - 1 ? 2 : 1)) * 3 + (wp == 0 ? 0 : (wp == p.W - 1 ? 2 : 1));
-      const float* bias = p.bias + (size_t)cls * p.cout + n0;
-      size_t out_off = 0, even_off = 0;
-      bool write_even = false;
-      if (p.out_mode == OUT_STD) {
-        out_off = (size_t)m * p.cout + n0;
-        if (p.out_even && valid && !(hp & 1) && !(wp & 1)) {
-          write_even = true;
-          even_off = ((size_t)(img * p.Hp2 + (hp >> 1)) * p.Wp2 + (wp >> 1)) * p.cout + n0;
-        }
-      } else if (p.out_mode == OUT_S2D) {
-        out_off = (((size_t)(img * p.Hp2 + (hp >> 1)) * p.Wp2 + (wp >> 1)) * 4 +
-                   (size_t)((hp & 1) * 2 + (wp & 1))) * p.cout + n0;
-      } else {
-        out_off = (size_t)m * p.cout + n0;
-      }
       mbar_wait(&tfull[acc], acc_phase, p.err_flag);
       tc_fence_after();
       const uint32_t taddr0 = tmem_base + acc * BN + ((uint32_t)(q * 32) << 16);
-#pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
-        uint32_t v[32];
-        tmem_ld32(taddr0 + c * 32, v);
-        if (valid) {
-          float f[32];
-#pragma unroll
-          for (int i = 0; i < 32; i += 4) {
-            const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + c * 32 + i));
-            f[i] = __uint_as_float(v[i]) + b4.x;
-            f[i + 1] = __uint_as_float(v[i + 1]) + b4.y;
-            f[i + 2] = __uint_as_float(v[i + 2]) + b4.z;
-            f[i + 3] = __uint_as_float(v[i + 3]) + b4.w;
-          }
-          if (p.prelu) {
-#pragma unroll
-            for (int i = 0; i < 32; i += 4) {
-              const float4 s4 = __ldg(reinterpret_cast<const float4*>(p.prelu + n0 + c * 32 + i));
-              f[i] = f[i] > 0.f ? f[i] : f[i] * s4.x;
-              f[i + 1] = f[i + 1] > 0.f ? f[i + 1] : f[i + 1] * s4.y;
-              f[i + 2] = f[i + 2] > 0.f ? f[i + 2] : f[i + 2] * s4.z;
-              f[i + 3] = f[i + 3] > 0.f ? f[i + 3] : f[i + 3] * s4.w;
-            }
-          }
-          if (p.out_mode == OUT_F32) {
-            float4* o = reinterpret_cast<float4*>(p.out_f32 + out_off + c * 32);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) o[i] = make_float4(f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]);
-          } else {
-            if (p.residual) {
-              const uint4* r = reinterpret_cast<const uint4*>(p.residual + (size_t)m * p.cout + n0 + c * 32);
-#pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                const uint4 rv = __ldg(r + i);
-                const uint32_t w[4] = {rv.x, rv.y, rv.z, rv.w};
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                  f[i * 8 + 2 * j] += __uint_as_float(w[j] << 16);
-                  f[i * 8 + 2 * j + 1] += __uint_as_float(w[j] & 0xffff0000u);
-                }
-              }
-            }
-            uint4 pk[4];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              pk[i].x = pack_bf16(f[i * 8 + 0], f[i * 8 + 1]);
-              pk[i].y = pack_bf16(f[i * 8 + 2], f[i * 8 + 3]);
-              pk[i].z = pack_bf16(f[i * 8 + 4], f[i * 8 + 5]);
-              pk[i].w = pack_bf16(f[i * 8 + 6], f[i * 8 + 7]);
-            }
-            uint4* o = reinterpret_cast<uint4*>(p.out + out_off + c * 32);
-#pragma unroll
-            for (int i = 0; i < 4; ++i) o[i] = pk[i];
-            if (write_even) {
-              uint4* oe = reinterpret_cast<uint4*>(p.out_even + even_off + c * 32);
-#pragma unroll
-              for (int i = 0; i < 4; ++i) oe[i] = pk[i];
-            }
-          }
-        }
-      }
+      epilogue_tile<BN>(p, taddr0, m0 + row, n0, 0);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty[acc]);
