@@ -332,6 +332,11 @@ def run_gpu(args, rank, world, local_rank):
              "k5_align_gbs_lower_bound": k5_bytes / (stage_ms["align"] / 1e3) / 1e9 if stage_ms["align"] > 0 else None,
              "hbm_peak_gbs": peaks["hbm_gbs"], "n_det_per_frame": n_det_mean, "valid_frac": valid_frac}
 
+    # ---- secondary metric: 1:N cosine search (BASELINE.json configs[4]), row-sharded gallery
+    gallery = None
+    if not args.no_gallery:
+        gallery = bench_gallery(ctx, capi, torch, dist if world > 1 else None, dev, rank, world, stream, peaks)
+
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         frames_sample = 3
@@ -354,11 +359,73 @@ def run_gpu(args, rank, world, local_rank):
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "ms_per_step": 1e3 * e2e_s / args.steps},
                 "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
-                "cpu_baseline": cpu_baseline, "detail": extra}
+                "cpu_baseline": cpu_baseline, "gallery_1toN": gallery, "detail": extra}
         print(json.dumps(line), flush=True)
     ctx.close()
     if world > 1:
         dist.destroy_process_group()
+
+
+def bench_gallery(ctx, capi, torch, dist, dev, rank, world, stream, peaks, rows_per_gpu=1_250_000, nq=4096, k=10,
+                  iters=5):
+    """1:N search: each rank holds rows_per_gpu synthetic unit rows (bf16, generated on the
+    device), searches the same nq queries, the per-rank top-k lists are all-gathered over NCCL and
+    merged.  Returns queries/s over the whole job (max over ranks) and per-GPU GEMM TFLOP/s."""
+    gal = capi.Gallery(ctx, rows_per_gpu, index_base=rank * rows_per_gpu)
+    gal.fill_synthetic(rows_per_gpu, seed=1000)
+    g = torch.Generator(device="cpu").manual_seed(7)
+    q = torch.randn(nq, 512, generator=g)
+    q = (q / q.norm(dim=1, keepdim=True)).to(dev)
+    # plant exact gallery rows of this job's first shard so top-1 is known
+    planted = gal.get_rows(0, 64) if rank == 0 else None
+    if world > 1:
+        pl = torch.zeros(64, 512, device=dev)
+        if rank == 0:
+            pl.copy_(torch.from_numpy(planted))
+        dist.broadcast(pl, 0)
+        q[:64] = pl
+    else:
+        q[:64] = torch.from_numpy(planted).to(dev)
+    ls = torch.empty(nq, k, dtype=torch.float32, device=dev)
+    li = torch.empty(nq, k, dtype=torch.int64, device=dev)
+    gs = torch.empty(world * nq, k, dtype=torch.float32, device=dev)
+    gi = torch.empty(world * nq, k, dtype=torch.int64, device=dev)
+    ms_ = torch.empty(nq, k, dtype=torch.float32, device=dev)
+    mi = torch.empty(nq, k, dtype=torch.int64, device=dev)
+
+    def one():
+        gal.search_dev(q.data_ptr(), nq, k, ls.data_ptr(), li.data_ptr())
+        if world > 1:
+            dist.all_gather_into_tensor(gs, ls)
+            dist.all_gather_into_tensor(gi, li)
+            capi.topk_merge_dev(ctx, gs.data_ptr(), gi.data_ptr(), world, nq, k, ms_.data_ptr(), mi.data_ptr())
+        else:
+            capi.topk_merge_dev(ctx, ls.data_ptr(), li.data_ptr(), 1, nq, k, ms_.data_ptr(), mi.data_ptr())
+
+    for _ in range(3):
+        one()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(iters):
+        one()
+    e1.record(stream)
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    top1_ok = bool((mi[:64, 0].cpu() == torch.arange(64)).all().item())
+    tflops = 2.0 * nq * rows_per_gpu * 512 * iters / (ms / 1e3) / 1e12
+    gal.close()
+    return {"metric": "1:N queries/s (top-10, 512-d cosine)", "value": nq * iters / (ms / 1e3), "unit": "queries/s",
+            "gallery_rows_total": rows_per_gpu * world, "rows_per_gpu": rows_per_gpu, "queries_per_batch": nq,
+            "ms_per_batch": ms / iters, "gemm_tflops_per_gpu": tflops,
+            "frac_of_sustained_bf16_peak": tflops / peaks["tflops_sustained"], "planted_top1_ok": top1_ok,
+            "merge": "NCCL all_gather_into_tensor + fr_topk_merge" if world > 1 else "fr_topk_merge (1 shard)"}
 
 
 def main():
@@ -368,6 +435,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-gallery", action="store_true")
     args = ap.parse_args()
     rank = _env_int("RANK", 0)
     world = _env_int("WORLD_SIZE", 1)

@@ -64,6 +64,8 @@ struct ConvLaunch {
   int bn = 64;
   int rows_per_img = 1;  // Hp*Wp of the output geometry
   bool halo = false;
+  int mt = 1;            // halo mode: M tiles per CTA iteration
+  bool resb = false;     // halo mode: resident weights (Cin == 64)
 };
 
 static int env_flag(const char* name, int dflt) {
@@ -74,7 +76,14 @@ static int env_flag(const char* name, int dflt) {
 // Configure halo mode for a 3x3 stride-1 conv whose A operand is `base` ([rows, cin], pitch cin).
 static bool tc_setup_halo(ConvLaunch& L, const void* base, uint64_t rows, int cin, int Wp) {
   if (!env_flag("FR_TC_HALO", 1)) return true;   // default on (FR_TC_HALO=0 selects the per-tap loader)
-  int a_rows = (tc::BM + 2 * Wp + 2 + 7) / 8 * 8;
+  // M tiles per CTA iteration: 1 measured best overall on B200 (2 halves the weight traffic but
+  // loses the TMEM double buffer at BN=256 and doubles the wave-quantisation tail); 3 = 2 where
+  // the accumulators still double-buffer (BN <= 128)
+  int mt = env_flag("FR_TC_MT", 1);
+  if (mt == 3) mt = L.bn <= 128 ? 2 : 1;
+  L.mt = mt;
+  L.resb = (cin == 64) && env_flag("FR_TC_RESB", 1);
+  int a_rows = (mt * tc::BM + 2 * Wp + 2 + 7) / 8 * 8;
   int boxes = 1;
   if (a_rows > 256) { boxes = 2; a_rows = (a_rows + 15) / 16 * 16; }
   L.p.a_rows = a_rows;
@@ -102,24 +111,28 @@ int tc_launch(fr_ctx* ctx, ConvLaunch& L, int m_rows) {
     FR_CUDA_OK(ctx, cudaFuncSetAttribute(tc::shift_gemm_kernel<256>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          tc::Cfg<256>::SMEM_BYTES));
-    FR_CUDA_OK(ctx, cudaFuncSetAttribute(tc::halo_gemm_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    FR_CUDA_OK(ctx, cudaFuncSetAttribute(tc::halo_gemm_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    FR_CUDA_OK(ctx, cudaFuncSetAttribute(tc::halo_gemm_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     attrs = true;
   }
   const int grid = std::min(total, num_sms);
   if (L.halo) {
-    switch (L.bn) {
-      case 64:
-        tc::halo_gemm_kernel<64><<<grid, tc::NUM_THREADS, tc::HaloCfg<64>::smem_bytes(L.p.a_rows), ctx->stream>>>(L.a_halo, L.b0, L.p);
-        break;
-      case 128:
-        tc::halo_gemm_kernel<128><<<grid, tc::NUM_THREADS, tc::HaloCfg<128>::smem_bytes(L.p.a_rows), ctx->stream>>>(L.a_halo, L.b0, L.p);
-        break;
-      default:
-        tc::halo_gemm_kernel<256><<<grid, tc::NUM_THREADS, tc::HaloCfg<256>::smem_bytes(L.p.a_rows), ctx->stream>>>(L.a_halo, L.b0, L.p);
-        break;
-    }
+    const int supers = ceil_div(L.p.num_m_tiles, L.mt) * L.p.n_tiles_n;
+    const int hgrid = std::min(supers, num_sms);
+#define FR_HALO_LAUNCH(BN_, MT_, RB_)                                                              \
+  do {                                                                                             \
+    static bool set_ = false;                                                                      \
+    if (!set_) {                                                                                   \
+      FR_CUDA_OK(ctx, cudaFuncSetAttribute(tc::halo_gemm_kernel<BN_, MT_, RB_>,                    \
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); \
+      set_ = true;                                                                                 \
+    }                                                                                              \
+    tc::halo_gemm_kernel<BN_, MT_, RB_><<<hgrid, tc::NUM_THREADS,                                  \
+        tc::HaloCfg<BN_, MT_, RB_>::smem_bytes(L.p.a_rows), ctx->stream>>>(L.a_halo, L.b0, L.p);   \
+  } while (0)
+    if (L.bn == 64 && L.resb) { if (L.mt == 2) FR_HALO_LAUNCH(64, 2, true); else FR_HALO_LAUNCH(64, 1, true); }
+    else if (L.bn == 64) { if (L.mt == 2) FR_HALO_LAUNCH(64, 2, false); else FR_HALO_LAUNCH(64, 1, false); }
+    else if (L.bn == 128) { if (L.mt == 2) FR_HALO_LAUNCH(128, 2, false); else FR_HALO_LAUNCH(128, 1, false); }
+    else { if (L.mt == 2) FR_HALO_LAUNCH(256, 2, false); else FR_HALO_LAUNCH(256, 1, false); }
+#undef FR_HALO_LAUNCH
     ctx->launches++;
     FR_CUDA_OK(ctx, cudaGetLastError());
     return FR_OK;

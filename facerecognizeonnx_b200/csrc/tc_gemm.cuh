@@ -436,38 +436,38 @@ shift_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
 // shared-memory address bits, which TMA used when it wrote the block; verified on B200: the
 // descriptor base_offset field must stay 0).  Weights stream
 // through their own ring.  Cuts the L2->SMEM traffic of the feed-bound layers 1.4-2.1x.
-template <int BN> struct HaloCfg {
+template <int BN, int MT, bool RESB> struct HaloCfg {
   static constexpr int B_TILE_BYTES = BN * BK * 2;
   static constexpr int A_STAGES = 2;
-  static constexpr int B_STAGES = BN == 256 ? 4 : 8;
-  static constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;
-  static int smem_bytes(int a_rows) { return A_STAGES * a_rows * 128 + B_STAGES * B_TILE_BYTES + 256 + 1024; }
+  static constexpr int B_STAGES = 4;
+  static constexpr int ACC_STAGES = (2 * MT * BN <= 512) ? 2 : 1;
+  static constexpr int TMEM_COLS = ACC_STAGES * MT * BN < 32 ? 32 : ACC_STAGES * MT * BN;
+  static constexpr int B_BYTES = RESB ? 9 * B_TILE_BYTES : B_STAGES * B_TILE_BYTES;
+  static int smem_bytes(int a_rows) { return A_STAGES * a_rows * 128 + B_BYTES + 256 + 1024; }
 };
 
-__device__ __forceinline__ uint64_t make_smem_desc_off(const void* p, int base_off_mode) {
-  uint64_t d = make_smem_desc(p);
-  if (base_off_mode) d |= (uint64_t)((smem_u32(p) >> 7) & 7u) << 49;
-  return d;
-}
-
-template <int BN>
+// MT   : M tiles (of 128 rows) per CTA iteration; they share one A block of
+//        MT*128 + 2*Wp + 2 rows and every streamed weight tile (halves the weight traffic)
+// RESB : Cin == 64 only: all nine weight tiles stay resident in shared memory
+template <int BN, int MT, bool RESB>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 halo_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ Params p) {
-  using C = HaloCfg<BN>;
+  using C = HaloCfg<BN, MT, RESB>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
   const int a_bytes = p.a_rows * 128;              // multiple of 1024
   uint8_t* sA = smem;
   uint8_t* sB = smem + C::A_STAGES * a_bytes;
-  uint64_t* afull = reinterpret_cast<uint64_t*>(sB + C::B_STAGES * C::B_TILE_BYTES);
+  uint64_t* afull = reinterpret_cast<uint64_t*>(sB + C::B_BYTES);
   uint64_t* aempty = afull + C::A_STAGES;
   uint64_t* bfull = aempty + C::A_STAGES;
   uint64_t* bempty = bfull + C::B_STAGES;
   uint64_t* tfull = bempty + C::B_STAGES;
   uint64_t* tempty = tfull + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  uint64_t* resfull = tempty + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(resfull + 1);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -475,6 +475,7 @@ halo_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     for (int s = 0; s < C::A_STAGES; ++s) { mbar_init(&afull[s], 1); mbar_init(&aempty[s], 1); }
     for (int s = 0; s < C::B_STAGES; ++s) { mbar_init(&bfull[s], 1); mbar_init(&bempty[s], 1); }
     for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 4); }
+    mbar_init(resfull, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     prefetch_tmap(&tmA);
     prefetch_tmap(&tmB);
@@ -490,17 +491,22 @@ halo_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  const int total_tiles = p.num_m_tiles * p.n_tiles_n;
+  const int num_super = (p.num_m_tiles + MT - 1) / MT;
+  const int total_tiles = num_super * p.n_tiles_n;
   const int nkb = p.taps[0].nkb;
   const int wp = p.Wp;
   const int box_rows = p.a_rows / p.a_boxes;
 
   if (warp == 0) {
     if (lane == 0) {
+      if (RESB) {   // n_tiles_n == 1 and nkb == 1: the whole weight tensor is 9 tiles
+        mbar_expect_tx(resfull, 9 * C::B_TILE_BYTES);
+        for (int t = 0; t < 9; ++t) tma_load_2d(sB + t * C::B_TILE_BYTES, &tmB, resfull, 0, t * p.cout);
+      }
       int sa = 0, sb = 0;
       uint32_t pa = 0, pb = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int m0 = (tile / p.n_tiles_n) * BM;
+        const int m0 = (tile / p.n_tiles_n) * (BM * MT);
         const int n0 = (tile % p.n_tiles_n) * BN;
         for (int kb = 0; kb < nkb; ++kb) {
           mbar_wait(&aempty[sa], pa ^ 1u, p.err_flag);
@@ -509,11 +515,13 @@ halo_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             tma_load_2d(sA + sa * a_bytes + bx * box_rows * 128, &tmA, &afull[sa], kb * BK,
                         m0 - wp - 1 + bx * box_rows);
           if (++sa == C::A_STAGES) { sa = 0; pa ^= 1u; }
-          for (int t = 0; t < 9; ++t) {
-            mbar_wait(&bempty[sb], pb ^ 1u, p.err_flag);
-            mbar_expect_tx(&bfull[sb], C::B_TILE_BYTES);
-            tma_load_2d(sB + sb * C::B_TILE_BYTES, &tmB, &bfull[sb], kb * BK, t * p.cout + n0);
-            if (++sb == C::B_STAGES) { sb = 0; pb ^= 1u; }
+          if (!RESB) {
+            for (int t = 0; t < 9; ++t) {
+              mbar_wait(&bempty[sb], pb ^ 1u, p.err_flag);
+              mbar_expect_tx(&bfull[sb], C::B_TILE_BYTES);
+              tma_load_2d(sB + sb * C::B_TILE_BYTES, &tmB, &bfull[sb], kb * BK, t * p.cout + n0);
+              if (++sb == C::B_STAGES) { sb = 0; pb ^= 1u; }
+            }
           }
         }
       }
@@ -523,30 +531,44 @@ halo_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       constexpr uint32_t idesc = make_idesc(BM, BN);
       int sa = 0, sb = 0;
       uint32_t pa = 0, pb = 0, it = 0;
+      if (RESB) {
+        mbar_wait(resfull, 0, p.err_flag);
+        tc_fence_after();
+      }
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
-        const uint32_t acc = it & 1u;
-        const uint32_t acc_phase = (it >> 1) & 1u;
+        const uint32_t acc = C::ACC_STAGES == 2 ? (it & 1u) : 0u;
+        const uint32_t acc_phase = C::ACC_STAGES == 2 ? ((it >> 1) & 1u) : (it & 1u);
         mbar_wait(&tempty[acc], acc_phase ^ 1u, p.err_flag);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * BN;
-        uint32_t accumulate = 0;
+        const uint32_t d_tmem = tmem_base + acc * (MT * BN);
         for (int kb = 0; kb < nkb; ++kb) {
           mbar_wait(&afull[sa], pa, p.err_flag);
           tc_fence_after();
           const uint8_t* ablk = sA + sa * a_bytes;
           for (int t = 0; t < 9; ++t) {
-            mbar_wait(&bfull[sb], pb, p.err_flag);
-            tc_fence_after();
-            const int off_rows = (t / 3) * wp + (t % 3);
-            const uint64_t adesc = make_smem_desc_off(ablk + off_rows * 128, p.base_off_mode);
-            const uint64_t bdesc = make_smem_desc(sB + sb * C::B_TILE_BYTES);
-#pragma unroll
-            for (int k = 0; k < BK / 16; ++k) {
-              mma_bf16(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, accumulate);
-              accumulate = 1;
+            const uint8_t* btile;
+            if (RESB) {
+              btile = sB + t * C::B_TILE_BYTES;
+            } else {
+              mbar_wait(&bfull[sb], pb, p.err_flag);
+              tc_fence_after();
+              btile = sB + sb * C::B_TILE_BYTES;
             }
-            tc_commit(&bempty[sb]);
-            if (++sb == C::B_STAGES) { sb = 0; pb ^= 1u; }
+            const int off_rows = (t / 3) * wp + (t % 3);
+            const uint64_t bdesc = make_smem_desc(btile);
+            const uint32_t accumulate = (kb | t) ? 1u : 0u;
+#pragma unroll
+            for (int mt = 0; mt < MT; ++mt) {
+              const uint64_t adesc = make_smem_desc(ablk + (mt * BM + off_rows) * 128);
+#pragma unroll
+              for (int k = 0; k < BK / 16; ++k)
+                mma_bf16(d_tmem + mt * BN, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc,
+                         (accumulate | (uint32_t)k) ? 1u : 0u);
+            }
+            if (!RESB) {
+              tc_commit(&bempty[sb]);
+              if (++sb == C::B_STAGES) { sb = 0; pb ^= 1u; }
+            }
           }
           tc_commit(&aempty[sa]);
           if (++sa == C::A_STAGES) { sa = 0; pa ^= 1u; }
@@ -559,14 +581,17 @@ halo_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int row = q * 32 + lane;
     uint32_t it = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
-      const int m0 = (tile / p.n_tiles_n) * BM;
+      const int m0 = (tile / p.n_tiles_n) * (BM * MT);
       const int n0 = (tile % p.n_tiles_n) * BN;
-      const uint32_t acc = it & 1u;
-      const uint32_t acc_phase = (it >> 1) & 1u;
+      const uint32_t acc = C::ACC_STAGES == 2 ? (it & 1u) : 0u;
+      const uint32_t acc_phase = C::ACC_STAGES == 2 ? ((it >> 1) & 1u) : (it & 1u);
       mbar_wait(&tfull[acc], acc_phase, p.err_flag);
       tc_fence_after();
-      const uint32_t taddr0 = tmem_base + acc * BN + ((uint32_t)(q * 32) << 16);
-      epilogue_tile<BN>(p, taddr0, m0 + row, n0, 0);
+#pragma unroll 1
+      for (int mt = 0; mt < MT; ++mt) {
+        const uint32_t taddr0 = tmem_base + acc * (MT * BN) + mt * BN + ((uint32_t)(q * 32) << 16);
+        epilogue_tile<BN>(p, taddr0, m0 + mt * BM + row, n0, 0);
+      }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty[acc]);
