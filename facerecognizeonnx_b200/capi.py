@@ -42,7 +42,7 @@ SYMBOLS = [
     "fr_gallery_get_rows", "fr_gallery_size", "fr_gallery_search", "fr_topk_merge",
     "fr_det_preprocess", "fr_scrfd_forward", "fr_scrfd_decode_nms", "fr_estimate_alignment",
     "fr_align_faces", "fr_warp_affine", "fr_resize_linear", "fr_iresnet_forward", "fr_iresnet_tap",
-    "fr_l2_normalize", "fr_test_conv",
+    "fr_l2_normalize", "fr_test_conv", "fr_scrfd_tap",
 ]
 
 
@@ -119,6 +119,7 @@ def _declare(L: C.CDLL) -> None:
     L.fr_resize_linear.argtypes = [vp, vp, i32, i32, sz, i32, i32, vp]
     L.fr_iresnet_forward.argtypes = [vp, vp, i32, vp]
     L.fr_iresnet_tap.argtypes = [vp, i32, i32, vp, sz]
+    L.fr_scrfd_tap.argtypes = [vp, i32, i32, vp, sz]
     L.fr_l2_normalize.argtypes = [vp, vp, i32, i32, i32, vp]
     L.fr_test_conv.argtypes = [vp, vp, i32, i32, i32, i32, vp, i32, i32, i32, vp, vp, vp, vp, vp, vp]
 
@@ -404,6 +405,13 @@ class Context:
         out = np.zeros((n,) + tuple(shape), np.float32)
         self._check(lib().fr_iresnet_tap(self.h, tap, n, out.ctypes.data, out.size))
         return out
+
+    def scrfd_tap(self, tap: int, n: int, shape_chw) -> np.ndarray:
+        """Activation `tap` of the last SCRFD forward, returned as NCHW (device layout is NHWC)."""
+        c, h, w = shape_chw
+        out = np.zeros((n, h, w, c), np.float32)
+        self._check(lib().fr_scrfd_tap(self.h, tap, n, out.ctypes.data, out.size))
+        return np.ascontiguousarray(out.transpose(0, 3, 1, 2))
 
     def l2_normalize(self, x: np.ndarray) -> np.ndarray:
         x = np.ascontiguousarray(x, np.float32)

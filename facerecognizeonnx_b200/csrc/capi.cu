@@ -677,6 +677,14 @@ int fr_iresnet_tap(fr_ctx* ctx, int tap, int n, float* out, size_t out_elems) {
   return rec_tap(ctx, tap, n, out, out_elems);
 }
 
+int fr_scrfd_tap(fr_ctx* ctx, int tap, int n, float* out, size_t out_elems) {
+  if (!ctx) return FR_ERR_INVALID_ARG;
+  Guard g(ctx);
+  if (!ctx->det) return fr_fail(ctx, FR_ERR_NOT_LOADED, "Model not loaded!");
+  if (!out || n <= 0) return fr_fail(ctx, FR_ERR_INVALID_ARG, "bad arguments");
+  return det_tap(ctx, tap, n, out, out_elems);
+}
+
 int fr_l2_normalize(fr_ctx* ctx, const float* in, int n, int dim, int memspace, float* out) {
   if (!ctx) return FR_ERR_INVALID_ARG;
   Guard g(ctx);

@@ -161,6 +161,7 @@ int k_align_warp(fr_ctx* ctx, const AlignRec* d_rec, int n_faces, const ImgDesc*
 int det_model_create(fr_ctx* ctx, const fr_weights* w);
 void det_model_destroy(fr_ctx* ctx);
 int det_forward(fr_ctx* ctx, const __nv_bfloat16* d_in_chw, int n_img, HeadPtrs* heads);
+int det_tap(fr_ctx* ctx, int tap, int n, float* h_out, size_t out_elems);
 
 // k_iresnet.cu
 int rec_model_create(fr_ctx* ctx, const fr_weights* w);

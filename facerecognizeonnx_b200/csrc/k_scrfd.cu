@@ -3,229 +3,474 @@
 // (depthwise-separable backbone 16/40/72/152/288, PAFPN 16 ch, per-stride heads 64 ch,
 // 2 anchors), BN folded into conv+bias, sigmoid on the score heads.
 //
-// The network is bandwidth / latency bound (depthwise 3x3 + thin 1x1; 1.47 GFLOP per frame,
-// channel counts hostile to MMA tiles) and must hold boxes to 1e-3 px, so it runs in fp32 on
-// the CUDA cores: NCHW planar activations, one thread per output pixel, weights broadcast
-// from shared memory as float4, depthwise 3x3 + ReLU fused into the following pointwise conv
-// (the depthwise value is recomputed per output-channel chunk instead of round-tripping HBM).
+// Boxes must hold 1e-3 px against an fp32 CPU engine, which rules out bf16 (2^-9) and plain
+// tf32 (2^-11) products.  Every pointwise / dense convolution therefore runs on the 5th-gen
+// tensor cores as a THREE-TERM TF32 SPLIT: x = x_hi + x_lo with x_hi = rna_tf32(x), and
+//     x * w  ~=  x_lo*w_hi + x_hi*w_lo + x_hi*w_hi          (dropped term <= 2^-22 |x w|)
+// accumulated in fp32 in TMEM -- fp32-grade results at tensor-core rate.
+//
+// One kernel (`sep_gemm_kernel`) serves all 33 GEMM-shaped layers.  Activations are fp32 NHWC
+// (K = channels contiguous).  Per 128-pixel tile and per 32-channel K block:
+//   loader warps (8, two groups working on alternating pipeline stages): gather the A operand
+//       straight from global memory -- plain (1x1), im2col (dense 3x3) or with the depthwise
+//       3x3 + bias + ReLU evaluated on the fly (the depthwise result never exists in HBM) --
+//       split it into tf32 hi/lo and store both as K-major SWIZZLE_128B tiles in shared memory,
+//       then fence.proxy.async + mbarrier arrive;
+//   warp 0 : TMA of the (host-pre-split) hi/lo weight tiles into the same stage;
+//   warp 1 : one lane issues 3 x tcgen05.mma.kind::tf32 (M=128, N=16..160, K=8) per K step;
+//   warps 2-5: epilogue, tcgen05.ld -> bias / ReLU / top-down upsample-add / accumulate ->
+//       fp32 NHWC float4 stores, or the anchor-major score (sigmoid) / bbox / kps scatter.
+// TMEM accumulators are double buffered, so gather, MMA and epilogue of consecutive tiles overlap.
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 
 #include "common.h"
+#include "tc_gemm.cuh"
+
+bool tc_make_map_2d_f32(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols,
+                        uint64_t pitch_elems, uint32_t box_rows);   // k_iresnet.cu
 
 namespace {
 
+using tc::make_smem_desc;
+using tc::mbar_arrive;
+using tc::mbar_expect_tx;
+using tc::mbar_init;
+using tc::mbar_wait;
+using tc::smem_u32;
+using tc::tc_commit;
+using tc::tc_fence_after;
+using tc::tc_fence_before;
+using tc::tma_load_2d;
+
 constexpr int DET = FR_DET_SIZE;
+constexpr int TM = 128;                 // pixels per tile (MMA M)
+constexpr int A_BYTES = TM * 128;       // one 128 x 32 fp32 operand tile
+constexpr int MAX_STAGES = 6;
+constexpr int LD_GROUPS = 2;            // loader groups, working on alternating stages
+constexpr int LD_WARPS = 8;
+constexpr int TG = LD_WARPS * 32 / LD_GROUPS;   // threads per loader group
+constexpr int ITEMS = TM * 8 / TG;              // (row, 16-byte chunk) items per thread per K block
+constexpr int ROW_STEP = TG / 8;
+constexpr int FIRST_LD_WARP = 6;
+constexpr int THREADS = (FIRST_LD_WARP + LD_WARPS) * 32;
+static_assert(ROW_STEP % 8 == 0, "row & 7 must be constant per thread");
 
-enum { MODE_IM2COL = 1, MODE_PW = 2 };
-constexpr int TP = 128;   // pixels per block tile (flattened over the batch)
-constexpr int KC = 16;    // K chunk staged in shared memory
+enum { LD_PW = 0, LD_DW = 1, LD_IM2COL = 2 };
+enum { EPI_STD = 0, EPI_HEAD = 1 };
 
-struct ConvArgs {
-  const void* in;        // fp32 NCHW (bf16 for the stem)
-  float* out;            // fp32 NCHW
-  const float* wt;       // [Kpad][Cpad] transposed weights, zero padded (im2col: row = tap*cin + ci)
-  const float* b;        // [Cpad]
-  const float* add_up;   // optional [n][cout][hout/2][wout/2], nearest-upsampled and added
-  int cin, cout, cpad, kdim, kpad;
-  int hin, win, hout, wout, stride;
-  int total_px;          // n * hout * wout
-  int relu;
-  int accumulate;        // out += result (PAFPN bottom-up path)
-  int head;              // scatter to score/bbox/kps (anchor-major) with sigmoid on the scores
+struct SepParams {
+  const float* in;      // fp32 NHWC [n][hin][win][cin]
+  float* out;           // fp32 NHWC [n][hout][wout][cout]
+  const float* dw_w;    // [9][cin] depthwise weights, tap major
+  const float* dw_b;    // [cin]
+  const float* bias;    // [npad_total]
+  const float* add_up;  // optional [n][hout/2][wout/2][cout], nearest-upsampled and added
   float* score;
   float* bbox;
   float* kps;
+  int cin, cout, kdim;
+  int hin, win, hout, wout, stride;
+  int mode, epi, relu, accumulate;
+  int nkb;              // 32-wide K blocks
+  int nt;               // MMA N (per N tile)
+  int n_tiles_n;
+  int npad_total;       // rows of the hi half of the packed weights
+  int total_px;         // n * hout * wout
+  int tiles_x, tiles_y; // 8 x 16 spatial tiles per image (0 = flattened pixel order)
+  int num_m_tiles;
+  int stages;
+  int tmem_cols;
+  int nbig;             // hi*hi accumulators per tile (k steps alternate between them)
+  int acc_stages;       // 2 = TMEM double buffered, 1 = single
+  int* err_flag;
 };
 
-// ---------------------------------------------------------------------------------------
-// Tiled SIMT GEMM:  out[co, px] = act( sum_k Wt[k, co] * X[k, px] + b[co] )
-//   MODE_PW     : X[ci, px] = in[ci, px]                           (1x1 conv)
-//   MODE_IM2COL : X[tap*cin + ci, px] = in[ci, tap of px]          (dense 3x3, pad 1, cin % 16 == 0)
-// Block = 128 threads; tile = 128 pixels x (8*CT) channels; thread tile 8 px x CT channels.
-// K is consumed in chunks of 16 staged in shared memory; the next chunk's global loads are
-// issued into registers before the current chunk is computed (register double buffering), so
-// HBM/L2 latency overlaps the FMAs.  All global accesses are coalesced along pixels.
-// grid (ceil(total_px/128), cpad/(8*CT)).
-template <int CT, int MODE>
-__global__ void __launch_bounds__(128)
-tile_conv_kernel(ConvArgs a) {
-  constexpr int TC = 8 * CT;
-  constexpr int WL = (KC * TC + 127) / 128;      // weight loads per thread per chunk
-  __shared__ __align__(16) float Xs[KC][TP];
-  __shared__ __align__(16) float Ws[KC][TC];
-  const int t = threadIdx.x;
-  const int hw = a.hout * a.wout;
-  const int c0 = blockIdx.y * TC;
-  const float* in = reinterpret_cast<const float*>(a.in);
-  // this thread's staging pixel
-  const int g = blockIdx.x * TP + t;
-  const bool gvalid = g < a.total_px;
-  const int gn = gvalid ? g / hw : 0;
-  const int gp = gvalid ? g - gn * hw : 0;
-  const int oy = gp / a.wout, ox = gp - oy * a.wout;
-  const size_t plane = (size_t)a.hin * a.win;
-  const size_t in_base = (size_t)gn * a.cin * plane;
-  const float gmask = gvalid ? 1.f : 0.f;
+__device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
 
-  float xv[KC], wv[WL];
-  auto prefetch = [&](int k0) {
-    if (MODE == MODE_PW) {
+__device__ __forceinline__ float tf32_rna(float x) {
+  uint32_t u;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
+  return __uint_as_float(u);
+}
+
+__device__ __forceinline__ void split_store(uint8_t* hi, uint8_t* lo, uint32_t off, const float4& v) {
+  float4 h, l;
+  h.x = tf32_rna(v.x); h.y = tf32_rna(v.y); h.z = tf32_rna(v.z); h.w = tf32_rna(v.w);
+  // the residual is rounded (not left to the tensor core's truncation) to tf32 as well
+  l.x = tf32_rna(v.x - h.x); l.y = tf32_rna(v.y - h.y); l.z = tf32_rna(v.z - h.z); l.w = tf32_rna(v.w - h.w);
+  *reinterpret_cast<float4*>(hi + off) = h;
+  *reinterpret_cast<float4*>(lo + off) = l;
+}
+
+__device__ __forceinline__ void fma4(float4& acc, const float4& v, const float4& w) {
+  acc.x = fmaf(v.x, w.x, acc.x);
+  acc.y = fmaf(v.y, w.y, acc.y);
+  acc.z = fmaf(v.z, w.z, acc.z);
+  acc.w = fmaf(v.w, w.w, acc.w);
+}
+
+// kind::tf32 instruction descriptor: tf32 x tf32 -> fp32, both operands K-major.
+__host__ __device__ constexpr uint32_t make_idesc_tf32(int m, int n) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+
+__device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                         uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      :
+      : "r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// 16 accumulator columns of one row: hi*hi partial sum(s) + the cross-term accumulator, added
+// in fp32 with round-to-nearest (small + (big0 + big1)).
+__device__ __forceinline__ void ld_sum16(uint32_t taddr, uint32_t small_off, int nbig, uint32_t nt, uint32_t (&v)[16]) {
+  uint32_t s[16];
+  tmem_ld16(taddr, v);
+  tmem_ld16(taddr + small_off, s);
+  if (nbig == 2) {
+    uint32_t b1[16];
+    tmem_ld16(taddr + nt, b1);
 #pragma unroll
-      for (int kk = 0; kk < KC; ++kk) {
-        const int ci = min(k0 + kk, a.cin - 1);
-        xv[kk] = __ldg(in + in_base + (size_t)ci * plane + gp);
+    for (int i = 0; i < 16; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) + __uint_as_float(b1[i]));
+  }
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) + __uint_as_float(s[i]));
+}
+
+// tile row -> output pixel.  2-D mode: 8 x 16 pixel patches (3x3 stencils of a patch overlap in
+// L1 instead of re-reading whole image rows); flattened mode for the 40^2 / 20^2 maps.
+__device__ __forceinline__ bool tile_pixel(const SepParams& p, int m_tile, int row, int& n, int& oy, int& ox) {
+  if (p.tiles_x > 0) {
+    const int per_img = p.tiles_x * p.tiles_y;
+    n = m_tile / per_img;
+    const int t = m_tile - n * per_img;
+    const int ty = t / p.tiles_x, tx = t - ty * p.tiles_x;
+    oy = ty * 8 + (row >> 4);
+    ox = tx * 16 + (row & 15);
+    return true;
+  }
+  const int m = m_tile * TM + row;
+  if (m >= p.total_px) {
+    n = oy = ox = 0;
+    return false;
+  }
+  const int hw = p.hout * p.wout;
+  n = m / hw;
+  const int r = m - n * hw;
+  oy = r / p.wout;
+  ox = r - oy * p.wout;
+  return true;
+}
+
+__global__ void __launch_bounds__(THREADS, 1)
+sep_gemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ SepParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  const int b_bytes = p.nt * 128;
+  const int stage_bytes = 2 * A_BYTES + 2 * b_bytes;
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + p.stages * stage_bytes);
+  uint64_t* empty = full + MAX_STAGES;
+  uint64_t* tfull = empty + MAX_STAGES;
+  uint64_t* tempty = tfull + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(&full[s], TG + 1);      // loader group threads + the weight TMA's expect_tx arrive
+      mbar_init(&empty[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tfull[a], 1);
+      mbar_init(&tempty[a], 4);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    tc::prefetch_tmap(&tmW);
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"((uint32_t)p.tmem_cols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int total_tiles = p.num_m_tiles * p.n_tiles_n;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------- weight TMA
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int n0 = (tile % p.n_tiles_n) * p.nt;
+        for (int kb = 0; kb < p.nkb; ++kb, ++it) {
+          const int stage = it % p.stages;
+          const uint32_t phase = (it / p.stages) & 1u;
+          mbar_wait(&empty[stage], phase ^ 1u, p.err_flag);
+          mbar_expect_tx(&full[stage], 2u * (uint32_t)b_bytes);
+          uint8_t* sb = smem + stage * stage_bytes + 2 * A_BYTES;
+          tma_load_2d(sb, &tmW, &full[stage], kb * 32, n0);
+          tma_load_2d(sb + b_bytes, &tmW, &full[stage], kb * 32, p.npad_total + n0);
+        }
       }
-    } else {
-      // the whole chunk shares one tap (cin % KC == 0)
-      const int q = k0 / a.cin, cbase = k0 - q * a.cin;
-      const int iy = oy * a.stride - 1 + q / 3, ix = ox * a.stride - 1 + q % 3;
-      const bool ok = gvalid && iy >= 0 && iy < a.hin && ix >= 0 && ix < a.win;
-      const size_t off = in_base + (size_t)cbase * plane + (ok ? (size_t)iy * a.win + ix : 0);
-#pragma unroll
-      for (int kk = 0; kk < KC; ++kk) xv[kk] = ok ? __ldg(in + off + (size_t)kk * plane) : 0.f;
     }
-#pragma unroll
-    for (int i = 0; i < WL; ++i) {
-      const int idx = t + i * 128;
-      const int kk = idx / TC, c = idx - kk * TC;
-      wv[i] = idx < KC * TC ? __ldg(a.wt + (size_t)(k0 + kk) * a.cpad + c0 + c) : 0.f;
+  } else if (warp == 1) {
+    // ------------------------------------------------------------- MMA issuer
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_tf32(TM, p.nt);
+      uint32_t it = 0, tt = 0;
+      const uint32_t slot_cols = (uint32_t)((p.nbig + 1) * p.nt);
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tt) {
+        const uint32_t acc = p.acc_stages == 2 ? (tt & 1u) : 0u;
+        const uint32_t acc_phase = p.acc_stages == 2 ? ((tt >> 1) & 1u) : (tt & 1u);
+        mbar_wait(&tempty[acc], acc_phase ^ 1u, p.err_flag);
+        tc_fence_after();
+        // The tensor core truncates when it adds a K=8 product group into the fp32 accumulator,
+        // a bias of ~2^-24 |D| per MMA.  So: the two small cross terms go to their own
+        // accumulator (their truncation is 2^-11 smaller), and the hi*hi products alternate
+        // between nbig accumulators; the epilogue adds the partial sums with round-to-nearest.
+        const uint32_t d_big = tmem_base + acc * slot_cols;
+        const uint32_t d_small = d_big + (uint32_t)(p.nbig * p.nt);
+        uint32_t ks_total = 0;
+        for (int kb = 0; kb < p.nkb; ++kb, ++it) {
+          const int stage = it % p.stages;
+          const uint32_t phase = (it / p.stages) & 1u;
+          mbar_wait(&full[stage], phase, p.err_flag);
+          tc_fence_after();
+          const uint8_t* sa = smem + stage * stage_bytes;
+          const uint64_t ahi = make_smem_desc(sa);
+          const uint64_t alo = make_smem_desc(sa + A_BYTES);
+          const uint64_t bhi = make_smem_desc(sa + 2 * A_BYTES);
+          const uint64_t blo = make_smem_desc(sa + 2 * A_BYTES + b_bytes);
+          const int ksteps = min(4, (p.kdim - kb * 32 + 7) >> 3);   // K = 8 tf32 per MMA
+          for (int k = 0; k < ksteps; ++k, ++ks_total) {
+            const uint64_t o = (uint64_t)(k * 2);   // +32 bytes inside the 128-byte swizzle row
+            mma_tf32(d_small, alo + o, bhi + o, idesc, ks_total ? 1u : 0u);
+            mma_tf32(d_small, ahi + o, blo + o, idesc, 1u);
+            const uint32_t which = p.nbig == 2 ? (ks_total & 1u) : 0u;
+            mma_tf32(d_big + which * (uint32_t)p.nt, ahi + o, bhi + o, idesc, ks_total >= (uint32_t)p.nbig ? 1u : 0u);
+          }
+          tc_commit(&empty[stage]);
+        }
+        tc_commit(&tfull[acc]);
+      }
     }
-  };
-
-  const int cg = t & 7, pg = t >> 3;
-  float acc[8][CT];
+  } else if (warp < FIRST_LD_WARP) {
+    // ------------------------------------------------------------- epilogue
+    const int q = warp & 3;            // TMEM lane quarter this warp may access
+    const int row = q * 32 + lane;
+    uint32_t tt = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tt) {
+      const int m_tile = tile / p.n_tiles_n;
+      const int n0 = (tile % p.n_tiles_n) * p.nt;
+      int n, oy, ox;
+      const bool valid = tile_pixel(p, m_tile, row, n, oy, ox);
+      const uint32_t acc = p.acc_stages == 2 ? (tt & 1u) : 0u;
+      const uint32_t acc_phase = p.acc_stages == 2 ? ((tt >> 1) & 1u) : (tt & 1u);
+      mbar_wait(&tfull[acc], acc_phase, p.err_flag);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + acc * (uint32_t)((p.nbig + 1) * p.nt) + ((uint32_t)(q * 32) << 16);
+      // kdim <= 8 * nbig would leave the second hi*hi accumulator unwritten; not the case here
+      const uint32_t small_off = (uint32_t)(p.nbig * p.nt);
+      if (p.epi == EPI_HEAD) {
+        // 30 channels of one pixel: [0,2) score (sigmoid), [2,10) bbox, [10,30) kps; the export's
+        // anchor-major layout is anchor = pixel*2 + a, i.e. contiguous per pixel
+        uint32_t v0[16], v1[16];
+        ld_sum16(taddr, small_off, p.nbig, (uint32_t)p.nt, v0);
+        ld_sum16(taddr + 16, small_off, p.nbig, (uint32_t)p.nt, v1);
+        if (valid) {
+          float f[32];
 #pragma unroll
-  for (int i = 0; i < 8; ++i)
+          for (int i = 0; i < 16; ++i) {
+            f[i] = __uint_as_float(v0[i]) + __ldg(p.bias + i);
+            f[16 + i] = __uint_as_float(v1[i]) + __ldg(p.bias + 16 + i);
+          }
+          const size_t hw = (size_t)p.hout * p.wout;
+          const size_t pix = (size_t)oy * p.wout + ox;
+          float2 sc;
+          sc.x = 1.0f / (1.0f + expf(-f[0]));
+          sc.y = 1.0f / (1.0f + expf(-f[1]));
+          *reinterpret_cast<float2*>(p.score + ((size_t)n * hw + pix) * 2) = sc;
+          float4* bb = reinterpret_cast<float4*>(p.bbox + ((size_t)n * hw + pix) * 8);
+          bb[0] = make_float4(f[2], f[3], f[4], f[5]);
+          bb[1] = make_float4(f[6], f[7], f[8], f[9]);
+          float4* kp = reinterpret_cast<float4*>(p.kps + ((size_t)n * hw + pix) * 20);
 #pragma unroll
-    for (int j = 0; j < CT; ++j) acc[i][j] = 0.f;
-
-  prefetch(0);
-  for (int k0 = 0; k0 < a.kpad; k0 += KC) {
-#pragma unroll
-    for (int kk = 0; kk < KC; ++kk)
-      Xs[kk][t] = (MODE == MODE_PW) ? ((k0 + kk < a.cin) ? xv[kk] * gmask : 0.f) : xv[kk];
-#pragma unroll
-    for (int i = 0; i < WL; ++i) {
-      const int idx = t + i * 128;
-      if (idx < KC * TC) (&Ws[0][0])[idx] = wv[i];
-    }
-    __syncthreads();
-    if (k0 + KC < a.kpad) prefetch(k0 + KC);
-#pragma unroll
-    for (int kk = 0; kk < KC; ++kk) {
-      const float4 xa = *reinterpret_cast<const float4*>(&Xs[kk][pg * 8]);
-      const float4 xb = *reinterpret_cast<const float4*>(&Xs[kk][pg * 8 + 4]);
-      const float x[8] = {xa.x, xa.y, xa.z, xa.w, xb.x, xb.y, xb.z, xb.w};
-      float w[CT];
-      if (CT % 4 == 0) {
-#pragma unroll
-        for (int j = 0; j < CT; j += 4) {
-          const float4 w4 = *reinterpret_cast<const float4*>(&Ws[kk][cg * CT + j]);
-          w[j] = w4.x; w[j + 1] = w4.y; w[j + 2] = w4.z; w[j + 3] = w4.w;
+          for (int i = 0; i < 5; ++i) kp[i] = make_float4(f[10 + 4 * i], f[11 + 4 * i], f[12 + 4 * i], f[13 + 4 * i]);
         }
       } else {
+        const size_t pix_off = valid ? ((size_t)(n * p.hout + oy) * p.wout + ox) * p.cout : 0;
+        const float* up = nullptr;
+        if (p.add_up && valid)
+          up = p.add_up + ((size_t)(n * (p.hout >> 1) + (oy >> 1)) * (p.wout >> 1) + (ox >> 1)) * p.cout;
+#pragma unroll 1
+        for (int c0 = 0; c0 < p.nt; c0 += 16) {
+          uint32_t v[16];
+          ld_sum16(taddr + c0, small_off, p.nbig, (uint32_t)p.nt, v);
+          if (valid) {
 #pragma unroll
-        for (int j = 0; j < CT; ++j) w[j] = Ws[kk][cg * CT + j];
+            for (int j = 0; j < 4; ++j) {
+              const int c = n0 + c0 + 4 * j;
+              if (c < p.cout) {
+                const float4 b4 = ldg4(p.bias + c);
+                float4 f = make_float4(__uint_as_float(v[4 * j]) + b4.x, __uint_as_float(v[4 * j + 1]) + b4.y,
+                                       __uint_as_float(v[4 * j + 2]) + b4.z, __uint_as_float(v[4 * j + 3]) + b4.w);
+                if (p.relu) {
+                  f.x = fmaxf(f.x, 0.f); f.y = fmaxf(f.y, 0.f); f.z = fmaxf(f.z, 0.f); f.w = fmaxf(f.w, 0.f);
+                }
+                if (up) {
+                  const float4 u = ldg4(up + c);
+                  f.x += u.x; f.y += u.y; f.z += u.z; f.w += u.w;
+                }
+                float4* o = reinterpret_cast<float4*>(p.out + pix_off + c);
+                if (p.accumulate) {
+                  const float4 e = *o;
+                  f.x += e.x; f.y += e.y; f.z += e.z; f.w += e.w;
+                }
+                *o = f;
+              }
+            }
+          }
+        }
       }
-#pragma unroll
-      for (int i = 0; i < 8; ++i)
-#pragma unroll
-        for (int j = 0; j < CT; ++j) acc[i][j] = fmaf(x[i], w[j], acc[i][j]);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[acc]);
     }
-    __syncthreads();
+  } else {
+    // ------------------------------------------------------------- A-operand gather
+    const int lw = warp - FIRST_LD_WARP;
+    const int grp = lw % LD_GROUPS;
+    const int lt = (lw / LD_GROUPS) * 32 + lane;     // 0 .. TG-1 within the group
+    const int chunk = lt & 7;                        // 16-byte chunk = 4 channels of the K block
+    const int r0 = lt >> 3;
+    const uint32_t off0 = (uint32_t)r0 * 128u + (uint32_t)((chunk ^ (r0 & 7)) << 4);   // SWIZZLE_128B
+    uint32_t it = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int m_tile = tile / p.n_tiles_n;
+      bool have = false;
+      int pix[ITEMS];
+      for (int kb = 0; kb < p.nkb; ++kb, ++it) {
+        if ((int)(it % LD_GROUPS) != grp) continue;
+        if (!have) {
+#pragma unroll
+          for (int j = 0; j < ITEMS; ++j) {
+            int n, oy, ox;
+            const bool ok = tile_pixel(p, m_tile, r0 + j * ROW_STEP, n, oy, ox);
+            pix[j] = ok ? ((n << 20) | (oy << 10) | ox) : -1;
+          }
+          have = true;
+        }
+        const int stage = it % p.stages;
+        const uint32_t phase = (it / p.stages) & 1u;
+        mbar_wait(&empty[stage], phase ^ 1u, p.err_flag);
+        uint8_t* hi = smem + stage * stage_bytes;
+        uint8_t* lo = hi + A_BYTES;
+        const int k = kb * 32 + chunk * 4;
+        if (p.mode == LD_DW) {
+          const bool kv = k < p.cin;
+          float4 w[9], b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+          for (int t = 0; t < 9; ++t) w[t] = kv ? ldg4(p.dw_w + t * p.cin + k) : make_float4(0.f, 0.f, 0.f, 0.f);
+          if (kv) b4 = ldg4(p.dw_b + k);
+#pragma unroll
+          for (int j = 0; j < ITEMS; ++j) {
+            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (kv && pix[j] >= 0) {
+              const int n = pix[j] >> 20, oy = (pix[j] >> 10) & 1023, ox = pix[j] & 1023;
+              const float* base = p.in + (size_t)n * p.hin * p.win * p.cin + k;
+              const int iy0 = oy * p.stride - 1, ix0 = ox * p.stride - 1;
+              float4 v[9];
+#pragma unroll
+              for (int r = 0; r < 3; ++r)
+#pragma unroll
+                for (int s = 0; s < 3; ++s) {
+                  const int iy = iy0 + r, ix = ix0 + s;
+                  const bool ok = iy >= 0 && iy < p.hin && ix >= 0 && ix < p.win;
+                  v[r * 3 + s] = ok ? ldg4(base + ((size_t)iy * p.win + ix) * p.cin) : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+              acc = b4;
+#pragma unroll
+              for (int t = 0; t < 9; ++t) fma4(acc, v[t], w[t]);
+              acc.x = fmaxf(acc.x, 0.f); acc.y = fmaxf(acc.y, 0.f);
+              acc.z = fmaxf(acc.z, 0.f); acc.w = fmaxf(acc.w, 0.f);
+            }
+            split_store(hi, lo, off0 + (uint32_t)(j * ROW_STEP) * 128u, acc);
+          }
+        } else if (p.mode == LD_PW) {
+          const bool kv = k < p.cin;
+          float4 v[ITEMS];
+#pragma unroll
+          for (int j = 0; j < ITEMS; ++j) {
+            v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (kv && pix[j] >= 0) {
+              const int n = pix[j] >> 20, oy = (pix[j] >> 10) & 1023, ox = pix[j] & 1023;
+              v[j] = ldg4(p.in + ((size_t)(n * p.hin + oy) * p.win + ox) * p.cin + k);
+            }
+          }
+#pragma unroll
+          for (int j = 0; j < ITEMS; ++j) split_store(hi, lo, off0 + (uint32_t)(j * ROW_STEP) * 128u, v[j]);
+        } else {
+          // dense 3x3, K index = tap * cin + c (a 16-byte chunk never straddles a tap: cin % 4 == 0)
+          const int tap = k / p.cin;
+          const int c = k - tap * p.cin;
+          const bool kv = tap < 9;
+          const int dy = tap / 3 - 1, dx = tap - (tap / 3) * 3 - 1;
+          float4 v[ITEMS];
+#pragma unroll
+          for (int j = 0; j < ITEMS; ++j) {
+            v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (kv && pix[j] >= 0) {
+              const int n = pix[j] >> 20, oy = (pix[j] >> 10) & 1023, ox = pix[j] & 1023;
+              const int iy = oy * p.stride + dy, ix = ox * p.stride + dx;
+              if (iy >= 0 && iy < p.hin && ix >= 0 && ix < p.win)
+                v[j] = ldg4(p.in + ((size_t)(n * p.hin + iy) * p.win + ix) * p.cin + c);
+            }
+          }
+#pragma unroll
+          for (int j = 0; j < ITEMS; ++j) split_store(hi, lo, off0 + (uint32_t)(j * ROW_STEP) * 128u, v[j]);
+        }
+        // generic-proxy stores -> visible to the tensor core (async proxy), then publish
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        mbar_arrive(&full[stage]);
+      }
+    }
   }
-  // ---- epilogue: this thread owns pixels g0..g0+7 (same image: hw % 8 == 0) x CT channels
-  const int g0 = blockIdx.x * TP + pg * 8;
-  if (g0 >= a.total_px) return;
-  const int n = g0 / hw;
-  const int p0 = g0 - n * hw;
-#pragma unroll
-  for (int j = 0; j < CT; ++j) {
-    const int c = c0 + cg * CT + j;
-    if (c >= a.cout) continue;
-    const float bias = __ldg(a.b + c);
-    float v[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      v[i] = acc[i][j] + bias;
-      if (a.relu) v[i] = fmaxf(v[i], 0.f);
-    }
-    if (a.head) {
-      // channel c of 30: [0,2) score (sigmoid), [2,10) bbox, [10,30) kps; anchor = p*2 + a
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const size_t p = (size_t)p0 + i;
-        if (c < 2) a.score[(size_t)n * hw * 2 + p * 2 + c] = 1.0f / (1.0f + expf(-v[i]));
-        else if (c < 10) a.bbox[(size_t)n * hw * 8 + p * 8 + (c - 2)] = v[i];
-        else a.kps[(size_t)n * hw * 20 + p * 20 + (c - 10)] = v[i];
-      }
-      continue;
-    }
-    if (a.add_up) {
-      const int uw = a.wout >> 1, uh = a.hout >> 1;
-      const float* up = a.add_up + ((size_t)n * a.cout + c) * uh * uw;
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int p = p0 + i;
-        const int y = p / a.wout, x = p - y * a.wout;
-        v[i] += __ldg(up + (size_t)(y >> 1) * uw + (x >> 1));
-      }
-    }
-    float4* o = reinterpret_cast<float4*>(a.out + ((size_t)n * a.cout + c) * hw + p0);
-    if (a.accumulate) {
-      const float4 o0 = o[0], o1 = o[1];
-      v[0] += o0.x; v[1] += o0.y; v[2] += o0.z; v[3] += o0.w;
-      v[4] += o1.x; v[5] += o1.y; v[6] += o1.z; v[7] += o1.w;
-    }
-    o[0] = make_float4(v[0], v[1], v[2], v[3]);
-    o[1] = make_float4(v[4], v[5], v[6], v[7]);
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)p.tmem_cols)
+                 : "memory");
   }
 }
 
 // ---------------------------------------------------------------------------------------
-// Depthwise 3x3 (pad 1, stride 1|2) + bias + ReLU, fp32 NCHW.  One thread = 4 horizontally
-// adjacent outputs of one channel (float4 store); memory bound.
-// grid (ceil(hout*wout/4/256), c, n).
-template <int STRIDE>
-__global__ void __launch_bounds__(256)
-dw3x3_kernel(const float* __restrict__ in, float* __restrict__ out, const float* __restrict__ w,
-             const float* __restrict__ b, int c_total, int hin, int win, int hout, int wout) {
-  const int q = blockIdx.x * blockDim.x + threadIdx.x;   // quad index within the plane
-  const int qw = wout >> 2;
-  if (q >= hout * qw) return;
-  const int c = blockIdx.y, n = blockIdx.z;
-  const int oy = q / qw, ox0 = (q - oy * qw) * 4;
-  const float* ip = in + ((size_t)n * c_total + c) * hin * win;
-  float wk[9];
-#pragma unroll
-  for (int i = 0; i < 9; ++i) wk[i] = __ldg(w + c * 9 + i);
-  const float bias = __ldg(b + c);
-  constexpr int NX = 3 * STRIDE + 3;         // input columns touched: 6 (s1) or 9 (s2)
-  const int ix0 = ox0 * STRIDE - 1;
-  float acc[4] = {bias, bias, bias, bias};
-#pragma unroll
-  for (int r = 0; r < 3; ++r) {
-    const int iy = oy * STRIDE - 1 + r;
-    const bool rok = iy >= 0 && iy < hin;
-    float v[NX];
-#pragma unroll
-    for (int x = 0; x < NX; ++x) {
-      const int ix = ix0 + x;
-      v[x] = (rok && ix >= 0 && ix < win) ? __ldg(ip + (size_t)iy * win + ix) : 0.f;
-    }
-#pragma unroll
-    for (int o = 0; o < 4; ++o)
-#pragma unroll
-      for (int s = 0; s < 3; ++s) acc[o] = fmaf(v[o * STRIDE + s], wk[r * 3 + s], acc[o]);
-  }
-  float4 res = make_float4(fmaxf(acc[0], 0.f), fmaxf(acc[1], 0.f), fmaxf(acc[2], 0.f), fmaxf(acc[3], 0.f));
-  *reinterpret_cast<float4*>(out + ((size_t)n * c_total + c) * hout * wout + (size_t)oy * wout + ox0) = res;
-}
-
-// ---------------------------------------------------------------------------------------
-// Stem: dense 3x3 stride-2 conv 3 -> 16 + bias + ReLU on the bf16 planar input produced by K1.
-// One thread = one output pixel x 16 channels; weights [27][16] broadcast from shared memory.
+// Stem: dense 3x3 stride-2 conv 3 -> 16 + bias + ReLU on the bf16 planar input produced by K1
+// (K = 27: CUDA cores; the layer is bound by its 6.5 MB / frame fp32 NHWC write).
+// One thread = one output pixel x 16 channels = one 64-byte NHWC record.
 __global__ void __launch_bounds__(256)
 stem_conv_kernel(const __nv_bfloat16* __restrict__ in, float* __restrict__ out, const float* __restrict__ w,
                  const float* __restrict__ b, int n_img) {
@@ -238,8 +483,8 @@ stem_conv_kernel(const __nv_bfloat16* __restrict__ in, float* __restrict__ out, 
   const size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (gid >= (size_t)n_img * HO * HO) return;
   const int n = (int)(gid / (HO * HO));
-  const int p = (int)(gid - (size_t)n * HO * HO);
-  const int oy = p / HO, ox = p - oy * HO;
+  const int pp = (int)(gid - (size_t)n * HO * HO);
+  const int oy = pp / HO, ox = pp - oy * HO;
   float acc[16];
 #pragma unroll
   for (int i = 0; i < 16; ++i) acc[i] = sb[i];
@@ -265,29 +510,34 @@ stem_conv_kernel(const __nv_bfloat16* __restrict__ in, float* __restrict__ out, 
         }
       }
     }
-  float* op = out + (size_t)n * 16 * HO * HO + p;
+  float4* op = reinterpret_cast<float4*>(out + gid * 16);
 #pragma unroll
-  for (int i = 0; i < 16; ++i) op[(size_t)i * HO * HO] = fmaxf(acc[i], 0.f);
+  for (int i = 0; i < 4; ++i)
+    op[i] = make_float4(fmaxf(acc[4 * i], 0.f), fmaxf(acc[4 * i + 1], 0.f), fmaxf(acc[4 * i + 2], 0.f),
+                        fmaxf(acc[4 * i + 3], 0.f));
 }
 
 }  // namespace
 
-struct PackedConv {       // device-side packed parameters of one (fused) conv
-  float* wt = nullptr;     // [kpad][cpad]
-  float* b = nullptr;      // [cpad]
-  float* wd = nullptr;     // [cin][9]   (dw-separable only)
-  float* bd = nullptr;     // [cin]
-  int cin = 0, cout = 0, cpad = 0, kdim = 0, kpad = 0, ct = 2;
+struct PackedConv {        // device-side packed parameters of one (fused) layer
+  float* wpack = nullptr;  // [2][npad_total][kpad]: tf32 hi half, then the residual lo half
+  float* bias = nullptr;   // [npad_total]
+  float* dw_w = nullptr;   // [9][cin]  (dw-separable only)
+  float* dw_b = nullptr;   // [cin]
+  CUtensorMap tmW;
+  int cin = 0, cout = 0, kdim = 0, nkb = 0, nt = 0, n_tiles_n = 1, npad_total = 0, mode = LD_PW;
 };
 
 struct DetModel {
   std::map<std::string, PackedConv> conv;
+  float* stem_w = nullptr;
+  float* stem_b = nullptr;
   std::vector<void*> allocs;
   int cap = 0;
   std::vector<void*> act_allocs;
-  // activations (fp32 NCHW)
-  float *a_stem = nullptr, *a_b0 = nullptr, *dw_tmp = nullptr;
-  std::vector<float*> a_stage;       // per dwsep block output
+  // activations (fp32 NHWC)
+  float *a_stem = nullptr, *a_b0 = nullptr;
+  std::vector<float*> a_stage;       // per dw-separable block output
   float* lat[3] = {nullptr, nullptr, nullptr};
   float* inter[3] = {nullptr, nullptr, nullptr};
   float* pout[3] = {nullptr, nullptr, nullptr};
@@ -296,25 +546,13 @@ struct DetModel {
   float* score[3] = {nullptr, nullptr, nullptr};
   float* bbox[3] = {nullptr, nullptr, nullptr};
   float* kps[3] = {nullptr, nullptr, nullptr};
+  int* err_flag = nullptr;
+  int num_sms = 148;
 };
 
 namespace {
 
 const int kStages[4][2] = {{2, 40}, {3, 72}, {2, 152}, {6, 288}};
-
-// output-channel thread tile: tile width is 8*CT channels
-int pick_ct(int cout) {
-  switch (cout) {
-    case 16: return 2;
-    case 30: return 4;
-    case 40: return 5;
-    case 64: return 8;
-    case 72: return 9;
-    case 152: return 10;
-    case 288: return 9;
-    default: return 4;
-  }
-}
 
 float* upload(DetModel* m, const std::vector<float>& h) {
   float* d = nullptr;
@@ -324,28 +562,47 @@ float* upload(DetModel* m, const std::vector<float>& h) {
   return d;
 }
 
-// w: [cout][kdim] row-major (OIHW flattened) -> transposed, zero-padded [kpad][cpad]
-bool pack(DetModel* m, PackedConv& pc, const std::vector<float>& w, const std::vector<float>& b, int cout,
-          int kdim, int cin, bool tap_major = false) {
+// round-to-nearest (ties away) to the 10-bit tf32 mantissa, like cvt.rna.tf32.f32
+float tf32_rna_host(float x) {
+  uint32_t u;
+  memcpy(&u, &x, 4);
+  if ((u & 0x7f800000u) != 0x7f800000u) u += 0x1000u;
+  u &= 0xffffe000u;
+  memcpy(&x, &u, 4);
+  return x;
+}
+
+// w: [cout][cin*ks*ks] (OIHW flattened).  GEMM K order: channel for 1x1, tap*cin + c for 3x3.
+bool pack(DetModel* m, PackedConv& pc, const std::vector<float>& w, const std::vector<float>& b, int cout, int cin,
+          int ks, int mode) {
   pc.cin = cin;
   pc.cout = cout;
-  pc.kdim = kdim;
-  pc.ct = pick_ct(cout);
-  const int tc = 8 * pc.ct;
-  pc.cpad = (cout + tc - 1) / tc * tc;
-  pc.kpad = (kdim + KC - 1) / KC * KC;
-  std::vector<float> wt((size_t)pc.kpad * pc.cpad, 0.f), bp(pc.cpad, 0.f);
-  for (int c = 0; c < cout; ++c) {
-    for (int k = 0; k < kdim; ++k) {
-      // source order is (ci, tap); tap-major kernels want row = tap*cin + ci
-      const int row = tap_major ? (k % 9) * cin + k / 9 : k;
-      wt[(size_t)row * pc.cpad + c] = w[(size_t)c * kdim + k];
-    }
-    bp[c] = b[c];
+  pc.mode = mode;
+  pc.kdim = cin * ks * ks;
+  pc.nkb = (pc.kdim + 31) / 32;
+  const int kpad = pc.nkb * 32;
+  pc.npad_total = (cout + 15) / 16 * 16;
+  pc.n_tiles_n = pc.npad_total > 256 ? 2 : 1;
+  pc.nt = pc.npad_total / pc.n_tiles_n;
+  if (pc.nt % 16 != 0 || cin % 4 != 0) return false;
+  std::vector<float> wp((size_t)2 * pc.npad_total * kpad, 0.f), bp(pc.npad_total, 0.f);
+  const int taps = ks * ks;
+  for (int co = 0; co < cout; ++co) {
+    for (int ci = 0; ci < cin; ++ci)
+      for (int t = 0; t < taps; ++t) {
+        const float v = w[((size_t)co * cin + ci) * taps + t];
+        const float h = tf32_rna_host(v);
+        const size_t kk = (size_t)t * cin + ci;
+        wp[(size_t)co * kpad + kk] = h;
+        wp[((size_t)pc.npad_total + co) * kpad + kk] = v - h;
+      }
+    bp[co] = b[co];
   }
-  pc.wt = upload(m, wt);
-  pc.b = upload(m, bp);
-  return pc.wt && pc.b;
+  pc.wpack = upload(m, wp);
+  pc.bias = upload(m, bp);
+  if (!pc.wpack || !pc.bias) return false;
+  return tc_make_map_2d_f32(&pc.tmW, pc.wpack, (uint64_t)2 * pc.npad_total, (uint64_t)kpad, (uint64_t)kpad,
+                            (uint32_t)pc.nt);
 }
 
 float* act_alloc(DetModel* m, size_t elems) {
@@ -375,7 +632,6 @@ int det_build_acts(fr_ctx* ctx, int cap) {
   };
   m->a_stem = A((size_t)16 * 320 * 320);
   m->a_b0 = A((size_t)16 * 320 * 320);
-  m->dw_tmp = A((size_t)16 * 320 * 320);   // largest depthwise output (b0)
   int hw = 320;
   for (int s = 0; s < 4; ++s)
     for (int b = 0; b < kStages[s][0]; ++b) {
@@ -402,34 +658,68 @@ int det_build_acts(fr_ctx* ctx, int cap) {
   return FR_OK;
 }
 
-template <int CT, int MODE>
-int launch_tile(fr_ctx* ctx, const ConvArgs& a) {
-  dim3 grid(ceil_div(a.total_px, TP), a.cpad / (8 * CT));
-  tile_conv_kernel<CT, MODE><<<grid, 128, 0, ctx->stream>>>(a);
-  ctx->launches++;
-  FR_CUDA_OK(ctx, cudaGetLastError());
-  return FR_OK;
-}
+struct LayerIO {
+  const float* in = nullptr;
+  float* out = nullptr;
+  int hin = 0, stride = 1, relu = 0, accumulate = 0;
+  const float* add_up = nullptr;
+  int head = -1;
+};
 
-template <int MODE>
-int launch_by_ct(fr_ctx* ctx, const ConvArgs& a, int ct) {
-  switch (ct) {
-    case 2: return launch_tile<2, MODE>(ctx, a);
-    case 4: return launch_tile<4, MODE>(ctx, a);
-    case 5: return launch_tile<5, MODE>(ctx, a);
-    case 8: return launch_tile<8, MODE>(ctx, a);
-    case 9: return launch_tile<9, MODE>(ctx, a);
-    case 10: return launch_tile<10, MODE>(ctx, a);
-    default: return fr_fail(ctx, FR_ERR_UNSUPPORTED, "unsupported channel tile");
+int launch_layer(fr_ctx* ctx, const PackedConv& pc, const LayerIO& io, int n) {
+  DetModel* m = ctx->det;
+  SepParams p;
+  memset(&p, 0, sizeof(p));
+  p.in = io.in;
+  p.out = io.out;
+  p.dw_w = pc.dw_w;
+  p.dw_b = pc.dw_b;
+  p.bias = pc.bias;
+  p.add_up = io.add_up;
+  p.cin = pc.cin;
+  p.cout = pc.cout;
+  p.kdim = pc.kdim;
+  p.hin = p.win = io.hin;
+  p.hout = p.wout = io.hin / io.stride;
+  p.stride = io.stride;
+  p.mode = pc.mode;
+  p.relu = io.relu;
+  p.accumulate = io.accumulate;
+  p.epi = io.head >= 0 ? EPI_HEAD : EPI_STD;
+  if (io.head >= 0) {
+    p.score = m->score[io.head];
+    p.bbox = m->bbox[io.head];
+    p.kps = m->kps[io.head];
   }
-}
-
-int launch_dw(fr_ctx* ctx, const float* in, float* out, const float* w, const float* b, int c, int hin,
-              int stride, int n) {
-  const int hout = hin / stride;
-  dim3 grid(ceil_div(hout * (hout / 4), 256), c, n);
-  if (stride == 1) dw3x3_kernel<1><<<grid, 256, 0, ctx->stream>>>(in, out, w, b, c, hin, hin, hout, hout);
-  else dw3x3_kernel<2><<<grid, 256, 0, ctx->stream>>>(in, out, w, b, c, hin, hin, hout, hout);
+  p.nkb = pc.nkb;
+  p.nt = pc.nt;
+  p.n_tiles_n = pc.n_tiles_n;
+  p.npad_total = pc.npad_total;
+  p.total_px = n * p.hout * p.wout;
+  if (p.wout % 16 == 0 && p.hout % 8 == 0) {
+    p.tiles_x = p.wout / 16;
+    p.tiles_y = p.hout / 8;
+    p.num_m_tiles = n * p.tiles_x * p.tiles_y;
+  } else {
+    p.num_m_tiles = ceil_div(p.total_px, TM);
+  }
+  const int stage_bytes = 2 * A_BYTES + 2 * pc.nt * 128;
+  const int budget = 227 * 1024 - 1024 - 512;
+  p.stages = std::min(MAX_STAGES, budget / stage_bytes);
+  if (p.stages < 2) return fr_fail(ctx, FR_ERR_UNSUPPORTED, "scrfd layer does not fit shared memory");
+  static const int nbig_env = getenv("FR_SCRFD_NBIG") ? atoi(getenv("FR_SCRFD_NBIG")) : 2;
+  p.nbig = (nbig_env == 1 || pc.kdim <= 16) ? 1 : 2;
+  const int slot = (p.nbig + 1) * pc.nt;
+  if (slot > 512) return fr_fail(ctx, FR_ERR_UNSUPPORTED, "scrfd layer does not fit tensor memory");
+  p.acc_stages = 2 * slot <= 512 ? 2 : 1;
+  int cols = 32;
+  while (cols < p.acc_stages * slot) cols *= 2;
+  p.tmem_cols = cols;
+  p.err_flag = m->err_flag;
+  const int smem = p.stages * stage_bytes + 1024 + 512;
+  const int total_tiles = p.num_m_tiles * p.n_tiles_n;
+  const int grid = std::min(total_tiles, m->num_sms);
+  sep_gemm_kernel<<<grid, THREADS, smem, ctx->stream>>>(pc.tmW, p);
   ctx->launches++;
   FR_CUDA_OK(ctx, cudaGetLastError());
   return FR_OK;
@@ -444,27 +734,29 @@ int det_model_create(fr_ctx* ctx, const fr_weights* w) {
   auto dense = [&](const std::string& name) {   // conv (3x3 or 1x1) as a [cout][cin*k*k] GEMM
     const fr_tensor& tw = w->at(name + ".w");
     const int cout = (int)tw.dims[0], cin = (int)tw.dims[1], k = (int)tw.dims[2];
-    ok = ok && pack(m.get(), m->conv[name], tw.data, w->at(name + ".b").data, cout, cin * k * k, cin,
-                    k == 3 && cin % KC == 0);
+    ok = ok && pack(m.get(), m->conv[name], tw.data, w->at(name + ".b").data, cout, cin, k, k == 3 ? LD_IM2COL : LD_PW);
   };
-  auto dwsep = [&](const std::string& name) {   // dw 3x3 (+ReLU) fused in front of the 1x1
+  auto dwsep = [&](const std::string& name) {   // dw 3x3 + ReLU evaluated inside the 1x1's operand gather
     const fr_tensor& pw = w->at(name + ".pw.w");
     const int cout = (int)pw.dims[0], cin = (int)pw.dims[1];
     PackedConv& pc = m->conv[name];
-    ok = ok && pack(m.get(), pc, pw.data, w->at(name + ".pw.b").data, cout, cin, cin);
-    pc.wd = upload(m.get(), w->at(name + ".dw.w").data);
-    pc.bd = upload(m.get(), w->at(name + ".dw.b").data);
-    ok = ok && pc.wd && pc.bd;
+    ok = ok && pack(m.get(), pc, pw.data, w->at(name + ".pw.b").data, cout, cin, 1, LD_DW);
+    const std::vector<float>& dw = w->at(name + ".dw.w").data;   // [cin][1][3][3] -> [9][cin]
+    std::vector<float> dwt((size_t)9 * cin);
+    for (int c = 0; c < cin; ++c)
+      for (int t = 0; t < 9; ++t) dwt[(size_t)t * cin + c] = dw[(size_t)c * 9 + t];
+    pc.dw_w = upload(m.get(), dwt);
+    pc.dw_b = upload(m.get(), w->at(name + ".dw.b").data);
+    ok = ok && pc.dw_w && pc.dw_b;
   };
   {
     const fr_tensor& tw = w->at("stem.w");   // [16][3][3][3] -> [27][16]
     std::vector<float> sw(27 * 16);
     for (int co = 0; co < 16; ++co)
       for (int k = 0; k < 27; ++k) sw[k * 16 + co] = tw.data[co * 27 + k];
-    PackedConv& pc = m->conv["stem"];
-    pc.wt = upload(m.get(), sw);
-    pc.b = upload(m.get(), w->at("stem.b").data);
-    ok = ok && pc.wt && pc.b;
+    m->stem_w = upload(m.get(), sw);
+    m->stem_b = upload(m.get(), w->at("stem.b").data);
+    ok = ok && m->stem_w && m->stem_b;
   }
   dwsep("b0");
   for (int s = 0; s < 4; ++s)
@@ -485,11 +777,23 @@ int det_model_create(fr_ctx* ctx, const fr_weights* w) {
       fw.insert(fw.end(), tw.data.begin(), tw.data.end());
       fb.insert(fb.end(), tb.data.begin(), tb.data.end());
     }
-    ok = ok && pack(m.get(), m->conv[h + ".out"], fw, fb, 30, 64 * 9, 64, true);
+    ok = ok && pack(m.get(), m->conv[h + ".out"], fw, fb, 30, 64, 3, LD_IM2COL);
+  }
+  if (ok) {
+    ok = cudaMalloc(&m->err_flag, sizeof(int)) == cudaSuccess;
+    if (ok) {
+      cudaMemset(m->err_flag, 0, sizeof(int));
+      m->allocs.push_back(m->err_flag);
+    }
+  }
+  if (ok) {
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, ctx->device) == cudaSuccess) m->num_sms = prop.multiProcessorCount;
+    ok = cudaFuncSetAttribute(sep_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) == cudaSuccess;
   }
   if (!ok) {
     for (void* p : m->allocs) cudaFree(p);
-    return fr_fail(ctx, FR_ERR_CUDA, "det weight upload failed");
+    return fr_fail(ctx, FR_ERR_CUDA, "det weight upload / tensor map creation failed");
   }
   ctx->det = m.release();
   return FR_OK;
@@ -511,31 +815,18 @@ int det_forward(fr_ctx* ctx, const __nv_bfloat16* d_in_chw, int n, HeadPtrs* hea
   int cap = 1;
   while (cap < n) cap *= 2;
   FR_CHECK(det_build_acts(ctx, cap));
-  auto args = [&](const PackedConv& pc, const void* in, float* out, int hin, int stride) {
-    ConvArgs a;
-    memset(&a, 0, sizeof(a));
-    a.in = in; a.out = out;
-    a.wt = pc.wt; a.b = pc.b;
-    a.cin = pc.cin; a.cout = pc.cout; a.cpad = pc.cpad; a.kdim = pc.kdim; a.kpad = pc.kpad;
-    a.hin = a.win = hin; a.hout = a.wout = hin / stride; a.stride = stride;
-    a.total_px = n * a.hout * a.wout;
-    return a;
-  };
-  // stem: 3x3 s2, 3 -> 16, ReLU (bf16 planar input from K1)
+  // stem: 3x3 s2, 3 -> 16, ReLU (bf16 planar input from K1) -> fp32 NHWC
   {
-    const PackedConv& pc = m->conv.at("stem");
     const size_t total = (size_t)n * (DET / 2) * (DET / 2);
-    stem_conv_kernel<<<(unsigned)((total + 255) / 256), 256, 0, ctx->stream>>>(d_in_chw, m->a_stem, pc.wt, pc.b, n);
+    stem_conv_kernel<<<(unsigned)((total + 255) / 256), 256, 0, ctx->stream>>>(d_in_chw, m->a_stem, m->stem_w,
+                                                                                m->stem_b, n);
     ctx->launches++;
     FR_CUDA_OK(ctx, cudaGetLastError());
   }
-  // depthwise-separable block: dw3x3(stride)+ReLU into the scratch plane set, then 1x1+ReLU
   auto dwsep = [&](const std::string& name, const float* in, float* out, int hin, int stride) -> int {
-    const PackedConv& pc = m->conv.at(name);
-    FR_CHECK(launch_dw(ctx, in, m->dw_tmp, pc.wd, pc.bd, pc.cin, hin, stride, n));
-    ConvArgs a = args(pc, m->dw_tmp, out, hin / stride, 1);
-    a.relu = 1;
-    return launch_by_ct<MODE_PW>(ctx, a, pc.ct);
+    LayerIO io;
+    io.in = in; io.out = out; io.hin = hin; io.stride = stride; io.relu = 1;
+    return launch_layer(ctx, m->conv.at(name), io, n);
   };
   FR_CHECK(dwsep("b0", m->a_stem, m->a_b0, 320, 1));
   const float* cur = m->a_b0;
@@ -551,19 +842,18 @@ int det_forward(fr_ctx* ctx, const __nv_bfloat16* d_in_chw, int n, HeadPtrs* hea
     if (s >= 1) feats[s - 1] = cur;
   }
   const int fh[3] = {80, 40, 20};
-  // laterals (1x1, no activation) with the top-down nearest-2x add fused in
+  // laterals (1x1, no activation) with the top-down nearest-2x add fused into the epilogue
   for (int i = 2; i >= 0; --i) {
-    const PackedConv& pc = m->conv.at("lat" + std::to_string(i));
-    ConvArgs a = args(pc, feats[i], m->lat[i], fh[i], 1);
-    a.add_up = i < 2 ? m->lat[i + 1] : nullptr;
-    FR_CHECK((launch_by_ct<MODE_PW>(ctx, a, pc.ct)));
+    LayerIO io;
+    io.in = feats[i]; io.out = m->lat[i]; io.hin = fh[i];
+    io.add_up = i < 2 ? m->lat[i + 1] : nullptr;
+    FR_CHECK(launch_layer(ctx, m->conv.at("lat" + std::to_string(i)), io, n));
   }
   auto conv3 = [&](const std::string& name, const float* in, float* out, int hin, int stride,
                    int accumulate) -> int {
-    const PackedConv& pc = m->conv.at(name);
-    ConvArgs a = args(pc, in, out, hin, stride);
-    a.accumulate = accumulate;
-    return launch_by_ct<MODE_IM2COL>(ctx, a, pc.ct);
+    LayerIO io;
+    io.in = in; io.out = out; io.hin = hin; io.stride = stride; io.accumulate = accumulate;
+    return launch_layer(ctx, m->conv.at(name), io, n);
   };
   for (int i = 0; i < 3; ++i) FR_CHECK(conv3("fpn" + std::to_string(i), m->lat[i], m->inter[i], fh[i], 1, 0));
   for (int i = 0; i < 2; ++i)
@@ -575,13 +865,33 @@ int det_forward(fr_ctx* ctx, const __nv_bfloat16* d_in_chw, int n, HeadPtrs* hea
     const std::string h = "h" + std::to_string(i);
     FR_CHECK(dwsep(h + ".t0", outs[i], m->tw0[i], fh[i], 1));
     FR_CHECK(dwsep(h + ".t1", m->tw0[i], m->tw1[i], fh[i], 1));
-    const PackedConv& pc = m->conv.at(h + ".out");
-    ConvArgs a = args(pc, m->tw1[i], nullptr, fh[i], 1);
-    a.head = 1; a.score = m->score[i]; a.bbox = m->bbox[i]; a.kps = m->kps[i];
-    FR_CHECK((launch_by_ct<MODE_IM2COL>(ctx, a, pc.ct)));
+    LayerIO io;
+    io.in = m->tw1[i]; io.hin = fh[i]; io.head = i;
+    FR_CHECK(launch_layer(ctx, m->conv.at(h + ".out"), io, n));
     heads->score[i] = m->score[i];
     heads->bbox[i] = m->bbox[i];
     heads->kps[i] = m->kps[i];
   }
+  return FR_OK;
+}
+
+// Test hook: copy one intermediate activation (fp32 NHWC) of the last det_forward to the host.
+// tap: 0 stem, 1 b0, 2..14 backbone blocks, 15..17 lat, 18..20 inter, 21..22 pout[1..2],
+// 23..25 head tower 0, 26..28 head tower 1.
+int det_tap(fr_ctx* ctx, int tap, int n, float* h_out, size_t out_elems) {
+  DetModel* m = ctx->det;
+  if (!m || m->cap < n) return fr_fail(ctx, FR_ERR_NOT_LOADED, "no detector activations");
+  const float* src = nullptr;
+  if (tap == 0) src = m->a_stem;
+  else if (tap == 1) src = m->a_b0;
+  else if (tap >= 2 && tap < 15) src = m->a_stage[tap - 2];
+  else if (tap < 18) src = m->lat[tap - 15];
+  else if (tap < 21) src = m->inter[tap - 18];
+  else if (tap < 23) src = m->pout[tap - 20];
+  else if (tap < 26) src = m->tw0[tap - 23];
+  else if (tap < 29) src = m->tw1[tap - 26];
+  if (!src) return fr_fail(ctx, FR_ERR_INVALID_ARG, "bad tap");
+  FR_CUDA_OK(ctx, cudaMemcpyAsync(h_out, src, out_elems * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+  FR_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
   return FR_OK;
 }

@@ -205,6 +205,10 @@ FR_API int fr_iresnet_forward(fr_ctx* ctx, const float* chw, int n, float* out_r
 /* Activation tap after block `tap` of the last IResNet forward (0 = stem, 1..24 = blocks),
  * returned as fp32 NCHW (host). */
 FR_API int fr_iresnet_tap(fr_ctx* ctx, int tap, int n, float* out, size_t out_elems);
+/* Activation tap of the last SCRFD forward, returned as fp32 NHWC (host).  tap: 0 stem, 1 b0,
+ * 2..14 backbone blocks, 15..17 laterals, 18..20 fpn/inter, 21..22 pafpn outs of strides 16/32,
+ * 23..25 / 26..28 head towers. */
+FR_API int fr_scrfd_tap(fr_ctx* ctx, int tap, int n, float* out, size_t out_elems);
 /* R4: L2 normalise rows (src/face_recognizer.cpp:306-318). */
 FR_API int fr_l2_normalize(fr_ctx* ctx, const float* in, int n, int dim, int memspace, float* out);
 /* Unit-test hook for the tcgen05 implicit-GEMM conv: x NCHW fp32, w OIHW fp32 (3x3 pad 1 or

@@ -86,30 +86,42 @@ def _dwsep(w, name, x, stride):
 
 
 @torch.no_grad()
-def scrfd_forward(w: Dict[str, np.ndarray], x: torch.Tensor):
+def scrfd_forward(w: Dict[str, np.ndarray], x: torch.Tensor, return_taps: bool = False):
     """x: [B,3,H,W] fp32 RGB in [-1,1].  Returns the 9 head tensors in the
     order/layout of the buffalo export, batched: scores [B,N_s,1], bbox
     [B,N_s,4], kps [B,N_s,10] for strides 8,16,32 (anchor index =
-    (gy*W_s+gx)*2+a; distances/offsets in stride units; sigmoid on scores)."""
+    (gy*W_s+gx)*2+a; distances/offsets in stride units; sigmoid on scores).
+    With return_taps also a list of the intermediate activations (NCHW) in the
+    order of the C-ABI test hook fr_scrfd_tap."""
+    taps = []
     y = _conv(w, "stem", x, stride=2, relu=True)
+    taps.append(y)
     y = _dwsep(w, "b0", y, 1)
+    taps.append(y)
     feats = []
     for si, (nb, _) in enumerate(DET_STAGES):
         for bi in range(nb):
             y = _dwsep(w, f"s{si}.{bi}", y, 2 if bi == 0 else 1)
+            taps.append(y)
         if si >= 1:
             feats.append(y)
     lat = [_conv(w, f"lat{i}", f) for i, f in enumerate(feats)]
     for i in (2, 1):
         lat[i - 1] = lat[i - 1] + F.interpolate(lat[i], scale_factor=2, mode="nearest")
+    taps += lat
     inter = [_conv(w, f"fpn{i}", lat[i]) for i in range(3)]
     for i in range(2):
         inter[i + 1] = inter[i + 1] + _conv(w, f"down{i}", inter[i], stride=2)
+    taps += inter
     outs = [inter[0]] + [_conv(w, f"pafpn{i - 1}", inter[i]) for i in (1, 2)]
+    taps += outs[1:]
     scores, bboxes, kpss = [], [], []
+    t0s, t1s = [], []
     for i, f in enumerate(outs):
         t = _dwsep(w, f"h{i}.t0", f, 1)
+        t0s.append(t)
         t = _dwsep(w, f"h{i}.t1", t, 1)
+        t1s.append(t)
         B = t.shape[0]
         cls = torch.sigmoid(_conv(w, f"h{i}.cls", t)).permute(0, 2, 3, 1).reshape(B, -1, 1)
         reg = _conv(w, f"h{i}.reg", t).permute(0, 2, 3, 1).reshape(B, -1, 4)
@@ -117,6 +129,9 @@ def scrfd_forward(w: Dict[str, np.ndarray], x: torch.Tensor):
         scores.append(cls)
         bboxes.append(reg)
         kpss.append(kps)
+    taps += t0s + t1s
+    if return_taps:
+        return scores + bboxes + kpss, taps
     return scores + bboxes + kpss
 
 

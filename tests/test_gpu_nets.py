@@ -2,9 +2,10 @@
 
 K6/K7 (IResNet-50, bf16 tensor cores, fp32 accumulate): cosine >= 0.999 vs the torch fp32
 oracle on shared weights (north_star tolerance), per-block taps within bf16 error.
-K2 (SCRFD, fp32 CUDA cores): heads within 1e-3 absolute (boxes are in stride units <= 32 px
-=> well inside the 1e-3 px budget after decode at fp32; the decode stage itself is bit-exact
-given identical heads, tests/test_gpu_stages.py)."""
+K2 (SCRFD, tcgen05 tf32 three-term split = fp32-grade products): bbox / kps heads within
+1e-3 px after decode (error in stride units x stride), every intermediate activation within
+2e-5 of its range; the decode stage itself is bit-exact given identical
+heads (tests/test_gpu_stages.py)."""
 import numpy as np
 import pytest
 import torch
@@ -105,11 +106,37 @@ def test_k6_embed_aligned_batch_cosine_and_batch_invariance(ctx, rec_wdict):
 
 
 def test_k2_scrfd_heads_vs_oracle(ctx, det_wdict):
+    """tcgen05 tf32 three-term split vs torch fp32: every activation tap and all 9 heads.  The
+    bar is north_star's: boxes and landmarks within 1e-3 px after decode, i.e. the bbox / kps
+    heads (stride units) within 1e-3 / stride; scores within 1e-5."""
     rng = np.random.default_rng(31)
-    x = ((rng.integers(0, 256, (2, 3, 640, 640)).astype(np.float32)) - 127.5) / 128
+    n = 3   # odd batch: the 40^2 / 20^2 maps end in a partial 128-pixel tile
+    x = ((rng.integers(0, 256, (n, 3, 640, 640)).astype(np.float32)) - 127.5) / 128
     got = ctx.scrfd_forward(x)
-    ref = nets.scrfd_forward(det_wdict, torch.from_numpy(x))
+    ref, taps = nets.scrfd_forward(det_wdict, torch.from_numpy(x), return_taps=True)
+    worst = []
+    for ti, t in enumerate(taps):
+        t = t.numpy()
+        g = ctx.scrfd_tap(ti, n, t.shape[1:])
+        err = float(np.abs(g - t).max() / (np.abs(t).max() + 1e-12))
+        worst.append((ti, err))
+    bad = [w for w in worst if not w[1] < 2e-5]
+    assert not bad, (bad[:6], worst)
+    errs = []
     for i, (g, r) in enumerate(zip(got, ref)):
         r = r.numpy()
         assert g.shape == r.shape
-        assert np.abs(g - r).max() < 1e-3, (i, float(np.abs(g - r).max()))
+        errs.append(float(np.abs(g - r).max()))
+    print("scrfd head max abs err:", errs, "tap rel err:", worst)
+    assert max(errs[:3]) < 1e-5, errs          # scores (sigmoid outputs)
+    px = [e * s for e, s in zip(errs[3:], (8, 16, 32, 8, 16, 32))]
+    assert max(px) < 1e-3, px                  # bbox / kps error in pixels after decode
+
+
+def test_k2_scrfd_batch_invariance(ctx):
+    rng = np.random.default_rng(32)
+    x = ((rng.integers(0, 256, (5, 3, 640, 640)).astype(np.float32)) - 127.5) / 128
+    all5 = ctx.scrfd_forward(x)
+    one = ctx.scrfd_forward(x[3:4])
+    for a, b in zip(all5, one):
+        assert np.array_equal(a[3], b[0])   # per-frame result independent of the batch around it
