@@ -72,6 +72,22 @@ bool tc_make_map_2d_f32(CUtensorMap* map, const void* base, uint64_t rows, uint6
   return r == CUDA_SUCCESS;
 }
 
+// 3-D fp32 tensor map over an NHWC activation with the image rows merged: dims (C, W, N*H),
+// box (box_c, box_w, box_rows), no swizzle, out-of-range elements read as zero (conv padding).
+bool tc_make_map_3d_f32(CUtensorMap* map, const void* base, uint64_t c, uint64_t w, uint64_t rows,
+                        uint32_t box_c, uint32_t box_w, uint32_t box_rows) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return false;
+  cuuint64_t dims[3] = {c, w, rows};
+  cuuint64_t strides[2] = {c * 4, w * c * 4};
+  cuuint32_t box[3] = {box_c, box_w, box_rows};
+  cuuint32_t es[3] = {1, 1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void*>(base), dims, strides,
+                  box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
+}
+
 struct ConvLaunch {
   CUtensorMap a0, a1, b0, b1;
   CUtensorMap a_halo;      // halo mode: box = (a_rows / a_boxes) x 64

@@ -10,17 +10,24 @@
 // accumulated in fp32 in TMEM -- fp32-grade results at tensor-core rate.
 //
 // One kernel (`sep_gemm_kernel`) serves all 33 GEMM-shaped layers.  Activations are fp32 NHWC
-// (K = channels contiguous).  Per 128-pixel tile and per 32-channel K block:
-//   loader warps (8, two groups working on alternating pipeline stages): gather the A operand
-//       straight from global memory -- plain (1x1), im2col (dense 3x3) or with the depthwise
-//       3x3 + bias + ReLU evaluated on the fly (the depthwise result never exists in HBM) --
-//       split it into tf32 hi/lo and store both as K-major SWIZZLE_128B tiles in shared memory,
-//       then fence.proxy.async + mbarrier arrive;
-//   warp 0 : TMA of the (host-pre-split) hi/lo weight tiles into the same stage;
-//   warp 1 : one lane issues 3 x tcgen05.mma.kind::tf32 (M=128, N=16..160, K=8) per K step;
-//   warps 2-5: epilogue, tcgen05.ld -> bias / ReLU / top-down upsample-add / accumulate ->
-//       fp32 NHWC float4 stores, or the anchor-major score (sigmoid) / bbox / kps scatter.
-// TMEM accumulators are double buffered, so gather, MMA and epilogue of consecutive tiles overlap.
+// (K = channels contiguous).  An output tile is TH x TW pixels (8x16, or 6x20 on the 40^2 /
+// 20^2 maps; MMA M = 128 rows) and K is consumed in blocks of KC channels (32, or 16):
+//   warp 0   : TMA (3-D tiled map [C, W, N*H], OOB zero fill = the conv padding) of the input
+//              halo box ((TH-1)*stride+3) x ((TW-1)*stride+3) x KC into an input ring;
+//   warps 7-14 (converters): build the A operand from that box in shared memory -- the
+//              depthwise 3x3 + bias + ReLU evaluated on the fly with a sliding register window
+//              (the depthwise result never exists in HBM), or an im2col tap of a dense 3x3,
+//              or the plain 1x1 input -- split it into tf32 hi/lo and store both as K-major
+//              SWIZZLE_128B tiles; fence.proxy.async + mbarrier arrive;
+//   warp 6   : TMA of the (host-pre-split) hi/lo weight tiles into the same A/B stage;
+//   warp 1   : one lane issues 3 x tcgen05.mma.kind::tf32 (M=128, N=16..160, K=8) per K step;
+//   warps 2-5: epilogue, tcgen05.ld -> sum of the partial accumulators -> bias / ReLU /
+//              top-down upsample-add / accumulate -> fp32 NHWC float4 stores, or the
+//              anchor-major score (sigmoid) / bbox / kps records.
+// The tensor core truncates when it adds each K=8 product group into the fp32 accumulator
+// (~2^-24 |D| bias per MMA, measured: 8e-5 at the kps head with one accumulator), so the two
+// cross terms get their own accumulator and the hi*hi products alternate between two; the
+// epilogue adds the partial sums with round-to-nearest (measured 2e-5 = 3.4e-4 px).
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
@@ -30,6 +37,8 @@
 
 bool tc_make_map_2d_f32(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols,
                         uint64_t pitch_elems, uint32_t box_rows);   // k_iresnet.cu
+bool tc_make_map_3d_f32(CUtensorMap* map, const void* base, uint64_t c, uint64_t w, uint64_t rows,
+                        uint32_t box_c, uint32_t box_w, uint32_t box_rows);   // k_iresnet.cu
 
 namespace {
 
@@ -45,23 +54,17 @@ using tc::tc_fence_before;
 using tc::tma_load_2d;
 
 constexpr int DET = FR_DET_SIZE;
-constexpr int TM = 128;                 // pixels per tile (MMA M)
+constexpr int TM = 128;                 // MMA M (tile rows; TH*TW of them are pixels)
 constexpr int A_BYTES = TM * 128;       // one 128 x 32 fp32 operand tile
-constexpr int MAX_STAGES = 6;
-constexpr int LD_GROUPS = 2;            // loader groups, working on alternating stages
-constexpr int LD_WARPS = 8;
-constexpr int TG = LD_WARPS * 32 / LD_GROUPS;   // threads per loader group
-constexpr int ITEMS = TM * 8 / TG;              // (row, 16-byte chunk) items per thread per K block
-constexpr int ROW_STEP = TG / 8;
-constexpr int FIRST_LD_WARP = 6;
-constexpr int THREADS = (FIRST_LD_WARP + LD_WARPS) * 32;
-static_assert(ROW_STEP % 8 == 0, "row & 7 must be constant per thread");
+constexpr int MAX_STAGES = 4;
+constexpr int CV_WARPS = 8;             // converter warps
+constexpr int FIRST_CV_WARP = 7;        // 0 input TMA, 1 MMA, 2-5 epilogue, 6 weight TMA
+constexpr int THREADS = (FIRST_CV_WARP + CV_WARPS) * 32;
 
 enum { LD_PW = 0, LD_DW = 1, LD_IM2COL = 2 };
 enum { EPI_STD = 0, EPI_HEAD = 1 };
 
 struct SepParams {
-  const float* in;      // fp32 NHWC [n][hin][win][cin]
   float* out;           // fp32 NHWC [n][hout][wout][cout]
   const float* dw_w;    // [9][cin] depthwise weights, tap major
   const float* dw_b;    // [cin]
@@ -70,17 +73,24 @@ struct SepParams {
   float* score;
   float* bbox;
   float* kps;
-  int cin, cout, kdim;
-  int hin, win, hout, wout, stride;
+  int cin, cout;
+  int hin, hout, wout, stride;
+  int rows_out;         // n * hout (image rows are merged into one axis)
   int mode, epi, relu, accumulate;
-  int nkb;              // 32-wide K blocks
+  int kc;               // channels per input box / K block (16 or 32)
+  int n_in;             // input boxes (channel blocks) per tile
+  int taps;             // A K-blocks built from one input box: 1 (1x1, depthwise) or 9 (dense 3x3)
   int nt;               // MMA N (per N tile)
   int n_tiles_n;
   int npad_total;       // rows of the hi half of the packed weights
-  int total_px;         // n * hout * wout
-  int tiles_x, tiles_y; // 8 x 16 spatial tiles per image (0 = flattened pixel order)
+  int th, tw;           // output tile = th x tw pixels; tile row = ty*tw + tx
+  int tiles_x;
+  uint32_t tiles_x_magic, hout_magic;   // ceil(2^32 / d) for exact small-range division (0: d == 1)
+  int n_shift;          // log2(n_tiles_n)
   int num_m_tiles;
-  int stages;
+  int bw, bh, halo;     // input box (pixels) and its halo (1 for 3x3 stencils, 0 for 1x1)
+  int in_bytes;         // bytes per input stage (rounded up to 1024)
+  int s_in, s_ab;       // ring depths
   int tmem_cols;
   int nbig;             // hi*hi accumulators per tile (k steps alternate between them)
   int acc_stages;       // 2 = TMEM double buffered, 1 = single
@@ -88,11 +98,36 @@ struct SepParams {
 };
 
 __device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+__device__ __forceinline__ float4 lds4(const uint8_t* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ float4 zero4() { return make_float4(0.f, 0.f, 0.f, 0.f); }
 
 __device__ __forceinline__ float tf32_rna(float x) {
   uint32_t u;
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
   return __uint_as_float(u);
+}
+
+// x / d for d >= 1 and x * d < 2^32, with m = ceil(2^32 / d) (m == 0 encodes d == 1)
+__device__ __forceinline__ int fastdiv(int x, uint32_t m) { return m ? (int)__umulhi((uint32_t)x, m) : x; }
+
+struct TileCoord {
+  int n_tile, rb, txi, gy0, y0;
+};
+// tile index -> N tile, row block, x tile, first merged output row and its row inside the image
+__device__ __forceinline__ TileCoord tile_coord(const SepParams& p, int tile) {
+  TileCoord c;
+  const int m_tile = tile >> p.n_shift;
+  c.n_tile = tile - (m_tile << p.n_shift);
+  c.rb = fastdiv(m_tile, p.tiles_x_magic);
+  c.txi = m_tile - c.rb * p.tiles_x;
+  c.gy0 = c.rb * p.th;
+  c.y0 = c.gy0 - fastdiv(c.gy0, p.hout_magic) * p.hout;
+  return c;
+}
+
+// row-major 128-byte rows, 16-byte chunk index XOR (row & 7): what TMA / UMMA call SWIZZLE_128B
+__device__ __forceinline__ uint32_t sw128(int row, int chunk) {
+  return (uint32_t)row * 128u + (uint32_t)((chunk ^ (row & 7)) << 4);
 }
 
 __device__ __forceinline__ void split_store(uint8_t* hi, uint8_t* lo, uint32_t off, const float4& v) {
@@ -127,6 +162,16 @@ __device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64
       : "memory");
 }
 
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1,
+                                            int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5}], [%2];"
+      :
+      : "r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
@@ -139,7 +184,7 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
 }
 
 // 16 accumulator columns of one row: hi*hi partial sum(s) + the cross-term accumulator, added
-// in fp32 with round-to-nearest (small + (big0 + big1)).
+// in fp32 with round-to-nearest ((big0 + big1) + small).
 __device__ __forceinline__ void ld_sum16(uint32_t taddr, uint32_t small_off, int nbig, uint32_t nt, uint32_t (&v)[16]) {
   uint32_t s[16];
   tmem_ld16(taddr, v);
@@ -154,57 +199,172 @@ __device__ __forceinline__ void ld_sum16(uint32_t taddr, uint32_t small_off, int
   for (int i = 0; i < 16; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) + __uint_as_float(s[i]));
 }
 
-// tile row -> output pixel.  2-D mode: 8 x 16 pixel patches (3x3 stencils of a patch overlap in
-// L1 instead of re-reading whole image rows); flattened mode for the 40^2 / 20^2 maps.
-__device__ __forceinline__ bool tile_pixel(const SepParams& p, int m_tile, int row, int& n, int& oy, int& ox) {
-  if (p.tiles_x > 0) {
-    const int per_img = p.tiles_x * p.tiles_y;
-    n = m_tile / per_img;
-    const int t = m_tile - n * per_img;
-    const int ty = t / p.tiles_x, tx = t - ty * p.tiles_x;
-    oy = ty * 8 + (row >> 4);
-    ox = tx * 16 + (row & 15);
-    return true;
+struct Rings {
+  uint8_t* in;          // s_in input boxes
+  uint8_t* ab;          // s_ab x (A_hi, A_lo, B_hi, B_lo)
+  uint64_t* full_in;
+  uint64_t* empty_in;
+  uint64_t* full_ab;
+  uint64_t* empty_ab;
+  int ab_bytes;
+};
+
+// Converter warps: input box (shared memory, written by TMA) -> A operand hi/lo tiles.
+//   KC = 32: a thread owns 4 consecutive output pixels of one row x one 16-byte channel chunk
+//            (a quarter warp = the 8 chunks of one pixel = 128 contiguous bytes: no conflicts);
+//   KC = 16: 2 consecutive pixels x one chunk; a quarter warp = 4 chunks x 2 adjacent tile rows
+//            (the host makes the box width odd for stride 1 so those rows hit different banks).
+template <int KC, int STRIDE, int MODE>
+__device__ __forceinline__ void converter_loop(const SepParams& p, const Rings& r, const float* s_dw, int t,
+                                               int lane) {
+  constexpr int PXT = KC == 32 ? 4 : 2;
+  constexpr int PP = KC * 4;                        // pixel pitch inside the box (bytes)
+  constexpr int NV = (PXT - 1) * STRIDE + 3;        // box columns a thread's window spans
+  const int xgroups = p.tw / PXT;
+  int chunk, ty, xg;
+  if (KC == 32) {
+    chunk = t & 7;
+    const int g = t >> 3;
+    ty = g / xgroups;
+    xg = g - ty * xgroups;
+  } else {
+    chunk = t & 3;
+    const int g = t >> 3;
+    const int typ = g / xgroups;
+    xg = g - typ * xgroups;
+    ty = 2 * typ + ((t >> 2) & 1);
   }
-  const int m = m_tile * TM + row;
-  if (m >= p.total_px) {
-    n = oy = ox = 0;
-    return false;
+  const bool active = ty < p.th;
+  const int row0 = ty * p.tw + xg * PXT;            // tile row of the first owned pixel
+  uint32_t soff[PXT];
+#pragma unroll
+  for (int j = 0; j < PXT; ++j) soff[j] = sw128(row0 + j, chunk);
+  // byte offset of the thread's window inside the box (row rr adds rr * bw * PP)
+  const int box_off = (MODE == LD_PW ? (ty * p.bw + xg * PXT) : (ty * STRIDE * p.bw + xg * PXT * STRIDE)) * PP + chunk * 16;
+  const int row_pitch = p.bw * PP;
+  const int total_tiles = p.num_m_tiles << p.n_shift;
+  // depthwise weights of this thread's 4 channels: [tap][cin] + bias row, staged in shared memory
+  float4 w[9], b4 = zero4();
+  auto load_dw = [&](int k0) {
+    const bool kin = k0 < p.cin;
+#pragma unroll
+    for (int q = 0; q < 9; ++q) w[q] = kin ? *reinterpret_cast<const float4*>(s_dw + q * p.cin + k0) : zero4();
+    b4 = kin ? *reinterpret_cast<const float4*>(s_dw + 9 * p.cin + k0) : zero4();
+  };
+  if (MODE == LD_DW) load_dw(chunk * 4);
+  int si = 0, sa = 0;
+  uint32_t ph_in = 0, ph_ab = 0;
+  for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    const TileCoord tc = tile_coord(p, tile);
+    const bool pix_ok = active && tc.gy0 + ty < p.rows_out;
+    int y = tc.y0 + ty;
+    if (y >= p.hout) y -= p.hout;
+    for (int i = 0; i < p.n_in; ++i) {
+      mbar_wait(&r.full_in[si], ph_in, p.err_flag);
+      const uint8_t* box = r.in + si * p.in_bytes + box_off;
+      const int k0 = i * KC + chunk * 4;
+      const bool kv = k0 < p.cin && pix_ok;
+      if (MODE == LD_DW && p.n_in > 1) load_dw(k0);
+      for (int tap = 0; tap < p.taps; ++tap) {
+        mbar_wait(&r.empty_ab[sa], ph_ab ^ 1u, p.err_flag);
+        uint8_t* hi = r.ab + sa * r.ab_bytes;
+        uint8_t* lo = hi + A_BYTES;
+        if (active) {
+          float4 acc[PXT];
+#pragma unroll
+          for (int j = 0; j < PXT; ++j) acc[j] = zero4();
+          if (kv) {
+            if (MODE == LD_DW) {
+#pragma unroll
+              for (int j = 0; j < PXT; ++j) acc[j] = b4;
+#pragma unroll
+              for (int rr = 0; rr < 3; ++rr) {
+                const int iy = y * STRIDE - 1 + rr;
+                if (iy >= 0 && iy < p.hin) {      // rows outside the image hold a neighbour image's data
+                  const uint8_t* rb = box + rr * row_pitch;
+                  float4 v[NV];
+#pragma unroll
+                  for (int c = 0; c < NV; ++c) v[c] = lds4(rb + c * PP);
+#pragma unroll
+                  for (int j = 0; j < PXT; ++j)
+#pragma unroll
+                    for (int s = 0; s < 3; ++s) fma4(acc[j], v[j * STRIDE + s], w[rr * 3 + s]);
+                }
+              }
+#pragma unroll
+              for (int j = 0; j < PXT; ++j) {
+                acc[j].x = fmaxf(acc[j].x, 0.f); acc[j].y = fmaxf(acc[j].y, 0.f);
+                acc[j].z = fmaxf(acc[j].z, 0.f); acc[j].w = fmaxf(acc[j].w, 0.f);
+              }
+            } else if (MODE == LD_IM2COL) {
+              const int dy = tap / 3, dx = tap - dy * 3;
+              const int iy = y * STRIDE - 1 + dy;
+              if (iy >= 0 && iy < p.hin) {
+                const uint8_t* rb = box + dy * row_pitch + dx * PP;
+#pragma unroll
+                for (int j = 0; j < PXT; ++j) acc[j] = lds4(rb + j * STRIDE * PP);
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < PXT; ++j) acc[j] = lds4(box + j * PP);
+            }
+          }
+#pragma unroll
+          for (int j = 0; j < PXT; ++j) split_store(hi, lo, soff[j], acc[j]);
+        }
+        // generic-proxy stores -> visible to the tensor core (async proxy), then publish
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&r.full_ab[sa]);
+        if (++sa == p.s_ab) { sa = 0; ph_ab ^= 1u; }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&r.empty_in[si]);   // every lane is done reading the box
+      if (++si == p.s_in) { si = 0; ph_in ^= 1u; }
+    }
   }
-  const int hw = p.hout * p.wout;
-  n = m / hw;
-  const int r = m - n * hw;
-  oy = r / p.wout;
-  ox = r - oy * p.wout;
-  return true;
 }
 
 __global__ void __launch_bounds__(THREADS, 1)
-sep_gemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ SepParams p) {
+sep_gemm_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant__ CUtensorMap tmW,
+                const __grid_constant__ SepParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
   const int b_bytes = p.nt * 128;
-  const int stage_bytes = 2 * A_BYTES + 2 * b_bytes;
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem + p.stages * stage_bytes);
-  uint64_t* empty = full + MAX_STAGES;
-  uint64_t* tfull = empty + MAX_STAGES;
+  Rings r;
+  r.ab_bytes = 2 * A_BYTES + 2 * b_bytes;
+  r.in = smem;
+  r.ab = smem + p.s_in * p.in_bytes;
+  r.full_in = reinterpret_cast<uint64_t*>(r.ab + p.s_ab * r.ab_bytes);
+  r.empty_in = r.full_in + MAX_STAGES;
+  r.full_ab = r.empty_in + MAX_STAGES;
+  r.empty_ab = r.full_ab + MAX_STAGES;
+  uint64_t* tfull = r.empty_ab + MAX_STAGES;
   uint64_t* tempty = tfull + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  float* s_dw = reinterpret_cast<float*>(tmem_slot + 4);   // [10][cin]: 9 depthwise taps + bias
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
+  if (p.mode == LD_DW) {
+    for (int i = threadIdx.x; i < 9 * p.cin; i += THREADS) s_dw[i] = p.dw_w[i];
+    for (int i = threadIdx.x; i < p.cin; i += THREADS) s_dw[9 * p.cin + i] = p.dw_b[i];
+  }
   if (warp == 0 && lane == 0) {
-    for (int s = 0; s < p.stages; ++s) {
-      mbar_init(&full[s], TG + 1);      // loader group threads + the weight TMA's expect_tx arrive
-      mbar_init(&empty[s], 1);
+    for (int s = 0; s < MAX_STAGES; ++s) {
+      mbar_init(&r.full_in[s], 1);
+      mbar_init(&r.empty_in[s], CV_WARPS);
+      mbar_init(&r.full_ab[s], CV_WARPS + 1);   // converter warps + the weight TMA's expect_tx arrive
+      mbar_init(&r.empty_ab[s], 1);
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tfull[a], 1);
       mbar_init(&tempty[a], 4);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    tc::prefetch_tmap(&tmIn);
     tc::prefetch_tmap(&tmW);
   }
   if (warp == 2) {
@@ -217,22 +377,41 @@ sep_gemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const int total_tiles = p.num_m_tiles * p.n_tiles_n;
+  const int total_tiles = p.num_m_tiles << p.n_shift;
+  const int nkb = p.n_in * p.taps;
 
   if (warp == 0) {
+    // ------------------------------------------------------------- input-box TMA
+    if (lane == 0) {
+      const uint32_t box_bytes = (uint32_t)(p.bh * p.bw * p.kc * 4);
+      int s = 0;
+      uint32_t ph = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const TileCoord tc = tile_coord(p, tile);
+        const int x0 = tc.txi * p.tw;
+        for (int i = 0; i < p.n_in; ++i) {
+          mbar_wait(&r.empty_in[s], ph ^ 1u, p.err_flag);
+          mbar_expect_tx(&r.full_in[s], box_bytes);
+          tma_load_3d(r.in + s * p.in_bytes, &tmIn, &r.full_in[s], i * p.kc, x0 * p.stride - p.halo,
+                      tc.gy0 * p.stride - p.halo);
+          if (++s == p.s_in) { s = 0; ph ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 6) {
     // ------------------------------------------------------------- weight TMA
     if (lane == 0) {
-      uint32_t it = 0;
+      int s = 0;
+      uint32_t ph = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int n0 = (tile % p.n_tiles_n) * p.nt;
-        for (int kb = 0; kb < p.nkb; ++kb, ++it) {
-          const int stage = it % p.stages;
-          const uint32_t phase = (it / p.stages) & 1u;
-          mbar_wait(&empty[stage], phase ^ 1u, p.err_flag);
-          mbar_expect_tx(&full[stage], 2u * (uint32_t)b_bytes);
-          uint8_t* sb = smem + stage * stage_bytes + 2 * A_BYTES;
-          tma_load_2d(sb, &tmW, &full[stage], kb * 32, n0);
-          tma_load_2d(sb + b_bytes, &tmW, &full[stage], kb * 32, p.npad_total + n0);
+        const int n0 = (tile & (p.n_tiles_n - 1)) * p.nt;
+        for (int kb = 0; kb < nkb; ++kb) {
+          mbar_wait(&r.empty_ab[s], ph ^ 1u, p.err_flag);
+          mbar_expect_tx(&r.full_ab[s], 2u * (uint32_t)b_bytes);
+          uint8_t* sb = r.ab + s * r.ab_bytes + 2 * A_BYTES;
+          tma_load_2d(sb, &tmW, &r.full_ab[s], kb * 32, n0);
+          tma_load_2d(sb + b_bytes, &tmW, &r.full_ab[s], kb * 32, p.npad_total + n0);
+          if (++s == p.s_ab) { s = 0; ph ^= 1u; }
         }
       }
     }
@@ -240,31 +419,29 @@ sep_gemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
     // ------------------------------------------------------------- MMA issuer
     if (lane == 0) {
       const uint32_t idesc = make_idesc_tf32(TM, p.nt);
-      uint32_t it = 0, tt = 0;
+      uint32_t tt = 0;
+      int s = 0;
+      uint32_t ph = 0;
       const uint32_t slot_cols = (uint32_t)((p.nbig + 1) * p.nt);
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tt) {
         const uint32_t acc = p.acc_stages == 2 ? (tt & 1u) : 0u;
         const uint32_t acc_phase = p.acc_stages == 2 ? ((tt >> 1) & 1u) : (tt & 1u);
         mbar_wait(&tempty[acc], acc_phase ^ 1u, p.err_flag);
         tc_fence_after();
-        // The tensor core truncates when it adds a K=8 product group into the fp32 accumulator,
-        // a bias of ~2^-24 |D| per MMA.  So: the two small cross terms go to their own
-        // accumulator (their truncation is 2^-11 smaller), and the hi*hi products alternate
-        // between nbig accumulators; the epilogue adds the partial sums with round-to-nearest.
         const uint32_t d_big = tmem_base + acc * slot_cols;
         const uint32_t d_small = d_big + (uint32_t)(p.nbig * p.nt);
         uint32_t ks_total = 0;
-        for (int kb = 0; kb < p.nkb; ++kb, ++it) {
-          const int stage = it % p.stages;
-          const uint32_t phase = (it / p.stages) & 1u;
-          mbar_wait(&full[stage], phase, p.err_flag);
+        int tap = 0, crem = p.cin;   // channels left from this K block's box on
+        for (int kb = 0; kb < nkb; ++kb) {
+          mbar_wait(&r.full_ab[s], ph, p.err_flag);
           tc_fence_after();
-          const uint8_t* sa = smem + stage * stage_bytes;
+          const uint8_t* sa = r.ab + s * r.ab_bytes;
           const uint64_t ahi = make_smem_desc(sa);
           const uint64_t alo = make_smem_desc(sa + A_BYTES);
           const uint64_t bhi = make_smem_desc(sa + 2 * A_BYTES);
           const uint64_t blo = make_smem_desc(sa + 2 * A_BYTES + b_bytes);
-          const int ksteps = min(4, (p.kdim - kb * 32 + 7) >> 3);   // K = 8 tf32 per MMA
+          const int ksteps = (min(p.kc, crem) + 7) >> 3;               // K = 8 tf32 per MMA
+          if (++tap == p.taps) { tap = 0; crem -= p.kc; }
           for (int k = 0; k < ksteps; ++k, ++ks_total) {
             const uint64_t o = (uint64_t)(k * 2);   // +32 bytes inside the 128-byte swizzle row
             mma_tf32(d_small, alo + o, bhi + o, idesc, ks_total ? 1u : 0u);
@@ -272,28 +449,31 @@ sep_gemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
             const uint32_t which = p.nbig == 2 ? (ks_total & 1u) : 0u;
             mma_tf32(d_big + which * (uint32_t)p.nt, ahi + o, bhi + o, idesc, ks_total >= (uint32_t)p.nbig ? 1u : 0u);
           }
-          tc_commit(&empty[stage]);
+          tc_commit(&r.empty_ab[s]);
+          if (++s == p.s_ab) { s = 0; ph ^= 1u; }
         }
         tc_commit(&tfull[acc]);
       }
     }
-  } else if (warp < FIRST_LD_WARP) {
+  } else if (warp < 6) {
     // ------------------------------------------------------------- epilogue
     const int q = warp & 3;            // TMEM lane quarter this warp may access
     const int row = q * 32 + lane;
+    const int ty = row / p.tw, tx = row - ty * p.tw;
     uint32_t tt = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tt) {
-      const int m_tile = tile / p.n_tiles_n;
-      const int n0 = (tile % p.n_tiles_n) * p.nt;
-      int n, oy, ox;
-      const bool valid = tile_pixel(p, m_tile, row, n, oy, ox);
+      const TileCoord tc = tile_coord(p, tile);
+      const int n0 = tc.n_tile * p.nt;
+      const int gy = tc.gy0 + ty;                            // merged output row = n * hout + y
+      const int ox = tc.txi * p.tw + tx;
+      const bool valid = ty < p.th && gy < p.rows_out;
       const uint32_t acc = p.acc_stages == 2 ? (tt & 1u) : 0u;
       const uint32_t acc_phase = p.acc_stages == 2 ? ((tt >> 1) & 1u) : (tt & 1u);
       mbar_wait(&tfull[acc], acc_phase, p.err_flag);
       tc_fence_after();
       const uint32_t taddr = tmem_base + acc * (uint32_t)((p.nbig + 1) * p.nt) + ((uint32_t)(q * 32) << 16);
-      // kdim <= 8 * nbig would leave the second hi*hi accumulator unwritten; not the case here
       const uint32_t small_off = (uint32_t)(p.nbig * p.nt);
+      const size_t pix = (size_t)gy * p.wout + ox;           // NHWC pixel index over the batch
       if (p.epi == EPI_HEAD) {
         // 30 channels of one pixel: [0,2) score (sigmoid), [2,10) bbox, [10,30) kps; the export's
         // anchor-major layout is anchor = pixel*2 + a, i.e. contiguous per pixel
@@ -307,24 +487,24 @@ sep_gemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
             f[i] = __uint_as_float(v0[i]) + __ldg(p.bias + i);
             f[16 + i] = __uint_as_float(v1[i]) + __ldg(p.bias + 16 + i);
           }
-          const size_t hw = (size_t)p.hout * p.wout;
-          const size_t pix = (size_t)oy * p.wout + ox;
           float2 sc;
           sc.x = 1.0f / (1.0f + expf(-f[0]));
           sc.y = 1.0f / (1.0f + expf(-f[1]));
-          *reinterpret_cast<float2*>(p.score + ((size_t)n * hw + pix) * 2) = sc;
-          float4* bb = reinterpret_cast<float4*>(p.bbox + ((size_t)n * hw + pix) * 8);
+          *reinterpret_cast<float2*>(p.score + pix * 2) = sc;
+          float4* bb = reinterpret_cast<float4*>(p.bbox + pix * 8);
           bb[0] = make_float4(f[2], f[3], f[4], f[5]);
           bb[1] = make_float4(f[6], f[7], f[8], f[9]);
-          float4* kp = reinterpret_cast<float4*>(p.kps + ((size_t)n * hw + pix) * 20);
+          float4* kp = reinterpret_cast<float4*>(p.kps + pix * 20);
 #pragma unroll
           for (int i = 0; i < 5; ++i) kp[i] = make_float4(f[10 + 4 * i], f[11 + 4 * i], f[12 + 4 * i], f[13 + 4 * i]);
         }
       } else {
-        const size_t pix_off = valid ? ((size_t)(n * p.hout + oy) * p.wout + ox) * p.cout : 0;
+        const size_t pix_off = valid ? pix * p.cout : 0;
         const float* up = nullptr;
-        if (p.add_up && valid)
+        if (p.add_up && valid) {
+          const int n = fastdiv(gy, p.hout_magic), oy = gy - n * p.hout;
           up = p.add_up + ((size_t)(n * (p.hout >> 1) + (oy >> 1)) * (p.wout >> 1) + (ox >> 1)) * p.cout;
+        }
 #pragma unroll 1
         for (int c0 = 0; c0 < p.nt; c0 += 16) {
           uint32_t v[16];
@@ -359,103 +539,19 @@ sep_gemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty[acc]);
     }
-  } else {
-    // ------------------------------------------------------------- A-operand gather
-    const int lw = warp - FIRST_LD_WARP;
-    const int grp = lw % LD_GROUPS;
-    const int lt = (lw / LD_GROUPS) * 32 + lane;     // 0 .. TG-1 within the group
-    const int chunk = lt & 7;                        // 16-byte chunk = 4 channels of the K block
-    const int r0 = lt >> 3;
-    const uint32_t off0 = (uint32_t)r0 * 128u + (uint32_t)((chunk ^ (r0 & 7)) << 4);   // SWIZZLE_128B
-    uint32_t it = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      const int m_tile = tile / p.n_tiles_n;
-      bool have = false;
-      int pix[ITEMS];
-      for (int kb = 0; kb < p.nkb; ++kb, ++it) {
-        if ((int)(it % LD_GROUPS) != grp) continue;
-        if (!have) {
-#pragma unroll
-          for (int j = 0; j < ITEMS; ++j) {
-            int n, oy, ox;
-            const bool ok = tile_pixel(p, m_tile, r0 + j * ROW_STEP, n, oy, ox);
-            pix[j] = ok ? ((n << 20) | (oy << 10) | ox) : -1;
-          }
-          have = true;
-        }
-        const int stage = it % p.stages;
-        const uint32_t phase = (it / p.stages) & 1u;
-        mbar_wait(&empty[stage], phase ^ 1u, p.err_flag);
-        uint8_t* hi = smem + stage * stage_bytes;
-        uint8_t* lo = hi + A_BYTES;
-        const int k = kb * 32 + chunk * 4;
-        if (p.mode == LD_DW) {
-          const bool kv = k < p.cin;
-          float4 w[9], b4 = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-          for (int t = 0; t < 9; ++t) w[t] = kv ? ldg4(p.dw_w + t * p.cin + k) : make_float4(0.f, 0.f, 0.f, 0.f);
-          if (kv) b4 = ldg4(p.dw_b + k);
-#pragma unroll
-          for (int j = 0; j < ITEMS; ++j) {
-            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (kv && pix[j] >= 0) {
-              const int n = pix[j] >> 20, oy = (pix[j] >> 10) & 1023, ox = pix[j] & 1023;
-              const float* base = p.in + (size_t)n * p.hin * p.win * p.cin + k;
-              const int iy0 = oy * p.stride - 1, ix0 = ox * p.stride - 1;
-              float4 v[9];
-#pragma unroll
-              for (int r = 0; r < 3; ++r)
-#pragma unroll
-                for (int s = 0; s < 3; ++s) {
-                  const int iy = iy0 + r, ix = ix0 + s;
-                  const bool ok = iy >= 0 && iy < p.hin && ix >= 0 && ix < p.win;
-                  v[r * 3 + s] = ok ? ldg4(base + ((size_t)iy * p.win + ix) * p.cin) : make_float4(0.f, 0.f, 0.f, 0.f);
-                }
-              acc = b4;
-#pragma unroll
-              for (int t = 0; t < 9; ++t) fma4(acc, v[t], w[t]);
-              acc.x = fmaxf(acc.x, 0.f); acc.y = fmaxf(acc.y, 0.f);
-              acc.z = fmaxf(acc.z, 0.f); acc.w = fmaxf(acc.w, 0.f);
-            }
-            split_store(hi, lo, off0 + (uint32_t)(j * ROW_STEP) * 128u, acc);
-          }
-        } else if (p.mode == LD_PW) {
-          const bool kv = k < p.cin;
-          float4 v[ITEMS];
-#pragma unroll
-          for (int j = 0; j < ITEMS; ++j) {
-            v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (kv && pix[j] >= 0) {
-              const int n = pix[j] >> 20, oy = (pix[j] >> 10) & 1023, ox = pix[j] & 1023;
-              v[j] = ldg4(p.in + ((size_t)(n * p.hin + oy) * p.win + ox) * p.cin + k);
-            }
-          }
-#pragma unroll
-          for (int j = 0; j < ITEMS; ++j) split_store(hi, lo, off0 + (uint32_t)(j * ROW_STEP) * 128u, v[j]);
-        } else {
-          // dense 3x3, K index = tap * cin + c (a 16-byte chunk never straddles a tap: cin % 4 == 0)
-          const int tap = k / p.cin;
-          const int c = k - tap * p.cin;
-          const bool kv = tap < 9;
-          const int dy = tap / 3 - 1, dx = tap - (tap / 3) * 3 - 1;
-          float4 v[ITEMS];
-#pragma unroll
-          for (int j = 0; j < ITEMS; ++j) {
-            v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (kv && pix[j] >= 0) {
-              const int n = pix[j] >> 20, oy = (pix[j] >> 10) & 1023, ox = pix[j] & 1023;
-              const int iy = oy * p.stride + dy, ix = ox * p.stride + dx;
-              if (iy >= 0 && iy < p.hin && ix >= 0 && ix < p.win)
-                v[j] = ldg4(p.in + ((size_t)(n * p.hin + iy) * p.win + ix) * p.cin + c);
-            }
-          }
-#pragma unroll
-          for (int j = 0; j < ITEMS; ++j) split_store(hi, lo, off0 + (uint32_t)(j * ROW_STEP) * 128u, v[j]);
-        }
-        // generic-proxy stores -> visible to the tensor core (async proxy), then publish
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        mbar_arrive(&full[stage]);
-      }
+  } else if (warp >= FIRST_CV_WARP) {
+    // ------------------------------------------------------------- A-operand converters
+    const int t = threadIdx.x - FIRST_CV_WARP * 32;
+    if (p.mode == LD_DW) {
+      if (p.kc == 32) converter_loop<32, 1, LD_DW>(p, r, s_dw, t, lane);
+      else if (p.stride == 1) converter_loop<16, 1, LD_DW>(p, r, s_dw, t, lane);
+      else converter_loop<16, 2, LD_DW>(p, r, s_dw, t, lane);
+    } else if (p.mode == LD_IM2COL) {
+      if (p.kc == 32) converter_loop<32, 1, LD_IM2COL>(p, r, s_dw, t, lane);
+      else if (p.stride == 1) converter_loop<16, 1, LD_IM2COL>(p, r, s_dw, t, lane);
+      else converter_loop<16, 2, LD_IM2COL>(p, r, s_dw, t, lane);
+    } else {
+      converter_loop<32, 1, LD_PW>(p, r, s_dw, t, lane);
     }
   }
   tc_fence_before();
@@ -525,7 +621,13 @@ struct PackedConv {        // device-side packed parameters of one (fused) layer
   float* dw_w = nullptr;   // [9][cin]  (dw-separable only)
   float* dw_b = nullptr;   // [cin]
   CUtensorMap tmW;
-  int cin = 0, cout = 0, kdim = 0, nkb = 0, nt = 0, n_tiles_n = 1, npad_total = 0, mode = LD_PW;
+  int cin = 0, cout = 0, nt = 0, n_tiles_n = 1, npad_total = 0, mode = LD_PW;
+  int stride = 1;          // fixed per layer (decides kc)
+  int kc = 32, n_in = 1, taps = 1;
+  // input tensor map, re-encoded only when the input pointer / batch changes
+  mutable CUtensorMap tmIn;
+  mutable const float* tm_in = nullptr;
+  mutable int tm_rows = 0, tm_bw = 0, tm_bh = 0;
 };
 
 struct DetModel {
@@ -572,29 +674,35 @@ float tf32_rna_host(float x) {
   return x;
 }
 
-// w: [cout][cin*ks*ks] (OIHW flattened).  GEMM K order: channel for 1x1, tap*cin + c for 3x3.
+// w: [cout][cin*ks*ks] (OIHW flattened).  The GEMM K axis is cut into 32-float blocks; block
+// kb = (channel block i) * taps + tap holds channels [i*kc, i*kc + kc) of that tap (kc = 16
+// leaves the upper half of the block zero; the MMA issuer never reads it).
 bool pack(DetModel* m, PackedConv& pc, const std::vector<float>& w, const std::vector<float>& b, int cout, int cin,
-          int ks, int mode) {
+          int ks, int mode, int stride) {
   pc.cin = cin;
   pc.cout = cout;
   pc.mode = mode;
-  pc.kdim = cin * ks * ks;
-  pc.nkb = (pc.kdim + 31) / 32;
-  const int kpad = pc.nkb * 32;
+  pc.stride = stride;
+  pc.kc = (stride == 2 || cin == 16) ? 16 : 32;
+  if (mode == LD_PW) pc.kc = 32;
+  pc.n_in = (cin + pc.kc - 1) / pc.kc;
+  pc.taps = ks * ks;
+  const int nkb = pc.n_in * pc.taps;
+  const int kpad = nkb * 32;
   pc.npad_total = (cout + 15) / 16 * 16;
   pc.n_tiles_n = pc.npad_total > 256 ? 2 : 1;
   pc.nt = pc.npad_total / pc.n_tiles_n;
   if (pc.nt % 16 != 0 || cin % 4 != 0) return false;
   std::vector<float> wp((size_t)2 * pc.npad_total * kpad, 0.f), bp(pc.npad_total, 0.f);
-  const int taps = ks * ks;
   for (int co = 0; co < cout; ++co) {
     for (int ci = 0; ci < cin; ++ci)
-      for (int t = 0; t < taps; ++t) {
-        const float v = w[((size_t)co * cin + ci) * taps + t];
+      for (int t = 0; t < pc.taps; ++t) {
+        const float v = w[((size_t)co * cin + ci) * pc.taps + t];
         const float h = tf32_rna_host(v);
-        const size_t kk = (size_t)t * cin + ci;
+        const float l = tf32_rna_host(v - h);
+        const size_t kk = (size_t)((ci / pc.kc) * pc.taps + t) * 32 + (ci % pc.kc);
         wp[(size_t)co * kpad + kk] = h;
-        wp[((size_t)pc.npad_total + co) * kpad + kk] = v - h;
+        wp[((size_t)pc.npad_total + co) * kpad + kk] = l;
       }
     bp[co] = b[co];
   }
@@ -668,9 +776,9 @@ struct LayerIO {
 
 int launch_layer(fr_ctx* ctx, const PackedConv& pc, const LayerIO& io, int n) {
   DetModel* m = ctx->det;
+  if (io.stride != pc.stride) return fr_fail(ctx, FR_ERR_INVALID_ARG, "scrfd layer stride mismatch");
   SepParams p;
   memset(&p, 0, sizeof(p));
-  p.in = io.in;
   p.out = io.out;
   p.dw_w = pc.dw_w;
   p.dw_b = pc.dw_b;
@@ -678,10 +786,10 @@ int launch_layer(fr_ctx* ctx, const PackedConv& pc, const LayerIO& io, int n) {
   p.add_up = io.add_up;
   p.cin = pc.cin;
   p.cout = pc.cout;
-  p.kdim = pc.kdim;
-  p.hin = p.win = io.hin;
+  p.hin = io.hin;
   p.hout = p.wout = io.hin / io.stride;
   p.stride = io.stride;
+  p.rows_out = n * p.hout;
   p.mode = pc.mode;
   p.relu = io.relu;
   p.accumulate = io.accumulate;
@@ -691,24 +799,46 @@ int launch_layer(fr_ctx* ctx, const PackedConv& pc, const LayerIO& io, int n) {
     p.bbox = m->bbox[io.head];
     p.kps = m->kps[io.head];
   }
-  p.nkb = pc.nkb;
+  p.kc = pc.kc;
+  p.n_in = pc.n_in;
+  p.taps = pc.taps;
   p.nt = pc.nt;
   p.n_tiles_n = pc.n_tiles_n;
   p.npad_total = pc.npad_total;
-  p.total_px = n * p.hout * p.wout;
-  if (p.wout % 16 == 0 && p.hout % 8 == 0) {
-    p.tiles_x = p.wout / 16;
-    p.tiles_y = p.hout / 8;
-    p.num_m_tiles = n * p.tiles_x * p.tiles_y;
+  // output tile: 8 x 16 pixels on the wide maps, 6 x 20 on the 40^2 / 20^2 ones
+  if (p.wout % 16 == 0 && p.hout % 8 == 0) { p.th = 8; p.tw = 16; }
+  else if (p.wout % 20 == 0) { p.th = 6; p.tw = 20; }
+  else return fr_fail(ctx, FR_ERR_UNSUPPORTED, "scrfd feature map size not tileable");
+  p.tiles_x = p.wout / p.tw;
+  p.tiles_x_magic = p.tiles_x == 1 ? 0u : (uint32_t)((0x100000000ull + p.tiles_x - 1) / p.tiles_x);
+  p.hout_magic = (uint32_t)((0x100000000ull + p.hout - 1) / p.hout);
+  p.n_shift = pc.n_tiles_n == 2 ? 1 : 0;
+  p.num_m_tiles = p.tiles_x * ceil_div(p.rows_out, p.th);
+  p.halo = pc.mode == LD_PW ? 0 : 1;
+  if (pc.mode == LD_PW) {
+    p.bh = p.th;
+    p.bw = p.tw;
   } else {
-    p.num_m_tiles = ceil_div(p.total_px, TM);
+    p.bh = (p.th - 1) * p.stride + 3;
+    p.bw = (p.tw - 1) * p.stride + 3;
+    // kc = 16, stride 1: a quarter warp reads 4 chunks x 2 adjacent box rows; an odd box width
+    // puts those rows on different banks
+    if (p.kc == 16 && p.stride == 1 && p.bw % 2 == 0) p.bw++;
   }
-  const int stage_bytes = 2 * A_BYTES + 2 * pc.nt * 128;
-  const int budget = 227 * 1024 - 1024 - 512;
-  p.stages = std::min(MAX_STAGES, budget / stage_bytes);
-  if (p.stages < 2) return fr_fail(ctx, FR_ERR_UNSUPPORTED, "scrfd layer does not fit shared memory");
-  static const int nbig_env = getenv("FR_SCRFD_NBIG") ? atoi(getenv("FR_SCRFD_NBIG")) : 2;
-  p.nbig = (nbig_env == 1 || pc.kdim <= 16) ? 1 : 2;
+  p.in_bytes = (p.bh * p.bw * p.kc * 4 + 1023) / 1024 * 1024;
+  const int ab_bytes = 2 * A_BYTES + 2 * pc.nt * 128;
+  const int dw_bytes = pc.mode == LD_DW ? (10 * pc.cin * 4 + 15) / 16 * 16 : 0;
+  const int budget = 227 * 1024 - 1024 - 512 - dw_bytes;
+  p.s_in = 2;
+  p.s_ab = 2;
+  if (p.s_in * p.in_bytes + p.s_ab * ab_bytes > budget)
+    return fr_fail(ctx, FR_ERR_UNSUPPORTED, "scrfd layer does not fit shared memory");
+  for (int round = 0; round < 2 * MAX_STAGES; ++round) {
+    int& grow = (round & 1) ? p.s_ab : p.s_in;
+    const int add = (round & 1) ? ab_bytes : p.in_bytes;
+    if (grow < MAX_STAGES && p.s_in * p.in_bytes + p.s_ab * ab_bytes + add <= budget) grow++;
+  }
+  p.nbig = pc.cin * pc.taps <= 16 ? 1 : 2;
   const int slot = (p.nbig + 1) * pc.nt;
   if (slot > 512) return fr_fail(ctx, FR_ERR_UNSUPPORTED, "scrfd layer does not fit tensor memory");
   p.acc_stages = 2 * slot <= 512 ? 2 : 1;
@@ -716,10 +846,20 @@ int launch_layer(fr_ctx* ctx, const PackedConv& pc, const LayerIO& io, int n) {
   while (cols < p.acc_stages * slot) cols *= 2;
   p.tmem_cols = cols;
   p.err_flag = m->err_flag;
-  const int smem = p.stages * stage_bytes + 1024 + 512;
+  const int rows_in = n * io.hin;
+  if (pc.tm_in != io.in || pc.tm_rows != rows_in || pc.tm_bw != p.bw || pc.tm_bh != p.bh) {
+    if (!tc_make_map_3d_f32(&pc.tmIn, io.in, (uint64_t)pc.cin, (uint64_t)io.hin, (uint64_t)rows_in, (uint32_t)p.kc,
+                            (uint32_t)p.bw, (uint32_t)p.bh))
+      return fr_fail(ctx, FR_ERR_CUDA, "scrfd input tensor map creation failed");
+    pc.tm_in = io.in;
+    pc.tm_rows = rows_in;
+    pc.tm_bw = p.bw;
+    pc.tm_bh = p.bh;
+  }
+  const int smem = p.s_in * p.in_bytes + p.s_ab * ab_bytes + 1024 + 512 + dw_bytes;
   const int total_tiles = p.num_m_tiles * p.n_tiles_n;
   const int grid = std::min(total_tiles, m->num_sms);
-  sep_gemm_kernel<<<grid, THREADS, smem, ctx->stream>>>(pc.tmW, p);
+  sep_gemm_kernel<<<grid, THREADS, smem, ctx->stream>>>(pc.tmIn, pc.tmW, p);
   ctx->launches++;
   FR_CUDA_OK(ctx, cudaGetLastError());
   return FR_OK;
@@ -731,16 +871,17 @@ int det_model_create(fr_ctx* ctx, const fr_weights* w) {
   if (!w || w->model != FR_MODEL_DET) return fr_fail(ctx, FR_ERR_MODEL, "det weights missing");
   std::unique_ptr<DetModel> m(new DetModel());
   bool ok = true;
-  auto dense = [&](const std::string& name) {   // conv (3x3 or 1x1) as a [cout][cin*k*k] GEMM
+  auto dense = [&](const std::string& name, int stride) {   // conv (3x3 or 1x1) as a [cout][cin*k*k] GEMM
     const fr_tensor& tw = w->at(name + ".w");
     const int cout = (int)tw.dims[0], cin = (int)tw.dims[1], k = (int)tw.dims[2];
-    ok = ok && pack(m.get(), m->conv[name], tw.data, w->at(name + ".b").data, cout, cin, k, k == 3 ? LD_IM2COL : LD_PW);
+    ok = ok && pack(m.get(), m->conv[name], tw.data, w->at(name + ".b").data, cout, cin, k,
+                    k == 3 ? LD_IM2COL : LD_PW, stride);
   };
-  auto dwsep = [&](const std::string& name) {   // dw 3x3 + ReLU evaluated inside the 1x1's operand gather
+  auto dwsep = [&](const std::string& name, int stride) {   // dw 3x3 + ReLU built inside the 1x1's operand
     const fr_tensor& pw = w->at(name + ".pw.w");
     const int cout = (int)pw.dims[0], cin = (int)pw.dims[1];
     PackedConv& pc = m->conv[name];
-    ok = ok && pack(m.get(), pc, pw.data, w->at(name + ".pw.b").data, cout, cin, 1, LD_DW);
+    ok = ok && pack(m.get(), pc, pw.data, w->at(name + ".pw.b").data, cout, cin, 1, LD_DW, stride);
     const std::vector<float>& dw = w->at(name + ".dw.w").data;   // [cin][1][3][3] -> [9][cin]
     std::vector<float> dwt((size_t)9 * cin);
     for (int c = 0; c < cin; ++c)
@@ -758,17 +899,17 @@ int det_model_create(fr_ctx* ctx, const fr_weights* w) {
     m->stem_b = upload(m.get(), w->at("stem.b").data);
     ok = ok && m->stem_w && m->stem_b;
   }
-  dwsep("b0");
+  dwsep("b0", 1);
   for (int s = 0; s < 4; ++s)
-    for (int b = 0; b < kStages[s][0]; ++b) dwsep("s" + std::to_string(s) + "." + std::to_string(b));
-  for (int i = 0; i < 3; ++i) dense("lat" + std::to_string(i));
-  for (int i = 0; i < 3; ++i) dense("fpn" + std::to_string(i));
-  for (int i = 0; i < 2; ++i) dense("down" + std::to_string(i));
-  for (int i = 0; i < 2; ++i) dense("pafpn" + std::to_string(i));
+    for (int b = 0; b < kStages[s][0]; ++b) dwsep("s" + std::to_string(s) + "." + std::to_string(b), b == 0 ? 2 : 1);
+  for (int i = 0; i < 3; ++i) dense("lat" + std::to_string(i), 1);
+  for (int i = 0; i < 3; ++i) dense("fpn" + std::to_string(i), 1);
+  for (int i = 0; i < 2; ++i) dense("down" + std::to_string(i), 2);
+  for (int i = 0; i < 2; ++i) dense("pafpn" + std::to_string(i), 1);
   for (int i = 0; i < 3; ++i) {
     const std::string h = "h" + std::to_string(i);
-    dwsep(h + ".t0");
-    dwsep(h + ".t1");
+    dwsep(h + ".t0", 1);
+    dwsep(h + ".t1", 1);
     // fuse the three head convs of the stride into one 64 -> 30 conv (cls 2 | reg 8 | kps 20)
     std::vector<float> fw, fb;
     for (const char* part : {".cls", ".reg", ".kps"}) {
@@ -777,7 +918,7 @@ int det_model_create(fr_ctx* ctx, const fr_weights* w) {
       fw.insert(fw.end(), tw.data.begin(), tw.data.end());
       fb.insert(fb.end(), tb.data.begin(), tb.data.end());
     }
-    ok = ok && pack(m.get(), m->conv[h + ".out"], fw, fb, 30, 64, 3, LD_IM2COL);
+    ok = ok && pack(m.get(), m->conv[h + ".out"], fw, fb, 30, 64, 3, LD_IM2COL, 1);
   }
   if (ok) {
     ok = cudaMalloc(&m->err_flag, sizeof(int)) == cudaSuccess;

@@ -98,22 +98,31 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-// Bounded spin: a protocol bug traps (launch failure) instead of hanging the GPU.
+// Blocking wait with a suspend-time hint (the warp sleeps in hardware instead of spinning and
+// stealing issue slots from the working warps; ncu showed a third of all executed instructions
+// in the un-hinted spin).  Bounded: a protocol bug traps (launch failure) instead of hanging.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int* err_flag) {
   const uint32_t addr = smem_u32(bar);
   uint32_t ok = 0;
-  long long t0 = 0;
-  for (uint32_t spin = 0;; ++spin) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(addr), "r"(parity)
+      : "memory");
+  if (ok) return;
+  const long long t0 = clock64();
+  for (;;) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(ok)
-        : "r"(addr), "r"(parity)
+        : "r"(addr), "r"(parity), "r"(0x989680u)
         : "memory");
     if (ok) return;
-    if (spin == 1024) t0 = clock64();
-    if (spin > 1024 && (spin & 1023) == 0 && clock64() - t0 > 4000000000ll) {
+    if (clock64() - t0 > 4000000000ll) {
       if (err_flag) atomicExch(err_flag, 1);
       __trap();
     }
