@@ -37,7 +37,7 @@ SYMBOLS = [
     "fr_enable_stage_timing", "fr_stage_times",
     "fr_detect", "fr_detect_batch",
     "fr_embed", "fr_embed_faces_batch", "fr_embed_simple", "fr_embed_aligned_batch",
-    "fr_compare", "fr_compare_batch", "fr_pipeline_batch",
+    "fr_compare", "fr_compare_batch", "fr_pipeline_batch", "fr_pipeline_submit", "fr_pipeline_wait",
     "fr_gallery_create", "fr_gallery_destroy", "fr_gallery_add", "fr_gallery_fill_synthetic",
     "fr_gallery_get_rows", "fr_gallery_size", "fr_gallery_search", "fr_topk_merge",
     "fr_det_preprocess", "fr_scrfd_forward", "fr_scrfd_decode_nms", "fr_estimate_alignment",
@@ -100,6 +100,8 @@ def _declare(L: C.CDLL) -> None:
     L.fr_compare.restype = f32
     L.fr_compare_batch.argtypes = [vp, vp, vp, i32, i32, i32, vp]
     L.fr_pipeline_batch.argtypes = [vp, vp, vp, vp, vp, i32, i32, f32, f32, i32, vp, vp, vp, vp, vp]
+    L.fr_pipeline_submit.argtypes = [vp, vp, vp, vp, vp, i32, f32, f32, i32, vp, vp, vp, vp, vp, vp]
+    L.fr_pipeline_wait.argtypes = [vp, i32]
     L.fr_gallery_create.argtypes = [vp, C.POINTER(vp), i64, i64]
     L.fr_gallery_destroy.argtypes = [vp]
     L.fr_gallery_destroy.restype = None
@@ -320,6 +322,26 @@ class Context:
                                             score_thr, nms_thr, K, _ptr(pad), faces.ctypes.data,
                                             n_det.ctypes.data, emb.ctypes.data, valid.ctypes.data))
         return faces, n_det, emb, valid
+
+    def pipeline_submit(self, images: Sequence[np.ndarray], faces_per_img: int, pad_faces: Optional[np.ndarray],
+                        out_faces: np.ndarray, out_n_det: np.ndarray, out_emb: np.ndarray, out_valid: np.ndarray,
+                        score_thr=0.5, nms_thr=0.4) -> int:
+        """Asynchronous pipeline: enqueue a batch (frames + caller-owned, ideally page-locked, output
+        arrays) and return a ticket for pipeline_wait.  The upload of this batch overlaps the
+        compute of the previous one.  All arrays must stay alive until the wait returns."""
+        b = _ImageBatch(images, FR_MEM_HOST)
+        t = C.c_int(-1)
+        self._inflight = getattr(self, "_inflight", {})
+        self._check(lib().fr_pipeline_submit(self.h, b.ptrs, b.rows, b.cols, b.step, b.n, score_thr, nms_thr,
+                                             faces_per_img, _ptr(pad_faces), out_faces.ctypes.data,
+                                             out_n_det.ctypes.data, out_emb.ctypes.data, out_valid.ctypes.data,
+                                             C.byref(t)))
+        self._inflight[t.value] = (b, images, pad_faces, out_faces, out_n_det, out_emb, out_valid)
+        return t.value
+
+    def pipeline_wait(self, ticket: int) -> None:
+        self._check(lib().fr_pipeline_wait(self.h, ticket))
+        getattr(self, "_inflight", {}).pop(ticket, None)
 
     def pipeline_dev(self, frame_ptrs: Sequence[int], rows: int, cols: int, step: int, faces_per_img: int,
                      pad_ptr: Optional[int], out_faces_ptr: Optional[int], out_ndet_ptr: Optional[int],

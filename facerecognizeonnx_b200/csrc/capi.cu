@@ -84,7 +84,8 @@ bool letterbox(int rows, int cols, ImgDesc& d) {
 // (row stride = cols*3) into ctx->img_stage; device images are used in place.
 int prepare_images(fr_ctx* ctx, const uint8_t* const* bgr, const int* rows, const int* cols,
                    const size_t* step, int n_img, int memspace, bool need_letterbox,
-                   const ImgDesc** d_desc_out, std::vector<ImgDesc>* h_desc_out = nullptr) {
+                   const ImgDesc** d_desc_out, std::vector<ImgDesc>* h_desc_out = nullptr,
+                   DevBuf* stage_buf = nullptr, cudaStream_t stage_stream = nullptr) {
   if (!bgr || !rows || !cols || n_img <= 0) return fr_fail(ctx, FR_ERR_INVALID_ARG, "Input image is empty!");
   std::vector<ImgDesc> h(n_img);
   std::vector<size_t> off(n_img);
@@ -110,15 +111,28 @@ int prepare_images(fr_ctx* ctx, const uint8_t* const* bgr, const int* rows, cons
     }
   }
   if (memspace != FR_MEM_DEVICE) {
-    if (!ctx->img_stage.reserve(total)) return fr_fail(ctx, FR_ERR_CUDA, "image staging allocation failed");
+    DevBuf& stage = stage_buf ? *stage_buf : ctx->img_stage;
+    cudaStream_t cs = stage_buf ? stage_stream : ctx->stream;
+    if (!stage.reserve(total)) return fr_fail(ctx, FR_ERR_CUDA, "image staging allocation failed");
     for (int i = 0; i < n_img; ++i) {
-      uint8_t* dst = ctx->img_stage.as<uint8_t>() + off[i];
+      uint8_t* dst = stage.as<uint8_t>() + off[i];
       const size_t st = step ? step[i] : (size_t)cols[i] * 3;
       const size_t rowb = (size_t)cols[i] * 3;
-      if (st == rowb)
-        FR_CUDA_OK(ctx, cudaMemcpyAsync(dst, bgr[i], rowb * rows[i], cudaMemcpyHostToDevice, ctx->stream));
-      else
-        FR_CUDA_OK(ctx, cudaMemcpy2DAsync(dst, rowb, bgr[i], st, rowb, rows[i], cudaMemcpyHostToDevice, ctx->stream));
+      // frames that are contiguous in host memory (one pinned block) go up as one copy
+      if (st == rowb) {
+        int j = i;
+        size_t bytes = rowb * rows[i];
+        while (j + 1 < n_img && (step ? step[j + 1] : (size_t)cols[j + 1] * 3) == (size_t)cols[j + 1] * 3 &&
+               bgr[j + 1] == bgr[i] + (off[j + 1] - off[i]) && off[j + 1] - off[j] == (size_t)rows[j] * cols[j] * 3) {
+          ++j;
+          bytes = (off[j] - off[i]) + (size_t)rows[j] * cols[j] * 3;
+        }
+        FR_CUDA_OK(ctx, cudaMemcpyAsync(dst, bgr[i], bytes, cudaMemcpyHostToDevice, cs));
+        for (int q = i; q <= j; ++q) h[q].ptr = stage.as<uint8_t>() + off[q];
+        i = j;
+        continue;
+      }
+      FR_CUDA_OK(ctx, cudaMemcpy2DAsync(dst, rowb, bgr[i], st, rowb, rows[i], cudaMemcpyHostToDevice, cs));
       h[i].ptr = dst;
     }
   }
@@ -236,6 +250,12 @@ void fr_destroy(fr_ctx* ctx) {
   det_model_destroy(ctx);
   rec_model_destroy(ctx);
   ctx->img_stage.release();
+  for (auto& sl : ctx->pslots) {
+    sl.stage.release();
+    if (sl.h2d) cudaEventDestroy(sl.h2d);
+    if (sl.done) cudaEventDestroy(sl.done);
+  }
+  if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
   ctx->img_desc.release();
   for (auto& sl : ctx->desc_cache) sl.d.release();
   ctx->faces_dev.release();
@@ -433,16 +453,10 @@ int fr_compare_batch(fr_ctx* ctx, const float* a, const float* b, int n, int dim
 }
 
 // ------------------------------------------------------------- fused pipeline
-int fr_pipeline_batch(fr_ctx* ctx, const uint8_t* const* bgr, const int* rows, const int* cols,
-                      const size_t* step, int n_img, int memspace, float score_thr, float nms_thr,
-                      int faces_per_img, const fr_face* pad_faces, fr_face* out_faces,
-                      int* out_n_det, float* out_emb, int* out_valid) {
-  if (!ctx) return FR_ERR_INVALID_ARG;
-  Guard g(ctx);
-  if (!ctx->det || !ctx->rec) return fr_fail(ctx, FR_ERR_NOT_LOADED, "Model not loaded!");
-  if (faces_per_img <= 0 || !out_emb) return fr_fail(ctx, FR_ERR_INVALID_ARG, "bad pipeline arguments");
-  const ImgDesc* d_desc = nullptr;
-  FR_CHECK(prepare_images(ctx, bgr, rows, cols, step, n_img, memspace, true, &d_desc));
+// det -> select -> align -> embed on staged images + result copies, all enqueued on ctx->stream
+static int pipeline_enqueue(fr_ctx* ctx, const ImgDesc* d_desc, int n_img, int memspace, float score_thr,
+                            float nms_thr, int faces_per_img, const fr_face* pad_faces, fr_face* out_faces,
+                            int* out_n_det, float* out_emb, int* out_valid) {
   const int K = faces_per_img;
   const int det_cap = std::max(K, 64);
   const int n_faces = n_img * K;
@@ -476,7 +490,61 @@ int fr_pipeline_batch(fr_ctx* ctx, const uint8_t* const* bgr, const int* rows, c
   FR_CHECK(copy_out(ctx, out_faces, d_sel, sizeof(fr_face) * n_faces, memspace));
   FR_CHECK(copy_out(ctx, out_n_det, d_ndet, sizeof(int) * n_img, memspace));
   FR_CHECK(copy_out(ctx, out_valid, d_valid, sizeof(int) * n_faces, memspace));
+  return FR_OK;
+}
+
+int fr_pipeline_batch(fr_ctx* ctx, const uint8_t* const* bgr, const int* rows, const int* cols,
+                      const size_t* step, int n_img, int memspace, float score_thr, float nms_thr,
+                      int faces_per_img, const fr_face* pad_faces, fr_face* out_faces,
+                      int* out_n_det, float* out_emb, int* out_valid) {
+  if (!ctx) return FR_ERR_INVALID_ARG;
+  Guard g(ctx);
+  if (!ctx->det || !ctx->rec) return fr_fail(ctx, FR_ERR_NOT_LOADED, "Model not loaded!");
+  if (faces_per_img <= 0 || !out_emb) return fr_fail(ctx, FR_ERR_INVALID_ARG, "bad pipeline arguments");
+  const ImgDesc* d_desc = nullptr;
+  FR_CHECK(prepare_images(ctx, bgr, rows, cols, step, n_img, memspace, true, &d_desc));
+  FR_CHECK(pipeline_enqueue(ctx, d_desc, n_img, memspace, score_thr, nms_thr, faces_per_img, pad_faces, out_faces,
+                            out_n_det, out_emb, out_valid));
   if (memspace != FR_MEM_DEVICE) FR_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+  return FR_OK;
+}
+
+int fr_pipeline_submit(fr_ctx* ctx, const uint8_t* const* bgr, const int* rows, const int* cols,
+                       const size_t* step, int n_img, float score_thr, float nms_thr, int faces_per_img,
+                       const fr_face* pad_faces, fr_face* out_faces, int* out_n_det, float* out_emb,
+                       int* out_valid, int* ticket) {
+  if (!ctx) return FR_ERR_INVALID_ARG;
+  Guard g(ctx);
+  if (!ctx->det || !ctx->rec) return fr_fail(ctx, FR_ERR_NOT_LOADED, "Model not loaded!");
+  if (faces_per_img <= 0 || !out_emb || !ticket) return fr_fail(ctx, FR_ERR_INVALID_ARG, "bad pipeline arguments");
+  if (!ctx->copy_stream) FR_CUDA_OK(ctx, cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+  const int si = ctx->pslot_next;
+  fr_ctx::PipeSlot& sl = ctx->pslots[si];
+  if (!sl.h2d) {
+    FR_CUDA_OK(ctx, cudaEventCreateWithFlags(&sl.h2d, cudaEventDisableTiming));
+    FR_CUDA_OK(ctx, cudaEventCreateWithFlags(&sl.done, cudaEventDisableTiming));
+  }
+  // the slot's staging buffer may still be read by the batch submitted two calls ago
+  if (sl.busy) FR_CUDA_OK(ctx, cudaStreamWaitEvent(ctx->copy_stream, sl.done, 0));
+  const ImgDesc* d_desc = nullptr;
+  FR_CHECK(prepare_images(ctx, bgr, rows, cols, step, n_img, FR_MEM_HOST, true, &d_desc, nullptr, &sl.stage,
+                          ctx->copy_stream));
+  FR_CUDA_OK(ctx, cudaEventRecord(sl.h2d, ctx->copy_stream));
+  FR_CUDA_OK(ctx, cudaStreamWaitEvent(ctx->stream, sl.h2d, 0));
+  FR_CHECK(pipeline_enqueue(ctx, d_desc, n_img, FR_MEM_HOST, score_thr, nms_thr, faces_per_img, pad_faces,
+                            out_faces, out_n_det, out_emb, out_valid));
+  FR_CUDA_OK(ctx, cudaEventRecord(sl.done, ctx->stream));
+  sl.busy = true;
+  ctx->pslot_next = si ^ 1;
+  *ticket = si;
+  return FR_OK;
+}
+
+int fr_pipeline_wait(fr_ctx* ctx, int ticket) {
+  if (!ctx) return FR_ERR_INVALID_ARG;
+  Guard g(ctx);
+  if (ticket < 0 || ticket > 1 || !ctx->pslots[ticket].done) return fr_fail(ctx, FR_ERR_INVALID_ARG, "bad ticket");
+  FR_CUDA_OK(ctx, cudaEventSynchronize(ctx->pslots[ticket].done));
   return FR_OK;
 }
 

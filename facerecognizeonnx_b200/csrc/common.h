@@ -97,6 +97,16 @@ struct fr_ctx {
   void* pinned = nullptr;
   size_t pinned_cap = 0;
   void* pin(size_t bytes);
+  // asynchronous pipeline (fr_pipeline_submit / fr_pipeline_wait): the frames of batch i+1 are
+  // copied on copy_stream into the other staging slot while batch i computes on `stream`
+  struct PipeSlot {
+    DevBuf stage;
+    cudaEvent_t h2d = nullptr, done = nullptr;
+    bool busy = false;
+  };
+  cudaStream_t copy_stream = nullptr;
+  PipeSlot pslots[2];
+  int pslot_next = 0;
 };
 
 #define FR_CUDA_OK(ctx, expr)                                                          \

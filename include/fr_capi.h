@@ -138,6 +138,17 @@ FR_API int fr_pipeline_batch(fr_ctx* ctx, const uint8_t* const* bgr, const int* 
                              float score_thr, float nms_thr, int faces_per_img,
                              const fr_face* pad_faces, fr_face* out_faces, int* out_n_det,
                              float* out_emb, int* out_valid);
+/* Asynchronous form (host buffers only): enqueue the batch and return a ticket.  The frames are
+ * copied on a separate copy stream into one of two staging slots, so the upload of batch i+1
+ * overlaps the compute of batch i; outputs are valid after fr_pipeline_wait(ticket).  At most
+ * two batches may be in flight; input and output buffers must stay alive (and should be
+ * page-locked for the copies to be asynchronous) until the wait returns. */
+FR_API int fr_pipeline_submit(fr_ctx* ctx, const uint8_t* const* bgr, const int* rows,
+                              const int* cols, const size_t* step, int n_img, float score_thr,
+                              float nms_thr, int faces_per_img, const fr_face* pad_faces,
+                              fr_face* out_faces, int* out_n_det, float* out_emb, int* out_valid,
+                              int* ticket);
+FR_API int fr_pipeline_wait(fr_ctx* ctx, int ticket);
 
 /* ------------------------------------------------------------- 1:N search --
  * North-star extension (the reference has only 1:1, src/face_recognizer.cpp:320-334).

@@ -101,3 +101,32 @@ def test_api_mirror_compare_mode(capi, tmp_path):
     bad = api.FaceBox((900, 900, 5, 5), 0.9, np.zeros((5, 2), np.float32))
     assert rec.extractFeature(im, bad).size == 0                       # alignment failed -> empty
     assert rec.extractFeatureSimple(im).shape == (512,)
+
+
+def test_pipeline_submit_wait_matches_sync(ctx, capi):
+    """fr_pipeline_submit / fr_pipeline_wait (two batches in flight, uploads on the copy stream)
+    return exactly what the synchronous fr_pipeline_batch returns."""
+    import torch
+    rng = np.random.default_rng(77)
+    K, n_img = 3, 4
+    batches = [[rng.integers(0, 256, (480, 640, 3), dtype=np.uint8) for _ in range(n_img)] for _ in range(3)]
+    lms = synth_landmarks(rng, n_img * K, 640, 480, outlier_frac=0.0)
+    pad = faces_from_landmarks(capi, lms).reshape(n_img, K)
+    ref = [ctx.pipeline(b, K, pad) for b in batches]
+
+    def outs():
+        return (np.zeros((n_img, K), capi.FACE_DTYPE), np.zeros(n_img, np.int32),
+                np.zeros((n_img, K, 512), np.float32), np.zeros((n_img, K), np.int32))
+
+    o = [outs() for _ in batches]
+    t0 = ctx.pipeline_submit(batches[0], K, pad, *o[0])
+    t1 = ctx.pipeline_submit(batches[1], K, pad, *o[1])
+    ctx.pipeline_wait(t0)
+    t2 = ctx.pipeline_submit(batches[2], K, pad, *o[2])
+    ctx.pipeline_wait(t1)
+    ctx.pipeline_wait(t2)
+    for got, exp in zip(o, ref):
+        assert np.array_equal(got[0].view(np.uint8), exp[0].view(np.uint8))
+        assert np.array_equal(got[1], exp[1])
+        assert np.array_equal(got[2], exp[2])
+        assert np.array_equal(got[3], exp[3])
