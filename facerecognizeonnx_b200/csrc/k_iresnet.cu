@@ -88,6 +88,22 @@ bool tc_make_map_3d_f32(CUtensorMap* map, const void* base, uint64_t c, uint64_t
   return r == CUDA_SUCCESS;
 }
 
+// 2-D tensor map of 8-byte elements [rows, cols] (dense), box = box_rows x box_cols, no swizzle,
+// out-of-range elements read as zero: whole NHWC pixel rows of a 16-channel fp32 map.
+bool tc_make_map_2d_u64(CUtensorMap* map, const void* base, uint64_t cols, uint64_t rows, uint32_t box_cols,
+                        uint32_t box_rows) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return false;
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {cols * 8};
+  cuuint32_t box[2] = {box_cols, box_rows};
+  cuuint32_t es[2] = {1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_UINT64, 2, const_cast<void*>(base), dims, strides, box, es,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
+}
+
 struct ConvLaunch {
   CUtensorMap a0, a1, b0, b1;
   CUtensorMap a_halo;      // halo mode: box = (a_rows / a_boxes) x 64

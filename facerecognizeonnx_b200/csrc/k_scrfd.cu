@@ -39,6 +39,8 @@ bool tc_make_map_2d_f32(CUtensorMap* map, const void* base, uint64_t rows, uint6
                         uint64_t pitch_elems, uint32_t box_rows);   // k_iresnet.cu
 bool tc_make_map_3d_f32(CUtensorMap* map, const void* base, uint64_t c, uint64_t w, uint64_t rows,
                         uint32_t box_c, uint32_t box_w, uint32_t box_rows);   // k_iresnet.cu
+bool tc_make_map_2d_u64(CUtensorMap* map, const void* base, uint64_t cols, uint64_t rows, uint32_t box_cols,
+                        uint32_t box_rows);                                     // k_iresnet.cu
 
 namespace {
 
@@ -56,7 +58,7 @@ using tc::tma_load_2d;
 constexpr int DET = FR_DET_SIZE;
 constexpr int TM = 128;                 // MMA M (tile rows; TH*TW of them are pixels)
 constexpr int A_BYTES = TM * 128;       // one 128 x 32 fp32 operand tile
-constexpr int MAX_STAGES = 4;
+constexpr int MAX_STAGES = 8;
 constexpr int CV_WARPS = 8;             // converter warps
 constexpr int FIRST_CV_WARP = 7;        // 0 input TMA, 1 MMA, 2-5 epilogue, 6 weight TMA
 constexpr int THREADS = (FIRST_CV_WARP + CV_WARPS) * 32;
@@ -90,21 +92,36 @@ struct SepParams {
   int num_m_tiles;
   int bw, bh, halo;     // input box (pixels) and its halo (1 for 3x3 stencils, 0 for 1x1)
   int in_bytes;         // bytes per input stage (rounded up to 1024)
+  int in_merged;        // cin == kc == 16: the map is 2-D over (W * 8 u64, N*H): one request per box row
   int s_in, s_ab;       // ring depths
   int tmem_cols;
   int nbig;             // hi*hi accumulators per tile (k steps alternate between them)
   int acc_stages;       // 2 = TMEM double buffered, 1 = single
+  long long* dbg;       // debug timeline [5 roles][256 slots][2] of clock64 (CTA 0 only), or null
   int* err_flag;
 };
 
 __device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
-__device__ __forceinline__ float4 lds4(const uint8_t* p) { return *reinterpret_cast<const float4*>(p); }
+// explicit shared-space accesses on 32-bit shared addresses (the generic pointer arithmetic
+// through the ring structs otherwise compiles to generic LD/ST)
+__device__ __forceinline__ float4 lds4(uint32_t a) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ void sts4(uint32_t a, const float4& v) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
 __device__ __forceinline__ float4 zero4() { return make_float4(0.f, 0.f, 0.f, 0.f); }
 
+// round-to-nearest (ties away) to the 10-bit tf32 mantissa: what cvt.rna.tf32.f32 does for finite
+// inputs, in two integer instructions (the PTX instruction expands to a NaN/Inf-safe sequence)
 __device__ __forceinline__ float tf32_rna(float x) {
-  uint32_t u;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
-  return __uint_as_float(u);
+  return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u);
+}
+
+__device__ __forceinline__ void dbg_stamp(const SepParams& p, int role, uint32_t idx, int ev) {
+  if (p.dbg && blockIdx.x == 0 && idx < 256) p.dbg[(role * 256 + idx) * 2 + ev] = clock64();
 }
 
 // x / d for d >= 1 and x * d < 2^32, with m = ceil(2^32 / d) (m == 0 encodes d == 1)
@@ -130,13 +147,13 @@ __device__ __forceinline__ uint32_t sw128(int row, int chunk) {
   return (uint32_t)row * 128u + (uint32_t)((chunk ^ (row & 7)) << 4);
 }
 
-__device__ __forceinline__ void split_store(uint8_t* hi, uint8_t* lo, uint32_t off, const float4& v) {
+__device__ __forceinline__ void split_store(uint32_t hi, uint32_t lo, uint32_t off, const float4& v) {
   float4 h, l;
   h.x = tf32_rna(v.x); h.y = tf32_rna(v.y); h.z = tf32_rna(v.z); h.w = tf32_rna(v.w);
   // the residual is rounded (not left to the tensor core's truncation) to tf32 as well
   l.x = tf32_rna(v.x - h.x); l.y = tf32_rna(v.y - h.y); l.z = tf32_rna(v.z - h.z); l.w = tf32_rna(v.w - h.w);
-  *reinterpret_cast<float4*>(hi + off) = h;
-  *reinterpret_cast<float4*>(lo + off) = l;
+  sts4(hi + off, h);
+  sts4(lo + off, l);
 }
 
 __device__ __forceinline__ void fma4(float4& acc, const float4& v, const float4& w) {
@@ -183,15 +200,26 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+__device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr)
+      : "memory");
+}
+
 // 16 accumulator columns of one row: hi*hi partial sum(s) + the cross-term accumulator, added
-// in fp32 with round-to-nearest ((big0 + big1) + small).
+// in fp32 with round-to-nearest ((big0 + big1) + small).  All TMEM loads are issued before the
+// single wait.
 __device__ __forceinline__ void ld_sum16(uint32_t taddr, uint32_t small_off, int nbig, uint32_t nt, uint32_t (&v)[16]) {
-  uint32_t s[16];
-  tmem_ld16(taddr, v);
-  tmem_ld16(taddr + small_off, s);
+  uint32_t s[16], b1[16];
+  tmem_ld16_nowait(taddr, v);
+  tmem_ld16_nowait(taddr + small_off, s);
+  if (nbig == 2) tmem_ld16_nowait(taddr + nt, b1);
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
   if (nbig == 2) {
-    uint32_t b1[16];
-    tmem_ld16(taddr + nt, b1);
 #pragma unroll
     for (int i = 0; i < 16; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) + __uint_as_float(b1[i]));
   }
@@ -242,18 +270,20 @@ __device__ __forceinline__ void converter_loop(const SepParams& p, const Rings& 
   // byte offset of the thread's window inside the box (row rr adds rr * bw * PP)
   const int box_off = (MODE == LD_PW ? (ty * p.bw + xg * PXT) : (ty * STRIDE * p.bw + xg * PXT * STRIDE)) * PP + chunk * 16;
   const int row_pitch = p.bw * PP;
+  const uint32_t in_base = smem_u32(r.in), ab_base = smem_u32(r.ab);
   const int total_tiles = p.num_m_tiles << p.n_shift;
   // depthwise weights of this thread's 4 channels: [tap][cin] + bias row, staged in shared memory
+  const uint32_t dw_base = smem_u32(s_dw);
   float4 w[9], b4 = zero4();
   auto load_dw = [&](int k0) {
     const bool kin = k0 < p.cin;
 #pragma unroll
-    for (int q = 0; q < 9; ++q) w[q] = kin ? *reinterpret_cast<const float4*>(s_dw + q * p.cin + k0) : zero4();
-    b4 = kin ? *reinterpret_cast<const float4*>(s_dw + 9 * p.cin + k0) : zero4();
+    for (int q = 0; q < 9; ++q) w[q] = kin ? lds4(dw_base + (uint32_t)((q * p.cin + k0) * 4)) : zero4();
+    b4 = kin ? lds4(dw_base + (uint32_t)((9 * p.cin + k0) * 4)) : zero4();
   };
   if (MODE == LD_DW) load_dw(chunk * 4);
   int si = 0, sa = 0;
-  uint32_t ph_in = 0, ph_ab = 0;
+  uint32_t ph_in = 0, ph_ab = 0, dbg_kb = 0, dbg_box = 0;
   for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
     const TileCoord tc = tile_coord(p, tile);
     const bool pix_ok = active && tc.gy0 + ty < p.rows_out;
@@ -261,14 +291,16 @@ __device__ __forceinline__ void converter_loop(const SepParams& p, const Rings& 
     if (y >= p.hout) y -= p.hout;
     for (int i = 0; i < p.n_in; ++i) {
       mbar_wait(&r.full_in[si], ph_in, p.err_flag);
-      const uint8_t* box = r.in + si * p.in_bytes + box_off;
+      if (t == 0) dbg_stamp(p, 3, dbg_box++, 1);
+      const uint32_t box = in_base + (uint32_t)(si * p.in_bytes + box_off);
       const int k0 = i * KC + chunk * 4;
       const bool kv = k0 < p.cin && pix_ok;
       if (MODE == LD_DW && p.n_in > 1) load_dw(k0);
       for (int tap = 0; tap < p.taps; ++tap) {
         mbar_wait(&r.empty_ab[sa], ph_ab ^ 1u, p.err_flag);
-        uint8_t* hi = r.ab + sa * r.ab_bytes;
-        uint8_t* lo = hi + A_BYTES;
+        if (t == 0) dbg_stamp(p, 0, dbg_kb, 0);
+        const uint32_t hi = ab_base + (uint32_t)(sa * r.ab_bytes);
+        const uint32_t lo = hi + A_BYTES;
         if (active) {
           float4 acc[PXT];
 #pragma unroll
@@ -281,7 +313,7 @@ __device__ __forceinline__ void converter_loop(const SepParams& p, const Rings& 
               for (int rr = 0; rr < 3; ++rr) {
                 const int iy = y * STRIDE - 1 + rr;
                 if (iy >= 0 && iy < p.hin) {      // rows outside the image hold a neighbour image's data
-                  const uint8_t* rb = box + rr * row_pitch;
+                  const uint32_t rb = box + (uint32_t)(rr * row_pitch);
                   float4 v[NV];
 #pragma unroll
                   for (int c = 0; c < NV; ++c) v[c] = lds4(rb + c * PP);
@@ -300,7 +332,7 @@ __device__ __forceinline__ void converter_loop(const SepParams& p, const Rings& 
               const int dy = tap / 3, dx = tap - dy * 3;
               const int iy = y * STRIDE - 1 + dy;
               if (iy >= 0 && iy < p.hin) {
-                const uint8_t* rb = box + dy * row_pitch + dx * PP;
+                const uint32_t rb = box + (uint32_t)(dy * row_pitch + dx * PP);
 #pragma unroll
                 for (int j = 0; j < PXT; ++j) acc[j] = lds4(rb + j * STRIDE * PP);
               }
@@ -316,6 +348,7 @@ __device__ __forceinline__ void converter_loop(const SepParams& p, const Rings& 
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncwarp();
         if (lane == 0) mbar_arrive(&r.full_ab[sa]);
+        if (t == 0) dbg_stamp(p, 0, dbg_kb++, 1);
         if (++sa == p.s_ab) { sa = 0; ph_ab ^= 1u; }
       }
       __syncwarp();
@@ -343,11 +376,13 @@ sep_gemm_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant_
   uint64_t* tfull = r.empty_ab + MAX_STAGES;
   uint64_t* tempty = tfull + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
-  float* s_dw = reinterpret_cast<float*>(tmem_slot + 4);   // [10][cin]: 9 depthwise taps + bias
+  float* s_bias = reinterpret_cast<float*>(tmem_slot + 4);   // [npad_total]
+  float* s_dw = s_bias + p.npad_total;                       // [10][cin]: 9 depthwise taps + bias
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
+  for (int i = threadIdx.x; i < p.npad_total; i += THREADS) s_bias[i] = p.bias[i];
   if (p.mode == LD_DW) {
     for (int i = threadIdx.x; i < 9 * p.cin; i += THREADS) s_dw[i] = p.dw_w[i];
     for (int i = threadIdx.x; i < p.cin; i += THREADS) s_dw[9 * p.cin + i] = p.dw_b[i];
@@ -385,15 +420,20 @@ sep_gemm_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant_
     if (lane == 0) {
       const uint32_t box_bytes = (uint32_t)(p.bh * p.bw * p.kc * 4);
       int s = 0;
-      uint32_t ph = 0;
+      uint32_t ph = 0, dbg_box = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         const TileCoord tc = tile_coord(p, tile);
         const int x0 = tc.txi * p.tw;
         for (int i = 0; i < p.n_in; ++i) {
           mbar_wait(&r.empty_in[s], ph ^ 1u, p.err_flag);
+          dbg_stamp(p, 3, dbg_box++, 0);
           mbar_expect_tx(&r.full_in[s], box_bytes);
-          tma_load_3d(r.in + s * p.in_bytes, &tmIn, &r.full_in[s], i * p.kc, x0 * p.stride - p.halo,
-                      tc.gy0 * p.stride - p.halo);
+          if (p.in_merged)
+            tma_load_2d(r.in + s * p.in_bytes, &tmIn, &r.full_in[s], (x0 * p.stride - p.halo) * 8,
+                        tc.gy0 * p.stride - p.halo);
+          else
+            tma_load_3d(r.in + s * p.in_bytes, &tmIn, &r.full_in[s], i * p.kc, x0 * p.stride - p.halo,
+                        tc.gy0 * p.stride - p.halo);
           if (++s == p.s_in) { s = 0; ph ^= 1u; }
         }
       }
@@ -402,11 +442,12 @@ sep_gemm_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant_
     // ------------------------------------------------------------- weight TMA
     if (lane == 0) {
       int s = 0;
-      uint32_t ph = 0;
+      uint32_t ph = 0, dbg_kb = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         const int n0 = (tile & (p.n_tiles_n - 1)) * p.nt;
         for (int kb = 0; kb < nkb; ++kb) {
           mbar_wait(&r.empty_ab[s], ph ^ 1u, p.err_flag);
+          dbg_stamp(p, 2, dbg_kb++, 0);
           mbar_expect_tx(&r.full_ab[s], 2u * (uint32_t)b_bytes);
           uint8_t* sb = r.ab + s * r.ab_bytes + 2 * A_BYTES;
           tma_load_2d(sb, &tmW, &r.full_ab[s], kb * 32, n0);
@@ -417,9 +458,22 @@ sep_gemm_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant_
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------- MMA issuer
-    if (lane == 0) {
+    // The whole warp runs this loop in uniform control flow (waits, counters and descriptor
+    // arithmetic stay on the uniform datapath); one elected lane issues the MMAs and commits.
+    // A shared-memory descriptor is (address >> 4) in its low 14 bits under constant upper
+    // bits, so stepping stages / K steps is a 32-bit add on the low word.
+    {
       const uint32_t idesc = make_idesc_tf32(TM, p.nt);
-      uint32_t tt = 0;
+      const uint64_t d0 = make_smem_desc(r.ab);
+      const uint32_t desc_hi = (uint32_t)(d0 >> 32);
+      const uint32_t a_lo0 = (uint32_t)d0;                         // A_hi tile of stage 0
+      const uint32_t stage_step = (uint32_t)r.ab_bytes >> 4;
+      const uint32_t off_alo = (uint32_t)A_BYTES >> 4, off_bhi = (uint32_t)(2 * A_BYTES) >> 4;
+      const uint32_t off_blo = (uint32_t)(2 * A_BYTES + b_bytes) >> 4;
+      const uint32_t nt = (uint32_t)p.nt;
+      const bool two_big = p.nbig == 2;
+      auto desc = [&](uint32_t lo) { return ((uint64_t)desc_hi << 32) | (uint64_t)lo; };
+      uint32_t tt = 0, dbg_kb = 0;
       int s = 0;
       uint32_t ph = 0;
       const uint32_t slot_cols = (uint32_t)((p.nbig + 1) * p.nt);
@@ -429,30 +483,38 @@ sep_gemm_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant_
         mbar_wait(&tempty[acc], acc_phase ^ 1u, p.err_flag);
         tc_fence_after();
         const uint32_t d_big = tmem_base + acc * slot_cols;
-        const uint32_t d_small = d_big + (uint32_t)(p.nbig * p.nt);
+        const uint32_t d_small = d_big + (uint32_t)p.nbig * nt;
         uint32_t ks_total = 0;
         int tap = 0, crem = p.cin;   // channels left from this K block's box on
         for (int kb = 0; kb < nkb; ++kb) {
           mbar_wait(&r.full_ab[s], ph, p.err_flag);
+          if (lane == 0) dbg_stamp(p, 1, dbg_kb, 0);
           tc_fence_after();
-          const uint8_t* sa = r.ab + s * r.ab_bytes;
-          const uint64_t ahi = make_smem_desc(sa);
-          const uint64_t alo = make_smem_desc(sa + A_BYTES);
-          const uint64_t bhi = make_smem_desc(sa + 2 * A_BYTES);
-          const uint64_t blo = make_smem_desc(sa + 2 * A_BYTES + b_bytes);
+          const uint32_t ahi = a_lo0 + (uint32_t)s * stage_step;
           const int ksteps = (min(p.kc, crem) + 7) >> 3;               // K = 8 tf32 per MMA
           if (++tap == p.taps) { tap = 0; crem -= p.kc; }
-          for (int k = 0; k < ksteps; ++k, ++ks_total) {
-            const uint64_t o = (uint64_t)(k * 2);   // +32 bytes inside the 128-byte swizzle row
-            mma_tf32(d_small, alo + o, bhi + o, idesc, ks_total ? 1u : 0u);
-            mma_tf32(d_small, ahi + o, blo + o, idesc, 1u);
-            const uint32_t which = p.nbig == 2 ? (ks_total & 1u) : 0u;
-            mma_tf32(d_big + which * (uint32_t)p.nt, ahi + o, bhi + o, idesc, ks_total >= (uint32_t)p.nbig ? 1u : 0u);
+          if (tc::elect_one()) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              if (k < ksteps) {
+                const uint32_t o = (uint32_t)(k * 2);   // +32 bytes inside the 128-byte swizzle row
+                const uint32_t kt = ks_total + (uint32_t)k;
+                mma_tf32(d_small, desc(ahi + off_alo + o), desc(ahi + off_bhi + o), idesc, kt ? 1u : 0u);
+                mma_tf32(d_small, desc(ahi + o), desc(ahi + off_blo + o), idesc, 1u);
+                const uint32_t which = two_big ? (kt & 1u) : 0u;
+                mma_tf32(d_big + which * nt, desc(ahi + o), desc(ahi + off_bhi + o), idesc, kt >= (uint32_t)p.nbig ? 1u : 0u);
+              }
+            }
+            tc_commit(&r.empty_ab[s]);
           }
-          tc_commit(&r.empty_ab[s]);
+          __syncwarp();
+          ks_total += (uint32_t)ksteps;
+          if (lane == 0) dbg_stamp(p, 1, dbg_kb, 1);
+          ++dbg_kb;
           if (++s == p.s_ab) { s = 0; ph ^= 1u; }
         }
-        tc_commit(&tfull[acc]);
+        if (tc::elect_one()) tc_commit(&tfull[acc]);
+        __syncwarp();
       }
     }
   } else if (warp < 6) {
@@ -470,6 +532,7 @@ sep_gemm_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant_
       const uint32_t acc = p.acc_stages == 2 ? (tt & 1u) : 0u;
       const uint32_t acc_phase = p.acc_stages == 2 ? ((tt >> 1) & 1u) : (tt & 1u);
       mbar_wait(&tfull[acc], acc_phase, p.err_flag);
+      if (warp == 2 && lane == 0) dbg_stamp(p, 4, tt, 0);
       tc_fence_after();
       const uint32_t taddr = tmem_base + acc * (uint32_t)((p.nbig + 1) * p.nt) + ((uint32_t)(q * 32) << 16);
       const uint32_t small_off = (uint32_t)(p.nbig * p.nt);
@@ -484,8 +547,8 @@ sep_gemm_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant_
           float f[32];
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
-            f[i] = __uint_as_float(v0[i]) + __ldg(p.bias + i);
-            f[16 + i] = __uint_as_float(v1[i]) + __ldg(p.bias + 16 + i);
+            f[i] = __uint_as_float(v0[i]) + s_bias[i];
+            f[16 + i] = __uint_as_float(v1[i]) + s_bias[16 + i];
           }
           float2 sc;
           sc.x = 1.0f / (1.0f + expf(-f[0]));
@@ -514,7 +577,7 @@ sep_gemm_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant_
             for (int j = 0; j < 4; ++j) {
               const int c = n0 + c0 + 4 * j;
               if (c < p.cout) {
-                const float4 b4 = ldg4(p.bias + c);
+                const float4 b4 = *reinterpret_cast<const float4*>(s_bias + c);
                 float4 f = make_float4(__uint_as_float(v[4 * j]) + b4.x, __uint_as_float(v[4 * j + 1]) + b4.y,
                                        __uint_as_float(v[4 * j + 2]) + b4.z, __uint_as_float(v[4 * j + 3]) + b4.w);
                 if (p.relu) {
@@ -538,6 +601,7 @@ sep_gemm_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant_
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty[acc]);
+      if (warp == 2 && lane == 0) dbg_stamp(p, 4, tt, 1);
     }
   } else if (warp >= FIRST_CV_WARP) {
     // ------------------------------------------------------------- A-operand converters
@@ -566,8 +630,11 @@ sep_gemm_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant_
 // ---------------------------------------------------------------------------------------
 // Stem: dense 3x3 stride-2 conv 3 -> 16 + bias + ReLU on the bf16 planar input produced by K1
 // (K = 27: CUDA cores; the layer is bound by its 6.5 MB / frame fp32 NHWC write).
-// One thread = one output pixel x 16 channels = one 64-byte NHWC record.
-__global__ void __launch_bounds__(256)
+// One thread = 4 horizontally adjacent output pixels x 16 channels: per (channel, row) one
+// 16-byte load brings input columns 2*ox .. 2*ox+7 and one 2-byte load column 2*ox-1; the
+// weights are broadcast from shared memory as float4 (1 LDS.128 per 16 FMAs); the thread
+// stores 256 contiguous bytes of NHWC output.
+__global__ void __launch_bounds__(128)
 stem_conv_kernel(const __nv_bfloat16* __restrict__ in, float* __restrict__ out, const float* __restrict__ w,
                  const float* __restrict__ b, int n_img) {
   __shared__ __align__(16) float sw[27 * 16];
@@ -575,42 +642,61 @@ stem_conv_kernel(const __nv_bfloat16* __restrict__ in, float* __restrict__ out, 
   for (int i = threadIdx.x; i < 27 * 16; i += blockDim.x) sw[i] = w[i];
   if (threadIdx.x < 16) sb[threadIdx.x] = b[threadIdx.x];
   __syncthreads();
-  constexpr int HO = DET / 2;
+  constexpr int HO = DET / 2, QW = HO / 4;
   const size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (gid >= (size_t)n_img * HO * HO) return;
-  const int n = (int)(gid / (HO * HO));
-  const int pp = (int)(gid - (size_t)n * HO * HO);
-  const int oy = pp / HO, ox = pp - oy * HO;
-  float acc[16];
+  if (gid >= (size_t)n_img * HO * QW) return;
+  const int n = (int)(gid / (HO * QW));
+  const int rem = (int)(gid - (size_t)n * HO * QW);
+  const int oy = rem / QW, ox0 = (rem - oy * QW) * 4;
+  float acc[4][16];
 #pragma unroll
-  for (int i = 0; i < 16; ++i) acc[i] = sb[i];
+  for (int j = 0; j < 4; ++j)
+#pragma unroll
+    for (int i = 0; i < 16; ++i) acc[j][i] = sb[i];
   const __nv_bfloat16* ip = in + (size_t)n * 3 * DET * DET;
 #pragma unroll
   for (int c = 0; c < 3; ++c)
 #pragma unroll
     for (int r = 0; r < 3; ++r) {
       const int iy = oy * 2 - 1 + r;
+      float v[9];   // input columns 2*ox0-1 .. 2*ox0+7
+#pragma unroll
+      for (int i = 0; i < 9; ++i) v[i] = 0.f;
+      if (iy >= 0 && iy < DET) {
+        const __nv_bfloat16* rp = ip + ((size_t)c * DET + iy) * DET + 2 * ox0;
+        const uint4 q = __ldg(reinterpret_cast<const uint4*>(rp));
+        const uint32_t qq[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          v[1 + 2 * i] = __uint_as_float(qq[i] << 16);
+          v[2 + 2 * i] = __uint_as_float(qq[i] & 0xffff0000u);
+        }
+        if (ox0 > 0) v[0] = __bfloat162float(rp[-1]);
+      }
 #pragma unroll
       for (int s = 0; s < 3; ++s) {
-        const int ix = ox * 2 - 1 + s;
-        float v = 0.f;
-        if (iy >= 0 && iy < DET && ix >= 0 && ix < DET) v = __bfloat162float(ip[((size_t)c * DET + iy) * DET + ix]);
         const float4* wp = reinterpret_cast<const float4*>(&sw[((c * 3 + r) * 3 + s) * 16]);
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           const float4 w4 = wp[i];
-          acc[4 * i] = fmaf(v, w4.x, acc[4 * i]);
-          acc[4 * i + 1] = fmaf(v, w4.y, acc[4 * i + 1]);
-          acc[4 * i + 2] = fmaf(v, w4.z, acc[4 * i + 2]);
-          acc[4 * i + 3] = fmaf(v, w4.w, acc[4 * i + 3]);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float x = v[2 * j + s];
+            acc[j][4 * i] = fmaf(x, w4.x, acc[j][4 * i]);
+            acc[j][4 * i + 1] = fmaf(x, w4.y, acc[j][4 * i + 1]);
+            acc[j][4 * i + 2] = fmaf(x, w4.z, acc[j][4 * i + 2]);
+            acc[j][4 * i + 3] = fmaf(x, w4.w, acc[j][4 * i + 3]);
+          }
         }
       }
     }
-  float4* op = reinterpret_cast<float4*>(out + gid * 16);
+  float4* op = reinterpret_cast<float4*>(out + (((size_t)n * HO + oy) * HO + ox0) * 16);
 #pragma unroll
-  for (int i = 0; i < 4; ++i)
-    op[i] = make_float4(fmaxf(acc[4 * i], 0.f), fmaxf(acc[4 * i + 1], 0.f), fmaxf(acc[4 * i + 2], 0.f),
-                        fmaxf(acc[4 * i + 3], 0.f));
+  for (int j = 0; j < 4; ++j)
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      op[j * 4 + i] = make_float4(fmaxf(acc[j][4 * i], 0.f), fmaxf(acc[j][4 * i + 1], 0.f),
+                                  fmaxf(acc[j][4 * i + 2], 0.f), fmaxf(acc[j][4 * i + 3], 0.f));
 }
 
 }  // namespace
@@ -826,19 +912,21 @@ int launch_layer(fr_ctx* ctx, const PackedConv& pc, const LayerIO& io, int n) {
     if (p.kc == 16 && p.stride == 1 && p.bw % 2 == 0) p.bw++;
   }
   p.in_bytes = (p.bh * p.bw * p.kc * 4 + 1023) / 1024 * 1024;
+  p.in_merged = (pc.cin == 16 && pc.kc == 16 && p.bw * 8 <= 256) ? 1 : 0;
   const int ab_bytes = 2 * A_BYTES + 2 * pc.nt * 128;
   const int dw_bytes = pc.mode == LD_DW ? (10 * pc.cin * 4 + 15) / 16 * 16 : 0;
-  const int budget = 227 * 1024 - 1024 - 512 - dw_bytes;
+  const int budget = 227 * 1024 - 1024 - 512 - dw_bytes - pc.npad_total * 4;
   p.s_in = 2;
   p.s_ab = 2;
   if (p.s_in * p.in_bytes + p.s_ab * ab_bytes > budget)
     return fr_fail(ctx, FR_ERR_UNSUPPORTED, "scrfd layer does not fit shared memory");
-  for (int round = 0; round < 2 * MAX_STAGES; ++round) {
-    int& grow = (round & 1) ? p.s_ab : p.s_in;
-    const int add = (round & 1) ? ab_bytes : p.in_bytes;
-    if (grow < MAX_STAGES && p.s_in * p.in_bytes + p.s_ab * ab_bytes + add <= budget) grow++;
-  }
-  p.nbig = pc.cin * pc.taps <= 16 ? 1 : 2;
+  // A/B stages to 3, then input boxes (TMA latency under load is ~3 us: keep many in flight), then A/B to 4
+  auto fits = [&](int add) { return p.s_in * p.in_bytes + p.s_ab * ab_bytes + add <= budget; };
+  if (fits(ab_bytes)) p.s_ab++;
+  while (p.s_in < MAX_STAGES && fits(p.in_bytes)) p.s_in++;
+  if (p.s_ab < 4 && fits(ab_bytes)) p.s_ab++;
+  // a second hi*hi accumulator only where one would take more than 12 truncating accumulations
+  p.nbig = pc.cin * pc.taps <= 96 ? 1 : 2;
   const int slot = (p.nbig + 1) * pc.nt;
   if (slot > 512) return fr_fail(ctx, FR_ERR_UNSUPPORTED, "scrfd layer does not fit tensor memory");
   p.acc_stages = 2 * slot <= 512 ? 2 : 1;
@@ -848,18 +936,40 @@ int launch_layer(fr_ctx* ctx, const PackedConv& pc, const LayerIO& io, int n) {
   p.err_flag = m->err_flag;
   const int rows_in = n * io.hin;
   if (pc.tm_in != io.in || pc.tm_rows != rows_in || pc.tm_bw != p.bw || pc.tm_bh != p.bh) {
-    if (!tc_make_map_3d_f32(&pc.tmIn, io.in, (uint64_t)pc.cin, (uint64_t)io.hin, (uint64_t)rows_in, (uint32_t)p.kc,
-                            (uint32_t)p.bw, (uint32_t)p.bh))
+    const bool ok_map = p.in_merged
+        ? tc_make_map_2d_u64(&pc.tmIn, io.in, (uint64_t)io.hin * 8, (uint64_t)rows_in, (uint32_t)p.bw * 8, (uint32_t)p.bh)
+        : tc_make_map_3d_f32(&pc.tmIn, io.in, (uint64_t)pc.cin, (uint64_t)io.hin, (uint64_t)rows_in, (uint32_t)p.kc,
+                             (uint32_t)p.bw, (uint32_t)p.bh);
+    if (!ok_map)
       return fr_fail(ctx, FR_ERR_CUDA, "scrfd input tensor map creation failed");
     pc.tm_in = io.in;
     pc.tm_rows = rows_in;
     pc.tm_bw = p.bw;
     pc.tm_bh = p.bh;
   }
-  const int smem = p.s_in * p.in_bytes + p.s_ab * ab_bytes + 1024 + 512 + dw_bytes;
+  const int smem = p.s_in * p.in_bytes + p.s_ab * ab_bytes + 1024 + 512 + dw_bytes + pc.npad_total * 4;
   const int total_tiles = p.num_m_tiles * p.n_tiles_n;
   const int grid = std::min(total_tiles, m->num_sms);
+  static const char* dbg_env = getenv("FR_SCRFD_DBG");   // "<launch index>:<file>"
+  static int dbg_count = 0;
+  long long* dbg_buf = nullptr;
+  if (dbg_env && atoi(dbg_env) == dbg_count++) {
+    cudaMallocManaged(&dbg_buf, 5 * 256 * 2 * sizeof(long long));
+    memset(dbg_buf, 0, 5 * 256 * 2 * sizeof(long long));
+    p.dbg = dbg_buf;
+  }
   sep_gemm_kernel<<<grid, THREADS, smem, ctx->stream>>>(pc.tmIn, pc.tmW, p);
+  if (dbg_buf) {
+    cudaStreamSynchronize(ctx->stream);
+    FILE* f = fopen(strchr(dbg_env, ':') + 1, "w");
+    if (f) {
+      fprintf(f, "# nkb_per_tile=%d n_in=%d taps=%d nt=%d s_in=%d s_ab=%d kc=%d\n", pc.n_in * pc.taps, pc.n_in, pc.taps, pc.nt, p.s_in, p.s_ab, p.kc);
+      for (int r = 0; r < 5; ++r)
+        for (int i = 0; i < 256; ++i) fprintf(f, "%d %d %lld %lld\n", r, i, dbg_buf[(r * 256 + i) * 2], dbg_buf[(r * 256 + i) * 2 + 1]);
+      fclose(f);
+    }
+    cudaFree(dbg_buf);
+  }
   ctx->launches++;
   FR_CUDA_OK(ctx, cudaGetLastError());
   return FR_OK;
@@ -958,8 +1068,8 @@ int det_forward(fr_ctx* ctx, const __nv_bfloat16* d_in_chw, int n, HeadPtrs* hea
   FR_CHECK(det_build_acts(ctx, cap));
   // stem: 3x3 s2, 3 -> 16, ReLU (bf16 planar input from K1) -> fp32 NHWC
   {
-    const size_t total = (size_t)n * (DET / 2) * (DET / 2);
-    stem_conv_kernel<<<(unsigned)((total + 255) / 256), 256, 0, ctx->stream>>>(d_in_chw, m->a_stem, m->stem_w,
+    const size_t total = (size_t)n * (DET / 2) * (DET / 2 / 4);
+    stem_conv_kernel<<<(unsigned)((total + 127) / 128), 128, 0, ctx->stream>>>(d_in_chw, m->a_stem, m->stem_w,
                                                                                 m->stem_b, n);
     ctx->launches++;
     FR_CUDA_OK(ctx, cudaGetLastError());
