@@ -385,8 +385,16 @@ shift_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    // The whole warp runs the loop in uniform control flow (waits, counters and descriptor
+    // arithmetic on the uniform datapath); one elected lane issues the MMAs and the commits.
+    // A shared-memory descriptor carries (address >> 4) in its low 14 bits under constant upper
+    // bits, so stepping stages / K steps is a 32-bit add on the low word.
+    {
       constexpr uint32_t idesc = make_idesc(BM, BN);
+      const uint64_t d0 = make_smem_desc(smem);
+      const uint32_t desc_hi = (uint32_t)(d0 >> 32);
+      const uint32_t lo0 = (uint32_t)d0;
+      auto desc = [&](uint32_t lo) { return ((uint64_t)desc_hi << 32) | (uint64_t)lo; };
       int stage = 0;
       uint32_t phase = 0;
       uint32_t it = 0;
@@ -402,21 +410,22 @@ shift_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
           for (int kb = 0; kb < nkb; ++kb) {
             mbar_wait(&full[stage], phase, p.err_flag);
             tc_fence_after();
-            const uint8_t* sa = smem + stage * C::STAGE_BYTES;
-            const uint64_t adesc = make_smem_desc(sa);
-            const uint64_t bdesc = make_smem_desc(sa + A_TILE_BYTES);
+            const uint32_t alo = lo0 + (uint32_t)stage * (uint32_t)(C::STAGE_BYTES >> 4);
+            const uint32_t blo = alo + (uint32_t)(A_TILE_BYTES >> 4);
+            if (elect_one()) {
 #pragma unroll
-            for (int k = 0; k < BK / 16; ++k) {
-              // advance 16 bf16 = 32 bytes inside the 128-byte swizzle row: +2 in 16-byte units
-              mma_bf16(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc,
-                       accumulate);
-              accumulate = 1;
+              for (int k = 0; k < BK / 16; ++k)
+                // advance 16 bf16 = 32 bytes inside the 128-byte swizzle row: +2 in 16-byte units
+                mma_bf16(d_tmem, desc(alo + k * 2), desc(blo + k * 2), idesc, (accumulate | (uint32_t)k) ? 1u : 0u);
+              tc_commit(&empty[stage]);
             }
-            tc_commit(&empty[stage]);
+            __syncwarp();
+            accumulate = 1;
             if (++stage == C::STAGES) { stage = 0; phase ^= 1u; }
           }
         }
-        tc_commit(&tfull[acc]);
+        if (elect_one()) tc_commit(&tfull[acc]);
+        __syncwarp();
       }
     }
   } else {
@@ -546,8 +555,15 @@ halo_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    // warp-uniform loop, one elected lane issues (see shift_gemm_kernel)
+    {
       constexpr uint32_t idesc = make_idesc(BM, BN);
+      const uint64_t d0 = make_smem_desc(sA);
+      const uint32_t desc_hi = (uint32_t)(d0 >> 32);
+      const uint32_t a_lo0 = (uint32_t)d0;
+      const uint32_t b_lo0 = (uint32_t)make_smem_desc(sB);
+      auto desc = [&](uint32_t lo) { return ((uint64_t)desc_hi << 32) | (uint64_t)lo; };
+      const uint32_t a_step = (uint32_t)a_bytes >> 4;
       int sa = 0, sb = 0;
       uint32_t pa = 0, pb = 0, it = 0;
       if (RESB) {
@@ -563,36 +579,42 @@ halo_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         for (int kb = 0; kb < nkb; ++kb) {
           mbar_wait(&afull[sa], pa, p.err_flag);
           tc_fence_after();
-          const uint8_t* ablk = sA + sa * a_bytes;
+          const uint32_t ablk = a_lo0 + (uint32_t)sa * a_step;
+#pragma unroll
           for (int t = 0; t < 9; ++t) {
-            const uint8_t* btile;
+            uint32_t btile;
             if (RESB) {
-              btile = sB + t * C::B_TILE_BYTES;
+              btile = b_lo0 + (uint32_t)t * (uint32_t)(C::B_TILE_BYTES >> 4);
             } else {
               mbar_wait(&bfull[sb], pb, p.err_flag);
               tc_fence_after();
-              btile = sB + sb * C::B_TILE_BYTES;
+              btile = b_lo0 + (uint32_t)sb * (uint32_t)(C::B_TILE_BYTES >> 4);
             }
-            const int off_rows = (t / 3) * wp + (t % 3);
-            const uint64_t bdesc = make_smem_desc(btile);
+            // a row of the A block is 128 bytes = 8 descriptor units
+            const uint32_t off_rows = (uint32_t)((t / 3) * wp + (t % 3)) * 8u;
             const uint32_t accumulate = (kb | t) ? 1u : 0u;
+            if (elect_one()) {
 #pragma unroll
-            for (int mt = 0; mt < MT; ++mt) {
-              const uint64_t adesc = make_smem_desc(ablk + (mt * BM + off_rows) * 128);
+              for (int mt = 0; mt < MT; ++mt) {
+                const uint32_t adesc = ablk + off_rows + (uint32_t)(mt * BM) * 8u;
 #pragma unroll
-              for (int k = 0; k < BK / 16; ++k)
-                mma_bf16(d_tmem + mt * BN, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc,
-                         (accumulate | (uint32_t)k) ? 1u : 0u);
+                for (int k = 0; k < BK / 16; ++k)
+                  mma_bf16(d_tmem + mt * BN, desc(adesc + k * 2), desc(btile + k * 2), idesc,
+                           (accumulate | (uint32_t)k) ? 1u : 0u);
+              }
+              if (!RESB) tc_commit(&bempty[sb]);
             }
+            __syncwarp();
             if (!RESB) {
-              tc_commit(&bempty[sb]);
               if (++sb == C::B_STAGES) { sb = 0; pb ^= 1u; }
             }
           }
-          tc_commit(&aempty[sa]);
+          if (elect_one()) tc_commit(&aempty[sa]);
+          __syncwarp();
           if (++sa == C::A_STAGES) { sa = 0; pa ^= 1u; }
         }
-        tc_commit(&tfull[acc]);
+        if (elect_one()) tc_commit(&tfull[acc]);
+        __syncwarp();
       }
     }
   } else {
