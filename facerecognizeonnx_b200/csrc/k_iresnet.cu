@@ -172,8 +172,9 @@ int tc_launch(fr_ctx* ctx, ConvLaunch& L, int m_rows) {
                                            cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); \
       set_ = true;                                                                                 \
     }                                                                                              \
-    tc::halo_gemm_kernel<BN_, MT_, RB_><<<hgrid, tc::NUM_THREADS,                                  \
-        tc::HaloCfg<BN_, MT_, RB_>::smem_bytes(L.p.a_rows), ctx->stream>>>(L.a_halo, L.b0, L.p);   \
+    L.p.a_stages = std::min(env_flag("FR_TC_ASTAGES", 2), tc::HaloCfg<BN_, MT_, RB_>::pick_a_stages(L.p.a_rows)); \
+    tc::halo_gemm_kernel<BN_, MT_, RB_><<<hgrid, tc::CONV_THREADS,                                  \
+        tc::HaloCfg<BN_, MT_, RB_>::smem_bytes(L.p.a_rows, L.p.a_stages), ctx->stream>>>(L.a_halo, L.b0, L.p);   \
   } while (0)
     if (L.bn == 64 && L.resb) { if (L.mt == 2) FR_HALO_LAUNCH(64, 2, true); else FR_HALO_LAUNCH(64, 1, true); }
     else if (L.bn == 64) { if (L.mt == 2) FR_HALO_LAUNCH(64, 2, false); else FR_HALO_LAUNCH(64, 1, false); }
@@ -186,15 +187,15 @@ int tc_launch(fr_ctx* ctx, ConvLaunch& L, int m_rows) {
   }
   switch (L.bn) {
     case 64:
-      tc::shift_gemm_kernel<64><<<grid, tc::NUM_THREADS, tc::Cfg<64>::SMEM_BYTES, ctx->stream>>>(
+      tc::shift_gemm_kernel<64><<<grid, tc::CONV_THREADS, tc::Cfg<64>::SMEM_BYTES, ctx->stream>>>(
           L.a0, L.a1, L.b0, L.b1, L.p);
       break;
     case 128:
-      tc::shift_gemm_kernel<128><<<grid, tc::NUM_THREADS, tc::Cfg<128>::SMEM_BYTES, ctx->stream>>>(
+      tc::shift_gemm_kernel<128><<<grid, tc::CONV_THREADS, tc::Cfg<128>::SMEM_BYTES, ctx->stream>>>(
           L.a0, L.a1, L.b0, L.b1, L.p);
       break;
     default:
-      tc::shift_gemm_kernel<256><<<grid, tc::NUM_THREADS, tc::Cfg<256>::SMEM_BYTES, ctx->stream>>>(
+      tc::shift_gemm_kernel<256><<<grid, tc::CONV_THREADS, tc::Cfg<256>::SMEM_BYTES, ctx->stream>>>(
           L.a0, L.a1, L.b0, L.b1, L.p);
       break;
   }

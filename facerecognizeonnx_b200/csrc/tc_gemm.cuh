@@ -33,7 +33,9 @@ constexpr int BM = 128;
 constexpr int BK = 64;
 constexpr int A_TILE_BYTES = BM * BK * 2;
 constexpr int MAX_TAPS = 10;
-constexpr int NUM_THREADS = 192;
+constexpr int NUM_THREADS = 192;        // gallery kernel: TMA warp, MMA warp, 4 epilogue warps
+constexpr int EPI_WARPS = 8;            // conv kernels: two warps per TMEM lane quarter, each half the columns
+constexpr int CONV_THREADS = (2 + EPI_WARPS) * 32;
 
 struct Tap {
   int a_src;        // 0/1: which A tensor map
@@ -73,6 +75,7 @@ struct Params {
   int a_rows;        // multiple of 8 (and of 16 when loaded as two boxes)
   int a_boxes;       // 1 or 2 TMA boxes per A block
   int base_off_mode; // 0: descriptor base_offset = 0; 1: base_offset = (addr >> 7) & 7
+  int a_stages;      // halo mode: A blocks in flight
 };
 
 template <int BN> struct Cfg {
@@ -209,7 +212,8 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
 // Epilogue of one output tile for one thread (= one accumulator row): TMEM -> registers ->
 // bias / PReLU / residual -> global.  All 32 lanes of the warp must call it (tcgen05.ld).
 template <int BN>
-__device__ __forceinline__ void epilogue_tile(const Params& p, uint32_t taddr0, int m, int n0, int split) {
+__device__ __forceinline__ void epilogue_tile(const Params& p, uint32_t taddr0, int m, int n0, int split,
+                                              int c_begin, int c_end) {
   bool valid = m < p.m_rows;
   int img = 0, hp = 0, wp = 0;
   if (valid && p.out_mode != OUT_F32) {
@@ -240,7 +244,7 @@ __device__ __forceinline__ void epilogue_tile(const Params& p, uint32_t taddr0, 
     out_off = (size_t)split * p.split_stride + (size_t)m * p.cout + n0;
   }
 #pragma unroll 1
-  for (int c = 0; c < BN / 32; ++c) {
+  for (int c = c_begin; c < c_end; ++c) {
     uint32_t v[32];
     tmem_ld32(taddr0 + c * 32, v);
     if (valid) {
@@ -313,7 +317,7 @@ __device__ __forceinline__ void tile_coords(const Params& p, int tile, int& m_ti
 
 // ------------------------------------------------------------------------ kernel
 template <int BN>
-__global__ void __launch_bounds__(NUM_THREADS, 1)
+__global__ void __launch_bounds__(CONV_THREADS, 1)
 shift_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                   const __grid_constant__ CUtensorMap tmB0, const __grid_constant__ CUtensorMap tmB1,
                   const __grid_constant__ Params p) {
@@ -337,7 +341,7 @@ shift_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tfull[a], 1);
-      mbar_init(&tempty[a], 4);
+      mbar_init(&tempty[a], EPI_WARPS);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     prefetch_tmap(&tmA0);
@@ -431,6 +435,8 @@ shift_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
   } else {
     const int q = warp & 3;            // TMEM lane quarter this warp may access
     const int row = q * 32 + lane;
+    constexpr int CPS = BN / 32 / (EPI_WARPS / 4);   // 32-column chunks per warp
+    const int c_begin = ((warp - 2) >> 2) * CPS;
     uint32_t it = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
       int m_tile, n_tile, split;
@@ -440,7 +446,7 @@ shift_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
       mbar_wait(&tfull[acc], acc_phase, p.err_flag);
       tc_fence_after();
       const uint32_t taddr0 = tmem_base + acc * BN + ((uint32_t)(q * 32) << 16);
-      epilogue_tile<BN>(p, taddr0, m_tile * BM + row, n_tile * BN, split);
+      epilogue_tile<BN>(p, taddr0, m_tile * BM + row, n_tile * BN, split, c_begin, c_begin + CPS);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty[acc]);
@@ -466,19 +472,24 @@ shift_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
 // through their own ring.  Cuts the L2->SMEM traffic of the feed-bound layers 1.4-2.1x.
 template <int BN, int MT, bool RESB> struct HaloCfg {
   static constexpr int B_TILE_BYTES = BN * BK * 2;
-  static constexpr int A_STAGES = 2;
+  static constexpr int MAX_A_STAGES = 6;   // runtime p.a_stages: as many A blocks in flight as shared memory allows
   static constexpr int B_STAGES = 4;
   static constexpr int ACC_STAGES = (2 * MT * BN <= 512) ? 2 : 1;
   static constexpr int TMEM_COLS = ACC_STAGES * MT * BN < 32 ? 32 : ACC_STAGES * MT * BN;
   static constexpr int B_BYTES = RESB ? 9 * B_TILE_BYTES : B_STAGES * B_TILE_BYTES;
-  static int smem_bytes(int a_rows) { return A_STAGES * a_rows * 128 + B_BYTES + 256 + 1024; }
+  static int smem_bytes(int a_rows, int a_stages) { return a_stages * a_rows * 128 + B_BYTES + 256 + 1024; }
+  static int pick_a_stages(int a_rows) {
+    int s = 2;
+    while (s < MAX_A_STAGES && smem_bytes(a_rows, s + 1) <= 227 * 1024) ++s;
+    return s;
+  }
 };
 
 // MT   : M tiles (of 128 rows) per CTA iteration; they share one A block of
 //        MT*128 + 2*Wp + 2 rows and every streamed weight tile (halves the weight traffic)
 // RESB : Cin == 64 only: all nine weight tiles stay resident in shared memory
 template <int BN, int MT, bool RESB>
-__global__ void __launch_bounds__(NUM_THREADS, 1)
+__global__ void __launch_bounds__(CONV_THREADS, 1)
 halo_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ Params p) {
   using C = HaloCfg<BN, MT, RESB>;
@@ -487,10 +498,10 @@ halo_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                                              ~static_cast<uintptr_t>(1023));
   const int a_bytes = p.a_rows * 128;              // multiple of 1024
   uint8_t* sA = smem;
-  uint8_t* sB = smem + C::A_STAGES * a_bytes;
+  uint8_t* sB = smem + p.a_stages * a_bytes;
   uint64_t* afull = reinterpret_cast<uint64_t*>(sB + C::B_BYTES);
-  uint64_t* aempty = afull + C::A_STAGES;
-  uint64_t* bfull = aempty + C::A_STAGES;
+  uint64_t* aempty = afull + C::MAX_A_STAGES;
+  uint64_t* bfull = aempty + C::MAX_A_STAGES;
   uint64_t* bempty = bfull + C::B_STAGES;
   uint64_t* tfull = bempty + C::B_STAGES;
   uint64_t* tempty = tfull + 2;
@@ -500,9 +511,9 @@ halo_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   if (warp == 0 && lane == 0) {
-    for (int s = 0; s < C::A_STAGES; ++s) { mbar_init(&afull[s], 1); mbar_init(&aempty[s], 1); }
+    for (int s = 0; s < C::MAX_A_STAGES; ++s) { mbar_init(&afull[s], 1); mbar_init(&aempty[s], 1); }
     for (int s = 0; s < C::B_STAGES; ++s) { mbar_init(&bfull[s], 1); mbar_init(&bempty[s], 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 4); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], EPI_WARPS); }
     mbar_init(resfull, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     prefetch_tmap(&tmA);
@@ -542,7 +553,7 @@ halo_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           for (int bx = 0; bx < p.a_boxes; ++bx)
             tma_load_2d(sA + sa * a_bytes + bx * box_rows * 128, &tmA, &afull[sa], kb * BK,
                         m0 - wp - 1 + bx * box_rows);
-          if (++sa == C::A_STAGES) { sa = 0; pa ^= 1u; }
+          if (++sa == p.a_stages) { sa = 0; pa ^= 1u; }
           if (!RESB) {
             for (int t = 0; t < 9; ++t) {
               mbar_wait(&bempty[sb], pb ^ 1u, p.err_flag);
@@ -611,7 +622,7 @@ halo_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           }
           if (elect_one()) tc_commit(&aempty[sa]);
           __syncwarp();
-          if (++sa == C::A_STAGES) { sa = 0; pa ^= 1u; }
+          if (++sa == p.a_stages) { sa = 0; pa ^= 1u; }
         }
         if (elect_one()) tc_commit(&tfull[acc]);
         __syncwarp();
@@ -620,6 +631,8 @@ halo_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   } else {
     const int q = warp & 3;
     const int row = q * 32 + lane;
+    constexpr int CPS = BN / 32 / (EPI_WARPS / 4);   // 32-column chunks per warp
+    const int c_begin = ((warp - 2) >> 2) * CPS;
     uint32_t it = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
       const int m0 = (tile / p.n_tiles_n) * (BM * MT);
@@ -631,7 +644,7 @@ halo_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll 1
       for (int mt = 0; mt < MT; ++mt) {
         const uint32_t taddr0 = tmem_base + acc * (MT * BN) + mt * BN + ((uint32_t)(q * 32) << 16);
-        epilogue_tile<BN>(p, taddr0, m0 + mt * BM + row, n0, 0);
+        epilogue_tile<BN>(p, taddr0, m0 + mt * BM + row, n0, 0, c_begin, c_begin + CPS);
       }
       tc_fence_before();
       __syncwarp();
