@@ -205,7 +205,7 @@ def run_reference(args, rank, world):
                              "sample": f"{args.steps} steps x (1 frame det + 8 faces align+embed); torch-CPU fp32 + cv2 "
                                        "stand-in for ORT-CPU + OpenCV, batch 1 per call, all host threads"},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # --------------------------------------------------------------------------- GPU arm
@@ -375,7 +375,7 @@ def run_gpu(args, rank, world, local_rank):
                         "ms_per_step": 1e3 * e2e_s / args.steps},
                 "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
                 "cpu_baseline": cpu_baseline, "gallery_1toN": gallery, "detail": extra}
-        print(json.dumps(line), flush=True)
+        emit(line)
     ctx.close()
     if world > 1:
         dist.destroy_process_group()
@@ -443,7 +443,25 @@ def bench_gallery(ctx, capi, torch, dist, dev, rank, world, stream, peaks, rows_
             "merge": "NCCL all_gather_into_tensor + fr_topk_merge" if world > 1 else "fr_topk_merge (1 shard)"}
 
 
+_JSON_FD = None
+
+
+def emit(line: dict) -> None:
+    """The ONE JSON line goes to the real stdout; everything else the process (or NCCL, which
+    prints its version banner with printf) writes to fd 1 has been redirected to stderr."""
+    data = (json.dumps(line) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, data)
+
+
 def main():
+    global _JSON_FD
+    sys.stdout.flush()
+    _JSON_FD = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
