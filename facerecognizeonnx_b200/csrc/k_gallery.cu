@@ -146,12 +146,29 @@ gallery_topk_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         uint32_t v[32];
         tmem_ld32(taddr0 + c * 32, v);
         const int cb = col0 + c * 32;
+        // Fast path: one compare per score against the current k-th best builds a candidate
+        // bit mask; almost always it is empty.  (Written as a branch on the mask so that the
+        // compiler cannot if-convert the 16-step insertion into every element's path.)
+        const float thr = ts[TOPK - 1];
+        uint32_t mask = 0;
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const float s = __uint_as_float(v[i]);
-          if (s > ts[TOPK - 1] && cb + i < p.n_rows) {
-            float cs = s;
-            int ci = cb + i;
+        for (int i = 0; i < 32; ++i) mask |= (__uint_as_float(v[i]) > thr) ? (1u << i) : 0u;
+        while (mask) {
+          const int i = __ffs(mask) - 1;
+          mask &= mask - 1;
+          // v[i] with a runtime i: 5-level select tree over the registers
+          uint32_t a16[16], a8[8], a4[4], a2[2];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) a16[j] = (i & 16) ? v[16 + j] : v[j];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) a8[j] = (i & 8) ? a16[8 + j] : a16[j];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) a4[j] = (i & 4) ? a8[4 + j] : a8[j];
+#pragma unroll
+          for (int j = 0; j < 2; ++j) a2[j] = (i & 2) ? a4[2 + j] : a4[j];
+          float cs = __uint_as_float((i & 1) ? a2[1] : a2[0]);
+          int ci = cb + i;
+          if (cs > ts[TOPK - 1] && ci < p.n_rows) {   // re-check: the threshold rises as we insert
             bool ins = false;   // once inserted, everything below shifts down by one
 #pragma unroll
             for (int j = 0; j < TOPK; ++j)
