@@ -142,6 +142,12 @@ static bool tc_setup_halo(ConvLaunch& L, const void* base, uint64_t rows, int ci
 
 int tc_launch(fr_ctx* ctx, ConvLaunch& L, int m_rows) {
   L.p.m_rows = m_rows;
+  {
+    const unsigned long long per_img = (unsigned long long)std::max(L.p.Hp * L.p.Wp, 1);
+    L.p.per_img_magic = ((1ull << 40) + per_img - 1) / per_img;
+    const unsigned long long wp = (unsigned long long)std::max(L.p.Wp, 1);
+    L.p.wp_magic = wp == 1 ? 0xffffffffu : (uint32_t)(((1ull << 32) + wp - 1) / wp);
+  }
   L.p.num_m_tiles = ceil_div(m_rows, tc::BM);
   const int total = L.p.num_m_tiles * L.p.n_tiles_n * (L.p.k_splits > 1 ? L.p.k_splits : 1);
   if (total <= 0) return FR_OK;

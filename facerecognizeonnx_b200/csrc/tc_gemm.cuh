@@ -76,6 +76,10 @@ struct Params {
   int a_boxes;       // 1 or 2 TMA boxes per A block
   int base_off_mode; // 0: descriptor base_offset = 0; 1: base_offset = (addr >> 7) & 7
   int a_stages;      // halo mode: A blocks in flight
+  // exact division by multiply-shift: m / (Hp*Wp) = m * ceil(2^40 / (Hp*Wp)) >> 40 for m * Hp*Wp < 2^40,
+  // r / Wp = umulhi(r, ceil(2^32 / Wp)) for r < Hp*Wp
+  unsigned long long per_img_magic;
+  uint32_t wp_magic;
 };
 
 template <int BN> struct Cfg {
@@ -189,6 +193,10 @@ __device__ __forceinline__ void mma_bf16(uint32_t tmem_d, uint64_t adesc, uint64
       : "r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ uint32_t fast_div(uint32_t x, uint32_t magic) { return __umulhi(x, magic); }
+
+template <bool WAIT = true>
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -201,7 +209,7 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
         "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
       : "r"(taddr)
       : "memory");
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+  if (WAIT) asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
@@ -218,9 +226,9 @@ __device__ __forceinline__ void epilogue_tile(const Params& p, uint32_t taddr0, 
   int img = 0, hp = 0, wp = 0;
   if (valid && p.out_mode != OUT_F32) {
     const int per_img = p.Hp * p.Wp;
-    img = m / per_img;
+    img = (int)(((unsigned long long)(uint32_t)m * p.per_img_magic) >> 40);
     const int rem = m - img * per_img;
-    hp = rem / p.Wp;
+    hp = (int)fast_div((uint32_t)rem, p.wp_magic);
     wp = rem - hp * p.Wp;
     valid = hp < p.H && wp < p.W;
   }
@@ -245,26 +253,43 @@ __device__ __forceinline__ void epilogue_tile(const Params& p, uint32_t taddr0, 
   }
 #pragma unroll 1
   for (int c = c_begin; c < c_end; ++c) {
+    // TMEM load first, then every global load the chunk needs (bias, PReLU slopes, residual:
+    // none depends on the accumulator), then one wait: the latencies overlap
     uint32_t v[32];
-    tmem_ld32(taddr0 + c * 32, v);
+    tmem_ld32<false>(taddr0 + c * 32, v);
+    float4 b4[8], s4[8];
+    uint4 rv[4];
+    const bool has_res = valid && p.residual != nullptr && p.out_mode != OUT_F32;
+    if (valid) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) b4[i] = __ldg(reinterpret_cast<const float4*>(bias + c * 32 + i * 4));
+      if (p.prelu) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) s4[i] = __ldg(reinterpret_cast<const float4*>(p.prelu + n0 + c * 32 + i * 4));
+      }
+      if (has_res) {
+        const uint4* r = reinterpret_cast<const uint4*>(p.residual + (size_t)m * p.cout + n0 + c * 32);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) rv[i] = __ldg(r + i);
+      }
+    }
+    tmem_wait_ld();
     if (valid) {
       float f[32];
 #pragma unroll
-      for (int i = 0; i < 32; i += 4) {
-        const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + c * 32 + i));
-        f[i] = __uint_as_float(v[i]) + b4.x * bias_on;
-        f[i + 1] = __uint_as_float(v[i + 1]) + b4.y * bias_on;
-        f[i + 2] = __uint_as_float(v[i + 2]) + b4.z * bias_on;
-        f[i + 3] = __uint_as_float(v[i + 3]) + b4.w * bias_on;
+      for (int i = 0; i < 8; ++i) {
+        f[4 * i] = __uint_as_float(v[4 * i]) + b4[i].x * bias_on;
+        f[4 * i + 1] = __uint_as_float(v[4 * i + 1]) + b4[i].y * bias_on;
+        f[4 * i + 2] = __uint_as_float(v[4 * i + 2]) + b4[i].z * bias_on;
+        f[4 * i + 3] = __uint_as_float(v[4 * i + 3]) + b4[i].w * bias_on;
       }
       if (p.prelu) {
 #pragma unroll
-        for (int i = 0; i < 32; i += 4) {
-          const float4 s4 = __ldg(reinterpret_cast<const float4*>(p.prelu + n0 + c * 32 + i));
-          f[i] = f[i] > 0.f ? f[i] : f[i] * s4.x;
-          f[i + 1] = f[i + 1] > 0.f ? f[i + 1] : f[i + 1] * s4.y;
-          f[i + 2] = f[i + 2] > 0.f ? f[i + 2] : f[i + 2] * s4.z;
-          f[i + 3] = f[i + 3] > 0.f ? f[i + 3] : f[i + 3] * s4.w;
+        for (int i = 0; i < 8; ++i) {
+          f[4 * i] = f[4 * i] > 0.f ? f[4 * i] : f[4 * i] * s4[i].x;
+          f[4 * i + 1] = f[4 * i + 1] > 0.f ? f[4 * i + 1] : f[4 * i + 1] * s4[i].y;
+          f[4 * i + 2] = f[4 * i + 2] > 0.f ? f[4 * i + 2] : f[4 * i + 2] * s4[i].z;
+          f[4 * i + 3] = f[4 * i + 3] > 0.f ? f[4 * i + 3] : f[4 * i + 3] * s4[i].w;
         }
       }
       if (p.out_mode == OUT_F32) {
@@ -272,12 +297,10 @@ __device__ __forceinline__ void epilogue_tile(const Params& p, uint32_t taddr0, 
 #pragma unroll
         for (int i = 0; i < 8; ++i) o[i] = make_float4(f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]);
       } else {
-        if (p.residual) {
-          const uint4* r = reinterpret_cast<const uint4*>(p.residual + (size_t)m * p.cout + n0 + c * 32);
+        if (has_res) {
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
-            const uint4 rv = __ldg(r + i);
-            const uint32_t w[4] = {rv.x, rv.y, rv.z, rv.w};
+            const uint32_t w[4] = {rv[i].x, rv[i].y, rv[i].z, rv[i].w};
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               f[i * 8 + 2 * j] += __uint_as_float(w[j] << 16);
