@@ -17,7 +17,7 @@ LIB_PATH = os.path.join(_HERE, "libfr_b200.so")
 
 FR_OK = 0
 FR_ERR_INVALID_ARG, FR_ERR_NOT_LOADED, FR_ERR_CUDA, FR_ERR_MODEL = -1, -2, -3, -4
-FR_ERR_ALIGN, FR_ERR_CAPACITY, FR_ERR_UNSUPPORTED = -5, -6, -7
+FR_ERR_ALIGN, FR_ERR_CAPACITY, FR_ERR_UNSUPPORTED, FR_ERR_IO = -5, -6, -7, -8
 FR_MEM_HOST, FR_MEM_DEVICE = 0, 1
 FR_MODEL_DET, FR_MODEL_REC = 0, 1
 DET_SIZE, REC_SIZE, FEAT_DIM, NUM_ANCHORS = 640, 112, 512, 16800
@@ -40,6 +40,7 @@ SYMBOLS = [
     "fr_compare", "fr_compare_batch", "fr_pipeline_batch", "fr_pipeline_submit", "fr_pipeline_wait",
     "fr_gallery_create", "fr_gallery_destroy", "fr_gallery_add", "fr_gallery_fill_synthetic",
     "fr_gallery_get_rows", "fr_gallery_size", "fr_gallery_search", "fr_topk_merge",
+    "fr_gallery_save", "fr_gallery_load", "fr_gallery_remove",
     "fr_det_preprocess", "fr_scrfd_forward", "fr_scrfd_decode_nms", "fr_estimate_alignment",
     "fr_align_faces", "fr_warp_affine", "fr_resize_linear", "fr_iresnet_forward", "fr_iresnet_tap",
     "fr_l2_normalize", "fr_test_conv", "fr_scrfd_tap",
@@ -110,6 +111,9 @@ def _declare(L: C.CDLL) -> None:
     L.fr_gallery_get_rows.argtypes = [vp, i64, i64, vp]
     L.fr_gallery_size.argtypes = [vp]
     L.fr_gallery_size.restype = i64
+    L.fr_gallery_save.argtypes = [vp, C.c_char_p]
+    L.fr_gallery_load.argtypes = [vp, C.c_char_p, vp]
+    L.fr_gallery_remove.argtypes = [vp, i64]
     L.fr_gallery_search.argtypes = [vp, vp, i32, i32, i32, vp, vp]
     L.fr_topk_merge.argtypes = [vp, vp, vp, i32, i32, i32, i32, vp, vp]
     L.fr_det_preprocess.argtypes = [vp, vp, vp, vp, vp, i32, i32, vp, vp]
@@ -492,6 +496,18 @@ class Gallery:
         out = np.zeros((n, FEAT_DIM), np.float32)
         self.ctx._check(lib().fr_gallery_get_rows(self.h, first, n, out.ctypes.data))
         return out
+
+    def save(self, path: str):
+        self.ctx._check(lib().fr_gallery_save(self.h, path.encode()))
+
+    def load(self, path: str) -> int:
+        """Appends the rows of a saved shard; returns the index_base recorded in the file."""
+        base = C.c_int64(0)
+        self.ctx._check(lib().fr_gallery_load(self.h, path.encode(), C.byref(base)))
+        return int(base.value)
+
+    def remove(self, row: int):
+        self.ctx._check(lib().fr_gallery_remove(self.h, row))
 
     def search(self, queries: np.ndarray, k: int = 10):
         q = np.ascontiguousarray(queries, np.float32)

@@ -14,7 +14,9 @@
 // merged by topk_merge_kernel with the (score desc, global index asc) order, so the result
 // does not depend on the number of splits or ranks.
 #include <cmath>
+#include <cstdio>
 #include <cstring>
+#include <vector>
 
 #include "common.h"
 #include "tc_gemm.cuh"
@@ -372,6 +374,94 @@ int fr_gallery_get_rows(fr_gallery* g, int64_t first, int64_t n, float* out_host
   ctx->launches++;
   FR_CUDA_OK(ctx, cudaMemcpyAsync(out_host, g->q_f32.p, elems * 4, cudaMemcpyDeviceToHost, ctx->stream));
   FR_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+  return FR_OK;
+}
+
+// ---- persistence / enrolment.  File = 32-byte header + size x 512 bf16 rows:
+//   char magic[8] = "FRGAL001"; int64 rows; int64 index_base; int32 dim; int32 dtype (1 = bf16)
+// The rows are stored exactly as they sit in HBM, so save -> load round-trips bit for bit and a
+// shard written by rank r of an N-rank job can be loaded by any rank of any job.
+namespace {
+struct GalHeader {
+  char magic[8];
+  int64_t rows, index_base;
+  int32_t dim, dtype;
+};
+static_assert(sizeof(GalHeader) == 32, "gallery file header is 32 bytes");
+constexpr size_t kIoChunkRows = 1 << 16;   // 64 MiB staging chunks
+}  // namespace
+
+int fr_gallery_save(fr_gallery* g, const char* path) {
+  if (!g || !path) return FR_ERR_INVALID_ARG;
+  fr_ctx* ctx = g->ctx;
+  GGuard gg(ctx);
+  FILE* f = fopen(path, "wb");
+  if (!f) return fr_fail(ctx, FR_ERR_IO, std::string("cannot open for writing: ") + path);
+  GalHeader h;
+  memcpy(h.magic, "FRGAL001", 8);
+  h.rows = g->size;
+  h.index_base = g->base;
+  h.dim = DIM;
+  h.dtype = 1;
+  bool ok = fwrite(&h, sizeof(h), 1, f) == 1;
+  std::vector<uint16_t> buf(std::min<size_t>(kIoChunkRows, (size_t)std::max<int64_t>(g->size, 1)) * DIM);
+  FR_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+  for (int64_t r = 0; ok && r < g->size; r += kIoChunkRows) {
+    const size_t n = (size_t)std::min<int64_t>(kIoChunkRows, g->size - r);
+    if (cudaMemcpy(buf.data(), g->rows + (size_t)r * DIM, n * DIM * 2, cudaMemcpyDeviceToHost) != cudaSuccess) ok = false;
+    ok = ok && fwrite(buf.data(), 2, n * DIM, f) == n * DIM;
+  }
+  ok = (fclose(f) == 0) && ok;
+  return ok ? FR_OK : fr_fail(ctx, FR_ERR_IO, std::string("short write: ") + path);
+}
+
+// Appends the rows of a saved shard to `g` (which keeps its own index_base); *file_index_base,
+// if not null, receives the base recorded in the file.
+int fr_gallery_load(fr_gallery* g, const char* path, int64_t* file_index_base) {
+  if (!g || !path) return FR_ERR_INVALID_ARG;
+  fr_ctx* ctx = g->ctx;
+  GGuard gg(ctx);
+  FILE* f = fopen(path, "rb");
+  if (!f) return fr_fail(ctx, FR_ERR_IO, std::string("cannot open: ") + path);
+  GalHeader h;
+  if (fread(&h, sizeof(h), 1, f) != 1 || memcmp(h.magic, "FRGAL001", 8) != 0 || h.dim != DIM || h.dtype != 1 ||
+      h.rows < 0) {
+    fclose(f);
+    return fr_fail(ctx, FR_ERR_IO, std::string("not a gallery file: ") + path);
+  }
+  if (g->size + h.rows > g->cap) {
+    fclose(f);
+    return fr_fail(ctx, FR_ERR_CAPACITY, "gallery full");
+  }
+  std::vector<uint16_t> buf(std::min<size_t>(kIoChunkRows, (size_t)std::max<int64_t>(h.rows, 1)) * DIM);
+  FR_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+  bool ok = true;
+  for (int64_t r = 0; ok && r < h.rows; r += kIoChunkRows) {
+    const size_t n = (size_t)std::min<int64_t>(kIoChunkRows, h.rows - r);
+    ok = fread(buf.data(), 2, n * DIM, f) == n * DIM;
+    if (ok && cudaMemcpy(g->rows + (size_t)(g->size + r) * DIM, buf.data(), n * DIM * 2, cudaMemcpyHostToDevice) !=
+                  cudaSuccess)
+      ok = false;
+  }
+  fclose(f);
+  if (!ok) return fr_fail(ctx, FR_ERR_IO, std::string("short read: ") + path);
+  g->size += h.rows;
+  if (file_index_base) *file_index_base = h.index_base;
+  return FR_OK;
+}
+
+// Removes local row `row` by moving the last row into its place (O(1); the moved row's index
+// changes from size-1 to `row`, which the caller's id table must mirror).
+int fr_gallery_remove(fr_gallery* g, int64_t row) {
+  if (!g || row < 0 || row >= g->size) return FR_ERR_INVALID_ARG;
+  fr_ctx* ctx = g->ctx;
+  GGuard gg(ctx);
+  const int64_t last = g->size - 1;
+  if (row != last)
+    FR_CUDA_OK(ctx, cudaMemcpyAsync(g->rows + (size_t)row * DIM, g->rows + (size_t)last * DIM, DIM * 2,
+                                    cudaMemcpyDeviceToDevice, ctx->stream));
+  FR_CUDA_OK(ctx, cudaMemsetAsync(g->rows + (size_t)last * DIM, 0, DIM * 2, ctx->stream));
+  g->size = last;
   return FR_OK;
 }
 

@@ -41,7 +41,8 @@ typedef enum fr_status {
   FR_ERR_MODEL = -4,         /* weight file unreadable / shape mismatch (loadModel -> false) */
   FR_ERR_ALIGN = -5,         /* alignment failed (face_recognizer.cpp:255-258) */
   FR_ERR_CAPACITY = -6,      /* caller buffer too small */
-  FR_ERR_UNSUPPORTED = -7
+  FR_ERR_UNSUPPORTED = -7,
+  FR_ERR_IO = -8             /* gallery file unreadable / unwritable / malformed */
 } fr_status;
 
 enum { FR_MEM_HOST = 0, FR_MEM_DEVICE = 1 };
@@ -162,6 +163,11 @@ FR_API int fr_gallery_add(fr_gallery* g, const float* rows, int64_t n, int memsp
 FR_API int fr_gallery_fill_synthetic(fr_gallery* g, int64_t n, uint64_t seed);
 FR_API int fr_gallery_get_rows(fr_gallery* g, int64_t first, int64_t n, float* out_host);
 FR_API int64_t fr_gallery_size(const fr_gallery* g);
+/* Persistence / enrolment: save a shard (bf16 rows as stored, bit-exact round trip), append the
+ * rows of a saved shard, remove one row (the last row moves into its place). */
+FR_API int fr_gallery_save(fr_gallery* g, const char* path);
+FR_API int fr_gallery_load(fr_gallery* g, const char* path, int64_t* file_index_base);
+FR_API int fr_gallery_remove(fr_gallery* g, int64_t row);
 FR_API int fr_gallery_search(fr_gallery* g, const float* queries, int nq, int k, int memspace,
                              float* out_scores, int64_t* out_idx);
 /* Merge `parts` per-shard top-k lists [parts][nq][k] (as gathered over NCCL) into [nq][k]. */

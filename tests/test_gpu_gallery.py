@@ -100,3 +100,42 @@ def test_k9_sharded_merge_equals_single(ctx, capi):
     os_, oi = ogal.merge_topk(parts_s, parts_i, 10)
     assert np.array_equal(mi, oi)
     whole.close()
+
+
+def test_gallery_save_load_remove_roundtrip(ctx, capi, tmp_path):
+    """a saved shard reloads bit for bit (same search results), rows can be
+    appended from several files, and remove() keeps the result set consistent."""
+    rng = np.random.default_rng(5)
+    g = rng.normal(size=(3000, 512)).astype(np.float32)
+    g /= np.linalg.norm(g, axis=1, keepdims=True)
+    q = g[rng.integers(0, 3000, 40)] + 0.02 * rng.normal(size=(40, 512)).astype(np.float32)
+    a = capi.Gallery(ctx, 4096, index_base=7000)
+    a.add(g[:2000])
+    p1, p2 = str(tmp_path / "a.frg"), str(tmp_path / "b.frg")
+    a.save(p1)
+    b = capi.Gallery(ctx, 1000, index_base=0)
+    b.add(g[2000:])
+    b.save(p2)
+    c = capi.Gallery(ctx, 4096, index_base=7000)
+    assert c.load(p1) == 7000 and c.load(p2) == 0 and len(c) == 3000
+    assert np.array_equal(c.get_rows(0, 3000), np.concatenate([a.get_rows(0, 2000), b.get_rows(0, 1000)]))
+    a.add(g[2000:])
+    s_a, i_a = a.search(q, 10)
+    s_c, i_c = c.search(q, 10)
+    assert np.array_equal(s_a, s_c) and np.array_equal(i_a, i_c)
+    # remove the best match of query 0: it must disappear, the former last row takes its index
+    top = int(i_c[0, 0]) - 7000
+    c.remove(top)
+    assert len(c) == 2999
+    s2, i2 = c.search(q[:1], 10)
+    ref = np.delete(np.arange(3000), top)
+    g_bf = c.get_rows(0, 2999)
+    assert np.array_equal(g_bf[top], a.get_rows(2999, 1)[0])
+    exp = np.sort((g_bf @ q[0]).astype(np.float32))[::-1][:10]
+    assert np.allclose(s2[0], exp, atol=3e-3)
+    with pytest.raises(capi.FrError):
+        capi.Gallery(ctx, 10).load(p1)            # does not fit
+    bad = str(tmp_path / "bad.frg")
+    open(bad, "wb").write(b"not a gallery")
+    with pytest.raises(capi.FrError):
+        c.load(bad)
