@@ -333,10 +333,17 @@ def run_gpu(args, rank, world, local_rank):
     trunk_s = stage_ms["trunk"] / 1e3
     tc_flop = n_faces * args.steps * (GFLOP_PER_FACE_TOTAL - GFLOP_PER_FACE_STEM) * 1e9
     achieved = tc_flop / trunk_s / 1e12 if trunk_s > 0 else 0.0
-    roofline = {"bound": "tensor", "kernel": "tc::shift_gemm_kernel<64|128|256> (IResNet-50 convs + FC)",
+    traffic, traffic_src = None, None
+    tp = os.path.join(ROOT, "profiles", "r1_tc_traffic.json")
+    if os.path.exists(tp):   # dram__bytes_read+write per launch from the committed ncu capture of this family
+        tj = json.load(open(tp))
+        traffic, traffic_src = tj["traffic_bytes_per_launch"], "profiles/r1_tc_traffic.json (ncu, averaged over the 49 launches)"
+    roofline = {"bound": "tensor", "kernel": "tc::halo_gemm_kernel / tc::shift_gemm_kernel <64|128|256> (IResNet-50 convs + FC)",
                 "achieved": achieved, "peak": peaks["tflops_sustained"], "unit": "TFLOP/s",
                 "frac": achieved / peaks["tflops_sustained"], "peak_source": peaks["source"] + " (sustained bf16)",
-                "traffic": None, "launches_per_step": TC_LAUNCHES_PER_STEP,
+                "traffic": traffic, "traffic_source": traffic_src,
+                "algorithmic_flop_per_launch": tc_flop / (args.steps * TC_LAUNCHES_PER_STEP) if args.steps else None,
+                "launches_per_step": TC_LAUNCHES_PER_STEP,
                 "avg_launch_ms": stage_ms["trunk"] / (args.steps * TC_LAUNCHES_PER_STEP),
                 "share_of_step": stage_ms["trunk"] / ms if ms > 0 else None}
     k1_bytes = n_img * args.steps * (FRAME * FRAME * 3 + FRAME * FRAME * 3 * 2)
@@ -367,7 +374,7 @@ def run_gpu(args, rank, world, local_rank):
                 "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
                 "config": {"workload": "det+align+embed: 64 frames 640x640 per GPU per step, 8 faces/frame "
                                        "(top post-NMS detections, padded with seeded synthetic landmark sets), "
-                                       "SCRFD det_500m fp32 + IResNet-50 bf16/fp32-accum, random-init weights seed 1",
+                                       "SCRFD det_500m on tcgen05 tf32x3 (fp32-grade) + IResNet-50 bf16/fp32-accum, random-init weights seed 1",
                            "frames_per_gpu_per_step": n_img, "faces_per_frame": K,
                            "l2": "inputs rotate over 4 batches (315 MB > 126 MB L2); activations > 4 GB",
                            "parallelism": f"dp{world} (independent frame batches, no data-path collective)"},
