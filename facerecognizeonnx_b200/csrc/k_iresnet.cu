@@ -123,10 +123,11 @@ static int env_flag(const char* name, int dflt) {
 // Configure halo mode for a 3x3 stride-1 conv whose A operand is `base` ([rows, cin], pitch cin).
 static bool tc_setup_halo(ConvLaunch& L, const void* base, uint64_t rows, int cin, int Wp) {
   if (!env_flag("FR_TC_HALO", 1)) return true;   // default on (FR_TC_HALO=0 selects the per-tap loader)
-  // M tiles per CTA iteration: 1 measured best overall on B200 (2 halves the weight traffic but
-  // loses the TMEM double buffer at BN=256 and doubles the wave-quantisation tail); 3 = 2 where
-  // the accumulators still double-buffer (BN <= 128)
-  int mt = env_flag("FR_TC_MT", 1);
+  // M tiles per CTA iteration (they share one A block and every streamed weight tile).  Measured
+  // per layer on B200: 2 wins only for the 128-channel 28x28 layers (114 -> 99 us); it loses at
+  // 64 channels (resident weights, nothing to share) and at BN = 256 (no TMEM double buffer).
+  int mt = env_flag("FR_TC_MT", 0);
+  if (mt == 0) mt = (L.bn == 128 && Wp <= 29) ? 2 : 1;
   if (mt == 3) mt = L.bn <= 128 ? 2 : 1;
   L.mt = mt;
   L.resb = (cin == 64) && env_flag("FR_TC_RESB", 1);

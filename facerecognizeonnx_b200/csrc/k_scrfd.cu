@@ -49,6 +49,7 @@ using tc::mbar_arrive;
 using tc::mbar_expect_tx;
 using tc::mbar_init;
 using tc::mbar_wait;
+using tc::mbar_wait_spin;
 using tc::smem_u32;
 using tc::tc_commit;
 using tc::tc_fence_after;
@@ -297,7 +298,7 @@ __device__ __forceinline__ void converter_loop(const SepParams& p, const Rings& 
       const bool kv = k0 < p.cin && pix_ok;
       if (MODE == LD_DW && p.n_in > 1) load_dw(k0);
       for (int tap = 0; tap < p.taps; ++tap) {
-        mbar_wait(&r.empty_ab[sa], ph_ab ^ 1u, p.err_flag);
+        mbar_wait_spin(&r.empty_ab[sa], ph_ab ^ 1u, p.err_flag);
         if (t == 0) dbg_stamp(p, 0, dbg_kb, 0);
         const uint32_t hi = ab_base + (uint32_t)(sa * r.ab_bytes);
         const uint32_t lo = hi + A_BYTES;
@@ -487,7 +488,7 @@ sep_gemm_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant_
         uint32_t ks_total = 0;
         int tap = 0, crem = p.cin;   // channels left from this K block's box on
         for (int kb = 0; kb < nkb; ++kb) {
-          mbar_wait(&r.full_ab[s], ph, p.err_flag);
+          mbar_wait_spin(&r.full_ab[s], ph, p.err_flag);
           if (lane == 0) dbg_stamp(p, 1, dbg_kb, 0);
           tc_fence_after();
           const uint32_t ahi = a_lo0 + (uint32_t)s * stage_step;
