@@ -278,8 +278,10 @@ std::vector<bf16> to_bf16(const std::vector<float>& v) {
 }
 
 // ------------------------------------------------------------------- stem kernel
-// One thread = 2 horizontally adjacent output pixels x 64 channels.  Input either u8 BGR HWC
-// crops (FaceRecognizer::preprocess fused: BGR->RGB, (v-127.5)/128) or fp32 CHW RGB.
+// One thread = 4 horizontally adjacent output pixels x 64 channels (four passes of 16).  Input
+// either u8 BGR HWC crops (FaceRecognizer::preprocess fused: BGR->RGB, (v-127.5)/128) or fp32
+// CHW RGB.  ncu on the 2-pixel version: bound by the shared-memory weight reads (short-scoreboard
+// stalls, one LDS.128 per 8 FMAs); 4 pixels per thread give 16 FMAs per weight float4.
 template <bool U8>
 __global__ void __launch_bounds__(128)
 stem_kernel(const void* __restrict__ in_, int n, const float* __restrict__ w,
@@ -291,19 +293,20 @@ stem_kernel(const void* __restrict__ in_, int n, const float* __restrict__ w,
   for (int i = threadIdx.x; i < 27 * 64; i += blockDim.x) sw[i] = w[i];
   if (threadIdx.x < 64) { sb[threadIdx.x] = b[threadIdx.x]; ss[threadIdx.x] = slope[threadIdx.x]; }
   __syncthreads();
-  const int pairs_per_img = REC * (REC / 2);
+  constexpr int PX = 4;
+  const int quads_per_img = REC * (REC / PX);
   const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (gid >= (long long)n * pairs_per_img) return;
-  const int img = (int)(gid / pairs_per_img);
-  const int rem = (int)(gid % pairs_per_img);
-  const int y = rem / (REC / 2);
-  const int x = (rem % (REC / 2)) * 2;
-  // 3 rows x 4 cols x 3 channels input window (RGB order)
-  float win[3][4][3];
+  if (gid >= (long long)n * quads_per_img) return;
+  const int img = (int)(gid / quads_per_img);
+  const int rem = (int)(gid % quads_per_img);
+  const int y = rem / (REC / PX);
+  const int x = (rem % (REC / PX)) * PX;
+  // 3 rows x 6 cols x 3 channels input window (RGB order)
+  float win[3][PX + 2][3];
 #pragma unroll
   for (int r = 0; r < 3; ++r)
 #pragma unroll
-    for (int s = 0; s < 4; ++s) {
+    for (int s = 0; s < PX + 2; ++s) {
       const int yy = y + r - 1, xx = x + s - 1;
       const bool ok = yy >= 0 && yy < REC && xx >= 0 && xx < REC;
 #pragma unroll
@@ -324,59 +327,55 @@ stem_kernel(const void* __restrict__ in_, int n, const float* __restrict__ w,
     }
   const int Wp = REC + 1, Hp = REC + 1, We = REC / 2 + 1, He = REC / 2 + 1;
   bf16* o0 = x0 + ((size_t)(img * Hp + y) * Wp + x) * 64;
-  bf16* o1 = o0 + 64;
   bf16* oe = (!(y & 1)) ? x0e + ((size_t)(img * He + (y >> 1)) * We + (x >> 1)) * 64 : nullptr;
 #pragma unroll 1
   for (int cg = 0; cg < 64; cg += 16) {
-    float a0[16], a1[16];
+    float a[PX][16];
 #pragma unroll
-    for (int i = 0; i < 16; ++i) { a0[i] = sb[cg + i]; a1[i] = a0[i]; }
+    for (int j = 0; j < PX; ++j)
+#pragma unroll
+      for (int i = 0; i < 16; ++i) a[j][i] = sb[cg + i];
 #pragma unroll
     for (int r = 0; r < 3; ++r)
 #pragma unroll
       for (int s = 0; s < 3; ++s)
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
-          const float v0 = win[r][s][c], v1 = win[r][s + 1][c];
           const float4* wp = reinterpret_cast<const float4*>(&sw[((r * 3 + s) * 3 + c) * 64 + cg]);
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             const float4 w4 = wp[i];
-            a0[4 * i] = fmaf(v0, w4.x, a0[4 * i]);
-            a0[4 * i + 1] = fmaf(v0, w4.y, a0[4 * i + 1]);
-            a0[4 * i + 2] = fmaf(v0, w4.z, a0[4 * i + 2]);
-            a0[4 * i + 3] = fmaf(v0, w4.w, a0[4 * i + 3]);
-            a1[4 * i] = fmaf(v1, w4.x, a1[4 * i]);
-            a1[4 * i + 1] = fmaf(v1, w4.y, a1[4 * i + 1]);
-            a1[4 * i + 2] = fmaf(v1, w4.z, a1[4 * i + 2]);
-            a1[4 * i + 3] = fmaf(v1, w4.w, a1[4 * i + 3]);
+#pragma unroll
+            for (int j = 0; j < PX; ++j) {
+              const float v = win[r][s + j][c];
+              a[j][4 * i] = fmaf(v, w4.x, a[j][4 * i]);
+              a[j][4 * i + 1] = fmaf(v, w4.y, a[j][4 * i + 1]);
+              a[j][4 * i + 2] = fmaf(v, w4.z, a[j][4 * i + 2]);
+              a[j][4 * i + 3] = fmaf(v, w4.w, a[j][4 * i + 3]);
+            }
           }
         }
-    uint4 p0[2], p1[2];
 #pragma unroll
-    for (int i = 0; i < 16; ++i) {
-      const float sl = ss[cg + i];
-      a0[i] = a0[i] > 0.f ? a0[i] : a0[i] * sl;
-      a1[i] = a1[i] > 0.f ? a1[i] : a1[i] * sl;
-    }
+    for (int j = 0; j < PX; ++j) {
 #pragma unroll
-    for (int i = 0; i < 2; ++i) {
-      p0[i].x = tc::pack_bf16(a0[8 * i], a0[8 * i + 1]);
-      p0[i].y = tc::pack_bf16(a0[8 * i + 2], a0[8 * i + 3]);
-      p0[i].z = tc::pack_bf16(a0[8 * i + 4], a0[8 * i + 5]);
-      p0[i].w = tc::pack_bf16(a0[8 * i + 6], a0[8 * i + 7]);
-      p1[i].x = tc::pack_bf16(a1[8 * i], a1[8 * i + 1]);
-      p1[i].y = tc::pack_bf16(a1[8 * i + 2], a1[8 * i + 3]);
-      p1[i].z = tc::pack_bf16(a1[8 * i + 4], a1[8 * i + 5]);
-      p1[i].w = tc::pack_bf16(a1[8 * i + 6], a1[8 * i + 7]);
-    }
-    reinterpret_cast<uint4*>(o0 + cg)[0] = p0[0];
-    reinterpret_cast<uint4*>(o0 + cg)[1] = p0[1];
-    reinterpret_cast<uint4*>(o1 + cg)[0] = p1[0];
-    reinterpret_cast<uint4*>(o1 + cg)[1] = p1[1];
-    if (oe) {
-      reinterpret_cast<uint4*>(oe + cg)[0] = p0[0];
-      reinterpret_cast<uint4*>(oe + cg)[1] = p0[1];
+      for (int i = 0; i < 16; ++i) {
+        const float sl = ss[cg + i];
+        a[j][i] = a[j][i] > 0.f ? a[j][i] : a[j][i] * sl;
+      }
+      uint4 pk[2];
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        pk[i].x = tc::pack_bf16(a[j][8 * i], a[j][8 * i + 1]);
+        pk[i].y = tc::pack_bf16(a[j][8 * i + 2], a[j][8 * i + 3]);
+        pk[i].z = tc::pack_bf16(a[j][8 * i + 4], a[j][8 * i + 5]);
+        pk[i].w = tc::pack_bf16(a[j][8 * i + 6], a[j][8 * i + 7]);
+      }
+      reinterpret_cast<uint4*>(o0 + j * 64 + cg)[0] = pk[0];
+      reinterpret_cast<uint4*>(o0 + j * 64 + cg)[1] = pk[1];
+      if (oe && !(j & 1)) {
+        reinterpret_cast<uint4*>(oe + (j >> 1) * 64 + cg)[0] = pk[0];
+        reinterpret_cast<uint4*>(oe + (j >> 1) * 64 + cg)[1] = pk[1];
+      }
     }
   }
 }
@@ -768,7 +767,7 @@ int rec_forward_crops(fr_ctx* ctx, const uint8_t* d_crops, int n, float* d_out_r
   if (!m) return fr_fail(ctx, FR_ERR_NOT_LOADED, "Model not loaded!");
   if (n <= 0) return FR_OK;
   FR_CHECK(rec_build_plan(ctx, rec_plan_cap(n)));
-  const long long threads = (long long)n * REC * (REC / 2);
+  const long long threads = (long long)n * REC * (REC / 4);
   ctx->stage_begin(FR_STAGE_STEM);
   stem_kernel<true><<<(unsigned)((threads + 127) / 128), 128, 0, ctx->stream>>>(
       d_crops, n, m->stem_w, m->stem_b, m->stem_prelu, m->x0.p, m->x0e.p);
@@ -792,7 +791,7 @@ int rec_forward_chw(fr_ctx* ctx, const float* d_chw, int n, float* d_out_raw) {
   if (!m) return fr_fail(ctx, FR_ERR_NOT_LOADED, "Model not loaded!");
   if (n <= 0) return FR_OK;
   FR_CHECK(rec_build_plan(ctx, rec_plan_cap(n)));
-  const long long threads = (long long)n * REC * (REC / 2);
+  const long long threads = (long long)n * REC * (REC / 4);
   stem_kernel<false><<<(unsigned)((threads + 127) / 128), 128, 0, ctx->stream>>>(
       d_chw, n, m->stem_w, m->stem_b, m->stem_prelu, m->x0.p, m->x0e.p);
   ctx->launches++;
