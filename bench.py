@@ -36,7 +36,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
-FRAMES_PER_STEP = 64
+FRAMES_PER_STEP = int(os.environ.get("FR_BENCH_FRAMES", "64"))
 FACES_PER_FRAME = 8
 FRAME = 640
 SEED = 1
@@ -349,7 +349,11 @@ def run_gpu(args, rank, world, local_rank):
     k1_bytes = n_img * args.steps * (FRAME * FRAME * 3 + FRAME * FRAME * 3 * 2)
     k5_bytes = n_faces * args.steps * (37632 + 37632)
     stages = {k: v / args.steps for k, v in stage_ms.items()}
+    det_ms = stages["preprocess"] + stages["scrfd"] + stages["decode_nms"]
+    emb_ms = stages["align"] + stages["stem"] + stages["trunk"] + stages["l2norm"]
     extra = {"stage_ms_per_step": stages,
+             "det_only_frames_per_s_per_gpu": n_img / (det_ms / 1e3) if det_ms > 0 else None,       # configs[1]
+             "embed_only_faces_per_s_per_gpu": n_faces / (emb_ms / 1e3) if emb_ms > 0 else None,    # configs[2]
              "k1_preprocess_gbs": k1_bytes / (stage_ms["preprocess"] / 1e3) / 1e9 if stage_ms["preprocess"] > 0 else None,
              "k5_align_gbs_lower_bound": k5_bytes / (stage_ms["align"] / 1e3) / 1e9 if stage_ms["align"] > 0 else None,
              "hbm_peak_gbs": peaks["hbm_gbs"], "n_det_per_frame": n_det_mean, "valid_frac": valid_frac}
