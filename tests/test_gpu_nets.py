@@ -25,7 +25,9 @@ def _bf16(x):
 
 
 @pytest.mark.parametrize("n,cin,cout,h,w", [(2, 64, 64, 8, 8), (1, 64, 64, 15, 13), (2, 128, 128, 14, 14),
-                                            (1, 64, 128, 9, 9), (1, 256, 256, 7, 7), (1, 128, 512, 7, 7)])
+                                            (1, 64, 128, 9, 9), (1, 256, 256, 7, 7), (1, 128, 512, 7, 7),
+                                            # 2-D tile mode (7x16 patches at 112^2, 8x14 at 56^2)
+                                            (2, 64, 64, 56, 56), (1, 64, 64, 112, 112), (1, 64, 128, 56, 56)])
 def test_tc_conv3x3_plain(ctx, n, cin, cout, h, w):
     rng = np.random.default_rng(cin + cout + h)
     x = rng.normal(size=(n, cin, h, w)).astype(np.float32)
