@@ -294,7 +294,7 @@ __device__ __forceinline__ void epilogue_tile(const Params& p, uint32_t taddr0, 
       if (has_res) {
         const uint4* r = reinterpret_cast<const uint4*>(p.residual + (size_t)m * p.cout + n0 + c * 32);
 #pragma unroll
-        for (int i = 0; i < 4; ++i) rv[i] = __ldg(r + i);
+        for (int i = 0; i < 4; ++i) rv[i] = __ldcs(r + i);   // streaming: keep L1 for the bias / PReLU rows
       }
     }
     tmem_wait_ld();
@@ -342,11 +342,11 @@ __device__ __forceinline__ void epilogue_tile(const Params& p, uint32_t taddr0, 
         }
         uint4* o = reinterpret_cast<uint4*>(p.out + out_off + c * 32);
 #pragma unroll
-        for (int i = 0; i < 4; ++i) o[i] = pk[i];
+        for (int i = 0; i < 4; ++i) __stcs(o + i, pk[i]);
         if (write_even) {
           uint4* oe = reinterpret_cast<uint4*>(p.out_even + even_off + c * 32);
 #pragma unroll
-          for (int i = 0; i < 4; ++i) oe[i] = pk[i];
+          for (int i = 0; i < 4; ++i) __stcs(oe + i, pk[i]);
         }
       }
     }
