@@ -228,6 +228,59 @@ __device__ __forceinline__ void ld_sum16(uint32_t taddr, uint32_t small_off, int
   for (int i = 0; i < 16; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) + __uint_as_float(s[i]));
 }
 
+// four partial accumulators at column offsets 0, nt, 2nt, 3nt: (big0 + big1) + (small0 + small1)
+__device__ __forceinline__ void ld_sum16x4(uint32_t taddr, uint32_t nt, uint32_t (&v)[16]) {
+  uint32_t b1[16], s0[16], s1[16];
+  tmem_ld16_nowait(taddr, v);
+  tmem_ld16_nowait(taddr + nt, b1);
+  tmem_ld16_nowait(taddr + 2 * nt, s0);
+  tmem_ld16_nowait(taddr + 3 * nt, s1);
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i)
+    v[i] = __float_as_uint((__uint_as_float(v[i]) + __uint_as_float(b1[i])) +
+                           (__uint_as_float(s0[i]) + __uint_as_float(s1[i])));
+}
+
+// tcgen05.mma.kind::tf32 with a compile-time accumulate flag (folds to UPT / !UPT: no predicate
+// set-up in the single-lane issue stream)
+template <bool ACC>
+__device__ __forceinline__ void mma_tf32_c(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc) {
+  if (ACC)
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.eq.u32 p, 1, 1;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc)
+        : "memory");
+  else
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.u32 p, 1, 1;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc)
+        : "memory");
+}
+
+// One tap (KS k-steps of K = 8) of the halo 3x3 kernel: 3 MMAs per k-step into small0 / small1 /
+// big[k & 1] (column offsets 2nt, 3nt, 0 / nt), fully unrolled, descriptor low words stepped by
+// immediates.  FIRST: the tile's first tap overwrites the accumulators.
+template <int KS, bool FIRST>
+__device__ __forceinline__ void c3_issue_tap(uint32_t d_base, uint32_t nt, uint32_t desc_hi, uint32_t ahi, uint32_t alo,
+                                             uint32_t bhi, uint32_t blo, uint32_t idesc) {
+  auto desc = [&](uint32_t lo) { return ((uint64_t)desc_hi << 32) | (uint64_t)lo; };
+#pragma unroll
+  for (int k = 0; k < KS; ++k) {
+    const uint32_t o = (uint32_t)(k * 2);
+    if (FIRST && k == 0) {
+      mma_tf32_c<false>(d_base + 2 * nt, desc(alo + o), desc(bhi + o), idesc);
+      mma_tf32_c<false>(d_base + 3 * nt, desc(ahi + o), desc(blo + o), idesc);
+      mma_tf32_c<false>(d_base, desc(ahi + o), desc(bhi + o), idesc);
+    } else {
+      mma_tf32_c<true>(d_base + 2 * nt, desc(alo + o), desc(bhi + o), idesc);
+      mma_tf32_c<true>(d_base + 3 * nt, desc(ahi + o), desc(blo + o), idesc);
+      if (FIRST && k == 1) mma_tf32_c<false>(d_base + nt, desc(ahi + o), desc(bhi + o), idesc);
+      else mma_tf32_c<true>(d_base + (uint32_t)(k & 1) * nt, desc(ahi + o), desc(bhi + o), idesc);
+    }
+  }
+}
+
 struct Rings {
   uint8_t* in;          // s_in input boxes
   uint8_t* ab;          // s_ab x (A_hi, A_lo, B_hi, B_lo)
@@ -629,6 +682,317 @@ sep_gemm_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant_
 }
 
 // ---------------------------------------------------------------------------------------
+// Dense 3x3 stride-1 convolutions (fpn / pafpn 16 -> 16, the fused 64 -> 30 head conv) in "halo
+// mode": the tile is a th x tw patch whose tile rows use the pitch tw2 = tw + 2 of its own halo
+// box, so the (th+2) x tw2 input box is split into tf32 hi/lo ONCE, as one operand block of
+// box-pixel rows, and the nine taps are row-shifted shared-memory descriptors
+// (start + (dy*tw2 + dx) rows) on it -- instead of nine im2col copies with nine hand-offs.
+// Tile row ty*tw2 + tx is output pixel (ty, tx) if ty < th and tx < tw, a dead row otherwise
+// (7 x 16 of 128 rows live at 80^2, 5 x 20 at 40^2 / 20^2).  Weights stream through their own
+// ring (or stay resident when all 9 * n_in blocks fit); roles and accumulators as in
+// sep_gemm_kernel.
+struct C3Params {
+  float* out;
+  const float* bias;
+  float* score;
+  float* bbox;
+  float* kps;
+  int cin, cout, h, w;        // square maps: h == w
+  int n_img, epi;
+  int kc, n_in, nt, npad_total;
+  int th, tw, tw2, tiles_x, tiles_y;
+  uint32_t tiles_per_img_magic, tiles_x_magic, tw2_magic, chunk_magic;
+  int num_tiles;
+  int box_px;                 // (th + 2) * tw2
+  int in_bytes, a_rows;       // bytes per input stage (1024-rounded), rows per A operand block
+  int s_in, s_a, s_b, b_resident;
+  int tmem_cols, acc_stages;
+  int* err_flag;
+};
+
+constexpr int C3_MAX_B = 20;
+
+__global__ void __launch_bounds__(THREADS, 1)
+conv3_halo_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant__ CUtensorMap tmW,
+                  const __grid_constant__ C3Params p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  const int a_blk = p.a_rows * 128;            // one hi (or lo) operand block
+  const int b_bytes = p.nt * 128;
+  uint8_t* s_inr = smem;
+  uint8_t* s_a = s_inr + p.s_in * p.in_bytes;
+  uint8_t* s_b = s_a + p.s_a * 2 * a_blk;
+  uint64_t* full_in = reinterpret_cast<uint64_t*>(s_b + p.s_b * 2 * b_bytes);
+  uint64_t* empty_in = full_in + MAX_STAGES;
+  uint64_t* full_a = empty_in + MAX_STAGES;
+  uint64_t* empty_a = full_a + MAX_STAGES;
+  uint64_t* full_b = empty_a + MAX_STAGES;
+  uint64_t* empty_b = full_b + C3_MAX_B;
+  uint64_t* tfull = empty_b + C3_MAX_B;
+  uint64_t* tempty = tfull + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  float* s_bias = reinterpret_cast<float*>(tmem_slot + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  for (int i = threadIdx.x; i < p.npad_total; i += THREADS) s_bias[i] = p.bias[i];
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < MAX_STAGES; ++s) {
+      mbar_init(&full_in[s], 1);
+      mbar_init(&empty_in[s], CV_WARPS);
+      mbar_init(&full_a[s], CV_WARPS);
+      mbar_init(&empty_a[s], 1);
+    }
+    for (int s = 0; s < C3_MAX_B; ++s) {
+      mbar_init(&full_b[s], 1);
+      mbar_init(&empty_b[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tfull[a], 1);
+      mbar_init(&tempty[a], 4);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    tc::prefetch_tmap(&tmIn);
+    tc::prefetch_tmap(&tmW);
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"((uint32_t)p.tmem_cols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int nkb = p.n_in * 9;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------- input-box TMA
+    if (lane == 0) {
+      const uint32_t box_bytes = (uint32_t)(p.box_px * p.kc * 4);
+      int s = 0;
+      uint32_t ph = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        const int img = fastdiv(tile, p.tiles_per_img_magic);
+        const int rem = tile - img * p.tiles_x * p.tiles_y;
+        const int tyi = fastdiv(rem, p.tiles_x_magic);
+        const int y0 = tyi * p.th, x0 = (rem - tyi * p.tiles_x) * p.tw;
+        for (int i = 0; i < p.n_in; ++i) {
+          mbar_wait(&empty_in[s], ph ^ 1u, p.err_flag);
+          mbar_expect_tx(&full_in[s], box_bytes);
+          tma_load_3d(s_inr + s * p.in_bytes, &tmIn, &full_in[s], i * p.kc, x0 - 1, img * p.h + y0 - 1);
+          if (++s == p.s_in) { s = 0; ph ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 6) {
+    // ------------------------------------------------------------- weight TMA
+    if (lane == 0) {
+      if (p.b_resident) {
+        for (int kb = 0; kb < nkb; ++kb) {
+          mbar_expect_tx(&full_b[kb], 2u * (uint32_t)b_bytes);
+          uint8_t* sb = s_b + kb * 2 * b_bytes;
+          tma_load_2d(sb, &tmW, &full_b[kb], kb * 32, 0);
+          tma_load_2d(sb + b_bytes, &tmW, &full_b[kb], kb * 32, p.npad_total);
+        }
+      } else {
+        int s = 0;
+        uint32_t ph = 0;
+        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x)
+          for (int kb = 0; kb < nkb; ++kb) {
+            mbar_wait(&empty_b[s], ph ^ 1u, p.err_flag);
+            mbar_expect_tx(&full_b[s], 2u * (uint32_t)b_bytes);
+            uint8_t* sb = s_b + s * 2 * b_bytes;
+            tma_load_2d(sb, &tmW, &full_b[s], kb * 32, 0);
+            tma_load_2d(sb + b_bytes, &tmW, &full_b[s], kb * 32, p.npad_total);
+            if (++s == p.s_b) { s = 0; ph ^= 1u; }
+          }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------- MMA issuer (warp-uniform)
+    const uint32_t idesc = make_idesc_tf32(TM, p.nt);
+    const uint64_t d0 = make_smem_desc(s_a);
+    const uint32_t desc_hi = (uint32_t)(d0 >> 32);
+    const uint32_t a_lo0 = (uint32_t)d0;
+    const uint32_t b_lo0 = (uint32_t)make_smem_desc(s_b);
+    const uint32_t a_step = (uint32_t)(2 * a_blk) >> 4, a_lo_off = (uint32_t)a_blk >> 4;
+    const uint32_t b_step = (uint32_t)(2 * b_bytes) >> 4, b_lo_off = (uint32_t)b_bytes >> 4;
+    const uint32_t nt = (uint32_t)p.nt;
+    const int ksteps = p.kc >> 3;
+    uint32_t tt = 0;
+    int sa = 0, sb = 0;
+    uint32_t pa = 0, pb = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++tt) {
+      const uint32_t acc = p.acc_stages == 2 ? (tt & 1u) : 0u;
+      const uint32_t acc_phase = p.acc_stages == 2 ? ((tt >> 1) & 1u) : (tt & 1u);
+      mbar_wait(&tempty[acc], acc_phase ^ 1u, p.err_flag);
+      tc_fence_after();
+      // four independent accumulators (big0, big1, small0, small1): consecutive MMAs never target the
+      // same one, so the accumulate-dependency latency of these short (N <= 32) MMAs is hidden
+      const uint32_t d_big = tmem_base + acc * 4u * nt;
+      int kb = 0;
+      for (int i = 0; i < p.n_in; ++i) {
+        mbar_wait_spin(&full_a[sa], pa, p.err_flag);
+        tc_fence_after();
+        const uint32_t ahi0 = a_lo0 + (uint32_t)sa * a_step;
+        // one elected lane runs all nine taps of the box (waits included): tap offsets are
+        // compile-time constants and there is no per-tap warp re-convergence
+        if (tc::elect_one()) {
+          int sb_l = sb;
+          uint32_t pb_l = pb;
+#pragma unroll
+          for (int tap = 0; tap < 9; ++tap) {
+            const int bslot = p.b_resident ? kb + tap : sb_l;
+            if (!p.b_resident || tt == 0) {
+              mbar_wait_spin(&full_b[bslot], p.b_resident ? 0u : pb_l, p.err_flag);
+              tc_fence_after();
+            }
+            const uint32_t ahi = ahi0 + (uint32_t)((tap / 3) * p.tw2 + (tap % 3)) * 8u;   // 128-byte rows = 8 units
+            const uint32_t bhi = b_lo0 + (uint32_t)bslot * b_step;
+            const uint32_t alo = ahi + a_lo_off, blo = bhi + b_lo_off;
+            if (ksteps == 4) {
+              if (tap == 0 && i == 0) c3_issue_tap<4, true>(d_big, nt, desc_hi, ahi, alo, bhi, blo, idesc);
+              else c3_issue_tap<4, false>(d_big, nt, desc_hi, ahi, alo, bhi, blo, idesc);
+            } else {
+              if (tap == 0 && i == 0) c3_issue_tap<2, true>(d_big, nt, desc_hi, ahi, alo, bhi, blo, idesc);
+              else c3_issue_tap<2, false>(d_big, nt, desc_hi, ahi, alo, bhi, blo, idesc);
+            }
+            if (!p.b_resident) {
+              tc_commit(&empty_b[sb_l]);
+              if (++sb_l == p.s_b) { sb_l = 0; pb_l ^= 1u; }
+            }
+          }
+        }
+        __syncwarp();
+        kb += 9;
+        if (!p.b_resident) {   // keep the ring position uniform across the warp
+          sb += 9;
+          while (sb >= p.s_b) { sb -= p.s_b; pb ^= 1u; }
+        }
+        if (tc::elect_one()) tc_commit(&empty_a[sa]);
+        __syncwarp();
+        if (++sa == p.s_a) { sa = 0; pa ^= 1u; }
+      }
+      if (tc::elect_one()) tc_commit(&tfull[acc]);
+      __syncwarp();
+    }
+  } else if (warp < 6) {
+    // ------------------------------------------------------------- epilogue
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const int ty = fastdiv(row, p.tw2_magic), tx = row - ty * p.tw2;
+    uint32_t tt = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++tt) {
+      const int img = fastdiv(tile, p.tiles_per_img_magic);
+      const int rem = tile - img * p.tiles_x * p.tiles_y;
+      const int tyi = fastdiv(rem, p.tiles_x_magic);
+      const int y = tyi * p.th + ty, x = (rem - tyi * p.tiles_x) * p.tw + tx;
+      const bool valid = ty < p.th && tx < p.tw && y < p.h;
+      const uint32_t acc = p.acc_stages == 2 ? (tt & 1u) : 0u;
+      const uint32_t acc_phase = p.acc_stages == 2 ? ((tt >> 1) & 1u) : (tt & 1u);
+      mbar_wait(&tfull[acc], acc_phase, p.err_flag);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + acc * 4u * (uint32_t)p.nt + ((uint32_t)(q * 32) << 16);
+      const size_t pix = ((size_t)img * p.h + y) * p.w + x;
+      if (p.epi == EPI_HEAD) {
+        uint32_t v0[16], v1[16];
+        ld_sum16x4(taddr, (uint32_t)p.nt, v0);
+        ld_sum16x4(taddr + 16, (uint32_t)p.nt, v1);
+        if (valid) {
+          float f[32];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            f[i] = __uint_as_float(v0[i]) + s_bias[i];
+            f[16 + i] = __uint_as_float(v1[i]) + s_bias[16 + i];
+          }
+          float2 sc;
+          sc.x = 1.0f / (1.0f + expf(-f[0]));
+          sc.y = 1.0f / (1.0f + expf(-f[1]));
+          *reinterpret_cast<float2*>(p.score + pix * 2) = sc;
+          float4* bb = reinterpret_cast<float4*>(p.bbox + pix * 8);
+          bb[0] = make_float4(f[2], f[3], f[4], f[5]);
+          bb[1] = make_float4(f[6], f[7], f[8], f[9]);
+          float4* kp = reinterpret_cast<float4*>(p.kps + pix * 20);
+#pragma unroll
+          for (int i = 0; i < 5; ++i) kp[i] = make_float4(f[10 + 4 * i], f[11 + 4 * i], f[12 + 4 * i], f[13 + 4 * i]);
+        }
+      } else {
+#pragma unroll 1
+        for (int c0 = 0; c0 < p.nt; c0 += 16) {
+          uint32_t v[16];
+          ld_sum16x4(taddr + c0, (uint32_t)p.nt, v);
+          if (valid) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const int c = c0 + 4 * j;
+              if (c < p.cout) {
+                const float4 b4 = *reinterpret_cast<const float4*>(s_bias + c);
+                *reinterpret_cast<float4*>(p.out + pix * p.cout + c) =
+                    make_float4(__uint_as_float(v[4 * j]) + b4.x, __uint_as_float(v[4 * j + 1]) + b4.y,
+                                __uint_as_float(v[4 * j + 2]) + b4.z, __uint_as_float(v[4 * j + 3]) + b4.w);
+              }
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[acc]);
+    }
+  } else if (warp >= FIRST_CV_WARP) {
+    // ------------------------------------------------------------- box -> hi/lo operand block
+    const int t = threadIdx.x - FIRST_CV_WARP * 32;
+    const int ch = p.kc >> 2;                 // 16-byte chunks per box pixel
+    const int pp = p.kc * 4;                  // box pixel pitch (bytes)
+    const int items = p.box_px * ch;
+    const uint32_t in_base = smem_u32(s_inr), a_base = smem_u32(s_a);
+    int si = 0, sa = 0;
+    uint32_t ph_in = 0, ph_a = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      const int img = fastdiv(tile, p.tiles_per_img_magic);
+      const int rem = tile - img * p.tiles_x * p.tiles_y;
+      const int y0 = fastdiv(rem, p.tiles_x_magic) * p.th;
+      (void)img;
+      for (int i = 0; i < p.n_in; ++i) {
+        mbar_wait_spin(&full_in[si], ph_in, p.err_flag);
+        mbar_wait_spin(&empty_a[sa], ph_a ^ 1u, p.err_flag);
+        const uint32_t box = in_base + (uint32_t)(si * p.in_bytes);
+        const uint32_t hi = a_base + (uint32_t)(sa * 2 * a_blk);
+        const uint32_t lo = hi + (uint32_t)a_blk;
+        for (int it = t; it < items; it += CV_WARPS * 32) {
+          const int px = fastdiv(it, p.chunk_magic);     // box pixel = operand row
+          const int chunk = it - px * ch;
+          const int r = fastdiv(px, p.tw2_magic);         // box row; image row = y0 - 1 + r
+          const int iy = y0 - 1 + r;
+          float4 v = zero4();
+          // rows outside the image hold a neighbour image's data (merged-row tensor map): zero them
+          if (iy >= 0 && iy < p.h) v = lds4(box + (uint32_t)(px * pp + chunk * 16));
+          split_store(hi, lo, sw128(px, chunk), v);
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) {
+          mbar_arrive(&full_a[sa]);
+          mbar_arrive(&empty_in[si]);
+        }
+        if (++sa == p.s_a) { sa = 0; ph_a ^= 1u; }
+        if (++si == p.s_in) { si = 0; ph_in ^= 1u; }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)p.tmem_cols)
+                 : "memory");
+  }
+}
+
+// ---------------------------------------------------------------------------------------
 // Stem: dense 3x3 stride-2 conv 3 -> 16 + bias + ReLU on the bf16 planar input produced by K1
 // (K = 27: CUDA cores; the layer is bound by its 6.5 MB / frame fp32 NHWC write).
 // One thread = 4 horizontally adjacent output pixels x 16 channels: per (channel, row) one
@@ -976,6 +1340,80 @@ int launch_layer(fr_ctx* ctx, const PackedConv& pc, const LayerIO& io, int n) {
   return FR_OK;
 }
 
+// dense 3x3 stride-1 conv through conv3_halo_kernel (head >= 0: the fused 64 -> 30 head conv)
+int launch_conv3_halo(fr_ctx* ctx, const PackedConv& pc, const float* in, float* out, int hw, int head, int n) {
+  DetModel* m = ctx->det;
+  if (pc.mode != LD_IM2COL || pc.stride != 1 || pc.n_tiles_n != 1)
+    return fr_fail(ctx, FR_ERR_INVALID_ARG, "conv3_halo: not a dense 3x3 stride-1 layer");
+  C3Params p;
+  memset(&p, 0, sizeof(p));
+  p.out = out;
+  p.bias = pc.bias;
+  p.epi = head >= 0 ? EPI_HEAD : EPI_STD;
+  if (head >= 0) {
+    p.score = m->score[head];
+    p.bbox = m->bbox[head];
+    p.kps = m->kps[head];
+  }
+  p.cin = pc.cin;
+  p.cout = pc.cout;
+  p.h = p.w = hw;
+  p.n_img = n;
+  p.kc = pc.kc;
+  p.n_in = pc.n_in;
+  p.nt = pc.nt;
+  p.npad_total = pc.npad_total;
+  if (hw % 16 == 0 && hw >= 80) { p.tw = 16; p.th = 7; }
+  else if (hw % 20 == 0) { p.tw = 20; p.th = 5; }
+  else return fr_fail(ctx, FR_ERR_UNSUPPORTED, "scrfd feature map size not tileable");
+  p.tw2 = p.tw + 2;
+  p.tiles_x = hw / p.tw;
+  p.tiles_y = ceil_div(hw, p.th);
+  p.num_tiles = n * p.tiles_x * p.tiles_y;
+  auto magic = [](uint32_t d) { return d <= 1 ? 0u : (uint32_t)(((1ull << 32) + d - 1) / d); };
+  p.tiles_per_img_magic = magic((uint32_t)(p.tiles_x * p.tiles_y));
+  p.tiles_x_magic = magic((uint32_t)p.tiles_x);
+  p.tw2_magic = magic((uint32_t)p.tw2);
+  p.chunk_magic = magic((uint32_t)(p.kc / 4));
+  p.box_px = (p.th + 2) * p.tw2;
+  p.in_bytes = (p.box_px * p.kc * 4 + 1023) / 1024 * 1024;
+  p.a_rows = (127 + 2 * p.tw2 + 2 + 1 + 7) / 8 * 8;
+  const int a2 = 2 * p.a_rows * 128, b2 = 2 * pc.nt * 128, nkb = pc.n_in * 9;
+  const int budget = 227 * 1024 - 1024 - 1024 - pc.npad_total * 4;
+  p.s_in = 2;
+  p.s_a = 2;
+  const int rest = budget - p.s_in * p.in_bytes - p.s_a * a2;
+  p.b_resident = (nkb <= C3_MAX_B && nkb * b2 <= rest) ? 1 : 0;
+  p.s_b = p.b_resident ? nkb : std::min(10, rest / b2);   // streamed weights: keep ~one box of taps in flight
+  if (p.s_b < 2) return fr_fail(ctx, FR_ERR_UNSUPPORTED, "conv3_halo: does not fit shared memory");
+  auto used = [&]() { return p.s_in * p.in_bytes + p.s_a * a2 + p.s_b * b2; };
+  if (used() + p.in_bytes <= budget) p.s_in++;
+  if (used() + a2 <= budget) p.s_a++;
+  if (used() + p.in_bytes <= budget) p.s_in++;
+  const int slot = 4 * pc.nt;
+  p.acc_stages = 2 * slot <= 512 ? 2 : 1;
+  int cols = 32;
+  while (cols < p.acc_stages * slot) cols *= 2;
+  p.tmem_cols = cols;
+  p.err_flag = m->err_flag;
+  const int rows_in = n * hw;
+  if (pc.tm_in != in || pc.tm_rows != rows_in || pc.tm_bw != p.tw2 || pc.tm_bh != p.th + 2) {
+    if (!tc_make_map_3d_f32(&pc.tmIn, in, (uint64_t)pc.cin, (uint64_t)hw, (uint64_t)rows_in, (uint32_t)p.kc,
+                            (uint32_t)p.tw2, (uint32_t)(p.th + 2)))
+      return fr_fail(ctx, FR_ERR_CUDA, "scrfd input tensor map creation failed");
+    pc.tm_in = in;
+    pc.tm_rows = rows_in;
+    pc.tm_bw = p.tw2;
+    pc.tm_bh = p.th + 2;
+  }
+  const int smem = used() + 1024 + 1024 + pc.npad_total * 4;
+  const int grid = std::min(p.num_tiles, m->num_sms);
+  conv3_halo_kernel<<<grid, THREADS, smem, ctx->stream>>>(pc.tmIn, pc.tmW, p);
+  ctx->launches++;
+  FR_CUDA_OK(ctx, cudaGetLastError());
+  return FR_OK;
+}
+
 }  // namespace
 
 int det_model_create(fr_ctx* ctx, const fr_weights* w) {
@@ -1041,7 +1479,8 @@ int det_model_create(fr_ctx* ctx, const fr_weights* w) {
   if (ok) {
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, ctx->device) == cudaSuccess) m->num_sms = prop.multiProcessorCount;
-    ok = cudaFuncSetAttribute(sep_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) == cudaSuccess;
+    ok = cudaFuncSetAttribute(sep_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) == cudaSuccess &&
+         cudaFuncSetAttribute(conv3_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) == cudaSuccess;
   }
   if (!ok) {
     for (void* p : m->allocs) cudaFree(p);
@@ -1103,6 +1542,8 @@ int det_forward(fr_ctx* ctx, const __nv_bfloat16* d_in_chw, int n, HeadPtrs* hea
   }
   auto conv3 = [&](const std::string& name, const float* in, float* out, int hin, int stride,
                    int accumulate) -> int {
+    static const bool use_halo = !getenv("FR_SCRFD_NO_C3HALO");
+    if (stride == 1 && !accumulate && use_halo) return launch_conv3_halo(ctx, m->conv.at(name), in, out, hin, -1, n);
     LayerIO io;
     io.in = in; io.out = out; io.hin = hin; io.stride = stride; io.accumulate = accumulate;
     return launch_layer(ctx, m->conv.at(name), io, n);
@@ -1117,9 +1558,14 @@ int det_forward(fr_ctx* ctx, const __nv_bfloat16* d_in_chw, int n, HeadPtrs* hea
     const std::string h = "h" + std::to_string(i);
     FR_CHECK(dwsep(h + ".t0", outs[i], m->tw0[i], fh[i], 1));
     FR_CHECK(dwsep(h + ".t1", m->tw0[i], m->tw1[i], fh[i], 1));
-    LayerIO io;
-    io.in = m->tw1[i]; io.hin = fh[i]; io.head = i;
-    FR_CHECK(launch_layer(ctx, m->conv.at(h + ".out"), io, n));
+    static const bool use_halo = !getenv("FR_SCRFD_NO_C3HALO");
+    if (use_halo) {
+      FR_CHECK(launch_conv3_halo(ctx, m->conv.at(h + ".out"), m->tw1[i], nullptr, fh[i], i, n));
+    } else {
+      LayerIO io;
+      io.in = m->tw1[i]; io.hin = fh[i]; io.head = i;
+      FR_CHECK(launch_layer(ctx, m->conv.at(h + ".out"), io, n));
+    }
     heads->score[i] = m->score[i];
     heads->bbox[i] = m->bbox[i];
     heads->kps[i] = m->kps[i];
