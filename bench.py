@@ -48,6 +48,17 @@ GFLOP_PER_FACE_STEM = 2 * 21.6760e-3  # 3->64 3x3 @112^2, runs on the CUDA cores
 TC_LAUNCHES_PER_STEP = 49           # 48 convs (the 4 shortcut 1x1 are fused as taps) + FC
 
 
+def bench_config(world):
+    """The workload both arms report (BASELINE.json configs[3] shape on one node)."""
+    return {"workload": "det+align+embed: 64 frames 640x640 per GPU per step, 8 faces/frame "
+                        "(top post-NMS detections, padded with seeded synthetic landmark sets), "
+                        "SCRFD det_500m on tcgen05 tf32x3 (fp32-grade) + IResNet-50 bf16/fp32-accum, "
+                        "random-init weights seed 1",
+            "frames_per_gpu_per_step": FRAMES_PER_STEP, "faces_per_frame": FACES_PER_FRAME,
+            "l2": "inputs rotate over 4 batches (315 MB > 126 MB L2); activations > 4 GB",
+            "parallelism": f"dp{world} (independent frame batches, no data-path collective)"}
+
+
 def _env_int(name, default):
     try:
         return int(os.environ.get(name, default))
@@ -198,12 +209,11 @@ def run_reference(args, rank, world):
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * secs / max(args.steps, 1),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
-            "config": {"workload": "det+align+embed, 8 faces/frame, 640x640 frames "
-                                   "(bounded sample: 1 frame + 8 faces per step)",
-                       "frames_per_step": frames_per_step, "faces_per_frame": FACES_PER_FRAME},
+            "config": bench_config(args.gpus),
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
-                             "sample": f"{args.steps} steps x (1 frame det + 8 faces align+embed); torch-CPU fp32 + cv2 "
-                                       "stand-in for ORT-CPU + OpenCV, batch 1 per call, all host threads"},
+                             "sample": f"bounded sample of the workload: {args.steps} steps x (1 frame det + 8 faces "
+                                       "align+embed); torch-CPU fp32 + cv2 stand-in for ORT-CPU + OpenCV, "
+                                       "batch 1 per call like the reference, all host threads"},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     emit(line)
 
@@ -376,12 +386,7 @@ def run_gpu(args, rank, world, local_rank):
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-                "config": {"workload": "det+align+embed: 64 frames 640x640 per GPU per step, 8 faces/frame "
-                                       "(top post-NMS detections, padded with seeded synthetic landmark sets), "
-                                       "SCRFD det_500m on tcgen05 tf32x3 (fp32-grade) + IResNet-50 bf16/fp32-accum, random-init weights seed 1",
-                           "frames_per_gpu_per_step": n_img, "faces_per_frame": K,
-                           "l2": "inputs rotate over 4 batches (315 MB > 126 MB L2); activations > 4 GB",
-                           "parallelism": f"dp{world} (independent frame batches, no data-path collective)"},
+                "config": bench_config(world),
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "ms_per_step": 1e3 * e2e_s / args.steps},
                 "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
