@@ -101,3 +101,30 @@ def test_cli_modes_match_the_c_abi(tmp_path, ctx, capi):
     # missing file: message, no crash (src/main.cpp:43-46)
     r = _run(["detect", str(tmp_path / "nope.ppm")], str(tmp_path))
     assert r.returncode == 0 and "无法读取图像" in (r.stdout + r.stderr)
+
+
+@pytest.mark.gpu
+def test_cli_webcam_frame_list(tmp_path, ctx, capi):
+    """webcam mode over a frame list (src/main.cpp:201-262): the first frame with a face sets the
+    reference, every face of the later frames is matched against it with the 0.6 rule; the
+    similarities equal fr_compare on the C-ABI embeddings (batched extractFeatures path)."""
+    _build_host()
+    rng = np.random.default_rng(4)
+    frames = [rng.integers(0, 256, (480, 640, 3), dtype=np.uint8) for _ in range(2)]
+    paths = []
+    for i, f in enumerate(frames):
+        p = str(tmp_path / f"f{i}.ppm")
+        _write_ppm(p, f)
+        paths.append(p)
+    r = _run(["webcam"] + paths, str(tmp_path))
+    assert r.returncode == 0, r.stderr
+    assert "已保存参考人脸特征" in r.stdout and "Reference set" in r.stdout
+    sims = [float(m) for m in re.findall(r"Sim: ([0-9.eE+-]+)", r.stdout)]
+    f0, f1 = ctx.detect(frames[0], cap=1024), ctx.detect(frames[1], cap=1024)
+    assert len(sims) == len(f1)
+    (ref,), _ = ctx.embed_faces([frames[0]], f0[:1], [0])
+    emb, valid = ctx.embed_faces([frames[1]], f1, [0] * len(f1))
+    exp = [capi.compare(ref, e) for e in emb]
+    assert np.allclose(sims, exp, atol=2e-5)
+    labels = re.findall(r"face \d+: (Match|Unknown)", r.stdout)
+    assert labels == ["Match" if s > 0.6 else "Unknown" for s in exp]
