@@ -394,7 +394,8 @@ stem_kernel(const void* __restrict__ in_, int n, const float* __restrict__ w,
 // store instruction writes 64 contiguous bytes per pixel (whole sectors: lane-per-pixel 16-byte
 // stores reach 1.4 TB/s, sector-complete ones > 6 TB/s, tests/dev_write_pattern.py).
 constexpr int STEM_ROWP = (REC + 2) * 3;              // strip row pitch in elements
-constexpr int STEM_WARPS = 8;                         // output rows per block (one warp each)
+constexpr int STEM_WARPS = 8;                         // output rows per row group (one warp each)
+constexpr int STEM_GROUPS = 2;                        // row groups per block (the next group's input is prefetched)
 constexpr int STEM_STRIP = (STEM_WARPS + 3) * STEM_ROWP;   // rows + halo + a spare zero row for k = 27..31
 constexpr int STEM_STAGE_PITCH = 144;                 // bytes per staged pixel (128 + 16: conflict-free)
 
@@ -406,92 +407,115 @@ __device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a
 }
 
 __global__ void __launch_bounds__(STEM_WARPS * 32)
-stem_mma_kernel(const uint8_t* __restrict__ crops, const uint2* __restrict__ bfrag, const float* __restrict__ b,
+stem_mma_kernel(const uint8_t* __restrict__ crops, const uint2* __restrict__ bfrag,
                 const float* __restrict__ slope, bf16* __restrict__ x0, bf16* __restrict__ x0e) {
   __shared__ __align__(16) uint16_t strip[(STEM_STRIP + 7) / 8 * 8];
   __shared__ __align__(16) uint2 sfrag[2 * 8 * 2 * 32];              // [kstep][ntile][hi/lo][lane]
   __shared__ __align__(16) uint8_t stage[STEM_WARPS][16 * STEM_STAGE_PITCH];
   constexpr int NT = STEM_WARPS * 32;
-  const int img = blockIdx.x / (REC / STEM_WARPS);
-  const int y0 = (blockIdx.x - img * (REC / STEM_WARPS)) * STEM_WARPS;
+  constexpr int ROW_WORDS = REC * 3 / 4;                             // 84 u32 per input row
+  constexpr int FILL_WORDS = (STEM_WARPS + 2) * ROW_WORDS;
+  constexpr int FILL_PER_THREAD = (FILL_WORDS + NT - 1) / NT;
+  constexpr int BLOCKS_PER_IMG = REC / (STEM_WARPS * STEM_GROUPS);
+  const int img = blockIdx.x / BLOCKS_PER_IMG;
+  const int yblk = (blockIdx.x - img * BLOCKS_PER_IMG) * (STEM_WARPS * STEM_GROUPS);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, t = lane & 3;
+  const uint8_t* face = crops + (size_t)img * REC * REC * 3;
+  // input words of the row group starting at output row yb (strip row i = input row yb - 1 + i)
+  uint32_t wv[FILL_PER_THREAD];
+  auto prefetch = [&](int yb) {
+#pragma unroll
+    for (int k = 0; k < FILL_PER_THREAD; ++k) {
+      const int i = threadIdx.x + k * NT;
+      const int row = i / ROW_WORDS, wd = i - row * ROW_WORDS, yy = yb - 1 + row;
+      wv[k] = (i < FILL_WORDS && yy >= 0 && yy < REC)
+                  ? __ldg(reinterpret_cast<const uint32_t*>(face + (size_t)yy * REC * 3) + wd) : 0u;
+    }
+  };
+  prefetch(yblk);
   for (int i = threadIdx.x; i < (STEM_STRIP + 7) / 8; i += NT) reinterpret_cast<uint4*>(strip)[i] = make_uint4(0, 0, 0, 0);
   for (int i = threadIdx.x; i < 2 * 8 * 2 * 32 / 2; i += NT)
     reinterpret_cast<uint4*>(sfrag)[i] = __ldg(reinterpret_cast<const uint4*>(bfrag) + i);
-  __syncthreads();
-  // strip row i = input row y0 - 1 + i; BGR bytes -> RGB bf16 of (v - 127.5) / 128 (exact)
-  for (int i = threadIdx.x; i < (STEM_WARPS + 2) * (REC * 3 / 4); i += NT) {
-    const int row = i / (REC * 3 / 4), wd = i - row * (REC * 3 / 4);
-    const int yy = y0 - 1 + row;
-    if (yy < 0 || yy >= REC) continue;
-    const uint32_t v4 = __ldg(reinterpret_cast<const uint32_t*>(crops + ((size_t)img * REC + yy) * REC * 3) + wd);
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const int e = wd * 4 + q, px = e / 3, cb = e - px * 3;
-      const float f = ((float)((v4 >> (8 * q)) & 0xffu) - 127.5f) * (1.0f / 128.0f);
-      strip[row * STEM_ROWP + (px + 1) * 3 + (2 - cb)] = __bfloat16_as_ushort(__float2bfloat16_rn(f));
-    }
-  }
-  __syncthreads();
-  // per-thread constants: offsets of its 8 k indices, bias and slope of its 16 channels
+  // per-thread constants: strip offsets of its 8 k indices, PReLU slopes of its 16 channels
   int koff[8];
 #pragma unroll
   for (int q = 0; q < 8; ++q) {
     const int k = (q >> 2) * 16 + ((q >> 1) & 1) * 8 + 2 * t + (q & 1);
     koff[q] = (k / 9) * STEM_ROWP + (k % 9);
   }
-  float bias[8][2], sl[8][2];
+  float2 sl[8];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    bias[j][0] = __ldg(b + 8 * j + 2 * t); bias[j][1] = __ldg(b + 8 * j + 2 * t + 1);
-    sl[j][0] = __ldg(slope + 8 * j + 2 * t); sl[j][1] = __ldg(slope + 8 * j + 2 * t + 1);
-  }
-  const int y = y0 + warp;
+  for (int j = 0; j < 8; ++j) sl[j] = __ldg(reinterpret_cast<const float2*>(slope + 8 * j + 2 * t));
   constexpr int Wp = REC + 1, Hp = REC + 1, We = REC / 2 + 1, He = REC / 2 + 1;
-  bf16* orow = x0 + (size_t)(img * Hp + y) * Wp * 64;
-  bf16* erow = (!(y & 1)) ? x0e + (size_t)(img * He + (y >> 1)) * We * 64 : nullptr;
   uint8_t* st = stage[warp];
 #pragma unroll 1
-  for (int m = 0; m < REC / 16; ++m) {
-    const uint16_t* s0 = strip + warp * STEM_ROWP + (16 * m + g) * 3;
-    float acc[8][4];
+  for (int gr = 0; gr < STEM_GROUPS; ++gr) {
+    const int y0 = yblk + gr * STEM_WARPS;
+    __syncthreads();                                   // zero fill done / previous group's readers done
+    // BGR bytes -> RGB bf16 of (v - 127.5) / 128 (exact in bf16); rows outside the face are zero
 #pragma unroll
-    for (int j = 0; j < 8; ++j) { acc[j][0] = bias[j][0]; acc[j][1] = bias[j][1]; acc[j][2] = bias[j][0]; acc[j][3] = bias[j][1]; }
+    for (int k = 0; k < FILL_PER_THREAD; ++k) {
+      const int i = threadIdx.x + k * NT;
+      if (i < FILL_WORDS) {
+        const int row = i / ROW_WORDS, wd = i - row * ROW_WORDS, yy = y0 - 1 + row;
+        const bool in = yy >= 0 && yy < REC;
 #pragma unroll
-    for (int ks = 0; ks < 2; ++ks) {
-      uint32_t a[4];
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {                       // a0:(g,k lo) a1:(g+8,k lo) a2:(g,k hi) a3:(g+8,k hi)
-        const uint16_t* sp = s0 + (q & 1) * 24;
-        const int ko = ks * 4 + (q >> 1) * 2;
-        a[q] = (uint32_t)sp[koff[ko]] | ((uint32_t)sp[koff[ko + 1]] << 16);
+        for (int q = 0; q < 4; ++q) {
+          const int e = wd * 4 + q, px = e / 3, cb = e - px * 3;
+          const float f = in ? ((float)((wv[k] >> (8 * q)) & 0xffu) - 127.5f) * (1.0f / 128.0f) : 0.f;
+          strip[row * STEM_ROWP + (px + 1) * 3 + (2 - cb)] = __bfloat16_as_ushort(__float2bfloat16_rn(f));
+        }
       }
+    }
+    __syncthreads();
+    if (gr + 1 < STEM_GROUPS) prefetch(y0 + STEM_WARPS);   // in flight while this group computes
+    const int y = y0 + warp;
+    bf16* orow = x0 + (size_t)(img * Hp + y) * Wp * 64;
+    bf16* erow = (!(y & 1)) ? x0e + (size_t)(img * He + (y >> 1)) * We * 64 : nullptr;
+#pragma unroll 1
+    for (int m = 0; m < REC / 16; ++m) {
+      const uint16_t* s0 = strip + warp * STEM_ROWP + (16 * m + g) * 3;
+      float acc[8][4];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { acc[j][0] = 0.f; acc[j][1] = 0.f; acc[j][2] = 0.f; acc[j][3] = 0.f; }
+#pragma unroll
+      for (int ks = 0; ks < 2; ++ks) {
+        uint32_t a[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {                     // a0:(g,k lo) a1:(g+8,k lo) a2:(g,k hi) a3:(g+8,k hi)
+          const uint16_t* sp = s0 + (q & 1) * 24;
+          const int ko = ks * 4 + (q >> 1) * 2;
+          a[q] = (uint32_t)sp[koff[ko]] | ((uint32_t)sp[koff[ko + 1]] << 16);
+        }
+        if (ks == 1 && t == 1) {                          // k = 27 carries the bias: A = 1.0
+          a[2] = (a[2] & 0xffffu) | 0x3f800000u;
+          a[3] = (a[3] & 0xffffu) | 0x3f800000u;
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          mma_bf16_16816(acc[j], a, sfrag[((ks * 8 + j) * 2 + 0) * 32 + lane]);
+          mma_bf16_16816(acc[j], a, sfrag[((ks * 8 + j) * 2 + 1) * 32 + lane]);
+        }
+      }
+      // PReLU, bf16, stage: pixel r of the tile at st + r*144, channel pair (8j + 2t) at byte 16j + 4t
+      __syncwarp();
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        mma_bf16_16816(acc[j], a, sfrag[((ks * 8 + j) * 2 + 0) * 32 + lane]);
-        mma_bf16_16816(acc[j], a, sfrag[((ks * 8 + j) * 2 + 1) * 32 + lane]);
+        float v0 = acc[j][0], v1 = acc[j][1], v2 = acc[j][2], v3 = acc[j][3];
+        v0 = v0 > 0.f ? v0 : v0 * sl[j].x; v1 = v1 > 0.f ? v1 : v1 * sl[j].y;
+        v2 = v2 > 0.f ? v2 : v2 * sl[j].x; v3 = v3 > 0.f ? v3 : v3 * sl[j].y;
+        *reinterpret_cast<uint32_t*>(st + g * STEM_STAGE_PITCH + 16 * j + 4 * t) = tc::pack_bf16(v0, v1);
+        *reinterpret_cast<uint32_t*>(st + (g + 8) * STEM_STAGE_PITCH + 16 * j + 4 * t) = tc::pack_bf16(v2, v3);
       }
-    }
-    // PReLU, bf16, stage: pixel row r of the tile at st + r*144, channel pair (8j + 2t) at byte 16j + 4t
-    __syncwarp();
+      __syncwarp();
+      // a quarter warp moves one pixel's 128 bytes: conflict-free reads, whole-line stores
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      float v0 = acc[j][0], v1 = acc[j][1], v2 = acc[j][2], v3 = acc[j][3];
-      v0 = v0 > 0.f ? v0 : v0 * sl[j][0]; v1 = v1 > 0.f ? v1 : v1 * sl[j][1];
-      v2 = v2 > 0.f ? v2 : v2 * sl[j][0]; v3 = v3 > 0.f ? v3 : v3 * sl[j][1];
-      *reinterpret_cast<uint32_t*>(st + g * STEM_STAGE_PITCH + 16 * j + 4 * t) = tc::pack_bf16(v0, v1);
-      *reinterpret_cast<uint32_t*>(st + (g + 8) * STEM_STAGE_PITCH + 16 * j + 4 * t) = tc::pack_bf16(v2, v3);
-    }
-    __syncwarp();
-#pragma unroll
-    for (int pass = 0; pass < 2; ++pass) {
-      const int r = pass * 8 + g, x = 16 * m + r;
-#pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        const uint4 v = *reinterpret_cast<const uint4*>(st + r * STEM_STAGE_PITCH + 64 * h + 16 * t);
-        *reinterpret_cast<uint4*>(orow + (size_t)x * 64 + 32 * h + 8 * t) = v;
-        if (erow && !(x & 1)) *reinterpret_cast<uint4*>(erow + (size_t)(x >> 1) * 64 + 32 * h + 8 * t) = v;
+      for (int pass = 0; pass < 4; ++pass) {
+        const int r = pass * 4 + (lane >> 3), x = 16 * m + r;
+        const uint4 v = *reinterpret_cast<const uint4*>(st + r * STEM_STAGE_PITCH + 16 * (lane & 7));
+        *reinterpret_cast<uint4*>(orow + (size_t)x * 64 + 8 * (lane & 7)) = v;
+        if (erow && !(x & 1)) *reinterpret_cast<uint4*>(erow + (size_t)(x >> 1) * 64 + 8 * (lane & 7)) = v;
       }
     }
   }
@@ -634,8 +658,9 @@ int rec_model_create(fr_ctx* ctx, const fr_weights* w) {
     m->stem_w = dev_upload(ctx, m.get(), pw);
     // B fragments of mma.m16n8k16 (lane = 4g + t): b0 = W[k0 + 2t, +1][n = 8j + g], b1 = W[k0 + 2t + 8, +9][n]
     std::vector<uint2> frag(2 * 8 * 2 * 32);
+    const std::vector<float>& sbias = w->at("stem.b").data;
     auto split = [&](int k, int n, int which) -> uint32_t {
-      const float v = k < 27 ? pw[(size_t)k * 64 + n] : 0.f;
+      const float v = k < 27 ? pw[(size_t)k * 64 + n] : (k == 27 ? sbias[n] : 0.f);   // k = 27: bias row (A = 1)
       const bf16 hi = __float2bfloat16_rn(v);
       const bf16 r = which == 0 ? hi : __float2bfloat16_rn(v - __bfloat162float(hi));
       uint16_t u;
@@ -912,8 +937,8 @@ int rec_forward_crops(fr_ctx* ctx, const uint8_t* d_crops, int n, float* d_out_r
     stem_kernel<true><<<(unsigned)((threads + 127) / 128), 128, 0, ctx->stream>>>(
         d_crops, n, m->stem_w, m->stem_b, m->stem_prelu, m->x0.p, m->x0e.p);
   } else {
-    stem_mma_kernel<<<(unsigned)(n * (REC / STEM_WARPS)), STEM_WARPS * 32, 0, ctx->stream>>>(d_crops, m->stem_bfrag, m->stem_b,
-                                                                       m->stem_prelu, m->x0.p, m->x0e.p);
+    stem_mma_kernel<<<(unsigned)(n * (REC / (STEM_WARPS * STEM_GROUPS))), STEM_WARPS * 32, 0, ctx->stream>>>(
+        d_crops, m->stem_bfrag, m->stem_prelu, m->x0.p, m->x0e.p);
   }
   ctx->stage_end();
   ctx->launches++;
