@@ -1064,6 +1064,133 @@ stem_conv_kernel(const __nv_bfloat16* __restrict__ in, float* __restrict__ out, 
                                   fmaxf(acc[j][4 * i + 2], 0.f), fmaxf(acc[j][4 * i + 3], 0.f));
 }
 
+
+// ---------------------------------------------------------------------------------------
+// The same stem on warp-level MMA (the default).  The CUDA-core kernel above is instruction bound
+// (432 FMAs per pixel) at 2.1 TB/s; the layer's bound is the 6.5 MB / frame write.  Here a warp
+// computes 16 pixels x 16 channels per step as an m16n8k16 bf16 GEMM with K = 27 (+ a bias row,
+// padded to 32).  K1's inputs (v - 127.5) / 128 are exact in bf16 and the fp32 weights enter as
+// three bf16 pieces (24 bits: exact), so every product is exact in fp32 and the result differs from
+// the FMA chain only by fp32 summation order.  A block walks SM_GROUPS groups of 4 output rows x half
+// a frame; each group's 9 input rows x 3 planes are staged in shared memory by cp.async, double
+// buffered so the next group lands while this one computes; the C fragments pass through a padded
+// per-warp tile so that every store instruction writes 512 contiguous bytes (8 pixels x 64 B).
+constexpr int SM_ROWS = 9, SM_COLS = DET / 2, SM_PITCH = SM_COLS + 16;   // strip: half a frame wide; ix0 - 1 at index 7
+constexpr int SM_STAGE_PITCH = 96;                                // bytes per staged pixel (64 + 32: conflict-free)
+
+__device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a)[4], uint2 b) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b.x), "r"(b.y));
+}
+
+constexpr int SM_GROUPS = 4;                                      // 4-row groups per block (double-buffered strips)
+constexpr int SM_STRIP_ELEMS = 3 * SM_ROWS * SM_PITCH;
+constexpr int SM_SMEM_BYTES = 2 * SM_STRIP_ELEMS * 2 + 4 * 16 * SM_STAGE_PITCH;
+
+__global__ void __launch_bounds__(128)
+stem_conv_mma_kernel(const __nv_bfloat16* __restrict__ in, float* __restrict__ out, const uint2* __restrict__ bfrag) {
+  extern __shared__ __align__(16) uint8_t sm_raw[];
+  uint16_t* strips = reinterpret_cast<uint16_t*>(sm_raw);                        // [2][3][SM_ROWS][SM_PITCH]
+  uint8_t* stage_base = sm_raw + 2 * SM_STRIP_ELEMS * 2;                         // [4 warps][16 px][96 B]
+  constexpr int HO = DET / 2, BLOCKS_PER_IMG = 2 * HO / (4 * SM_GROUPS);
+  const int n = blockIdx.x / BLOCKS_PER_IMG;
+  const int bi = blockIdx.x - n * BLOCKS_PER_IMG;
+  const int oyb = (bi >> 1) * (4 * SM_GROUPS);
+  const int ix0 = (bi & 1) * SM_COLS, ox0 = ix0 / 2;   // this block's half of the frame
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, t = lane & 3;
+  // strip[c][row][8 + ix - ix0] = input (c, 2*oy0 - 1 + row, ix); the 8 elements before ix0 are zero for the left half.
+  // Filled with 16-byte cp.async so that the next group's rows land while this group computes.
+  const __nv_bfloat16* ip = in + (size_t)n * 3 * DET * DET;
+  auto fill = [&](int buf, int oy0) {
+    uint16_t* sp = strips + buf * SM_STRIP_ELEMS;
+    for (int i = threadIdx.x; i < 3 * SM_ROWS * (SM_COLS / 8 + 1); i += 128) {
+      const int cr = i / (SM_COLS / 8 + 1), q = i - cr * (SM_COLS / 8 + 1) - 1;   // q = -1: the 8 columns before ix0
+      const int c = cr / SM_ROWS, row = cr - c * SM_ROWS, iy = 2 * oy0 - 1 + row;
+      uint16_t* dst = sp + (size_t)cr * SM_PITCH + 8 + 8 * q;
+      if (iy >= 0 && ix0 + 8 * q >= 0) {
+        const uint32_t d = smem_u32(dst);
+        const void* src = ip + ((size_t)c * DET + iy) * DET + ix0 + 8 * q;
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(src) : "memory");
+      } else {
+        *reinterpret_cast<uint4*>(dst) = make_uint4(0, 0, 0, 0);
+      }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  fill(0, oyb);
+  // per-thread constants: strip offsets of its 8 k indices (k = (c*3 + r)*3 + s), weight fragments
+  int koff[8];
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    const int k = (q >> 2) * 16 + ((q >> 1) & 1) * 8 + 2 * t + (q & 1);
+    const int c = k / 9, r = (k - c * 9) / 3, sx = k - c * 9 - r * 3;
+    koff[q] = k < 27 ? (c * SM_ROWS + r) * SM_PITCH + 7 + sx : 0;
+  }
+  uint2 bf[2][2][3];
+#pragma unroll
+  for (int ks = 0; ks < 2; ++ks)
+#pragma unroll
+    for (int j = 0; j < 2; ++j)
+#pragma unroll
+      for (int h = 0; h < 3; ++h) bf[ks][j][h] = __ldg(bfrag + ((ks * 2 + j) * 3 + h) * 32 + lane);
+  uint8_t* st = stage_base + warp * 16 * SM_STAGE_PITCH;
+  // read-back mapping: a quarter warp takes pixels r and r + 2 (distinct banks at a 96-byte pitch)
+  const int rq = ((lane >> 4) << 2) + ((lane >> 3) & 1) + (((lane >> 2) & 1) << 1);
+#pragma unroll 1
+  for (int gr = 0; gr < SM_GROUPS; ++gr) {
+    const int oy0 = oyb + 4 * gr;
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();                                   // this group's strip is complete; the other buffer is free
+    if (gr + 1 < SM_GROUPS) fill((gr + 1) & 1, oy0 + 4);
+    const uint16_t* strip = strips + (gr & 1) * SM_STRIP_ELEMS;
+    const int oy = oy0 + warp;
+    float* orow = out + (((size_t)n * HO + oy) * HO + ox0) * 16;
+#pragma unroll 1
+    for (int m = 0; m < HO / 32; ++m) {
+      const uint16_t* s0 = strip + (2 * warp) * SM_PITCH + 2 * (16 * m + g);
+      float acc[2][4];
+#pragma unroll
+      for (int j = 0; j < 2; ++j) { acc[j][0] = 0.f; acc[j][1] = 0.f; acc[j][2] = 0.f; acc[j][3] = 0.f; }
+#pragma unroll
+      for (int ks = 0; ks < 2; ++ks) {
+        uint32_t a[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {                     // a0:(g,k lo) a1:(g+8,k lo) a2:(g,k hi) a3:(g+8,k hi)
+          const uint16_t* sp = s0 + (q & 1) * 16;
+          const int ko = ks * 4 + (q >> 1) * 2;
+          a[q] = (uint32_t)sp[koff[ko]] | ((uint32_t)sp[koff[ko + 1]] << 16);
+        }
+        if (ks == 1 && t == 1) {                          // k = 27 carries the bias: A = 1.0
+          a[2] = (a[2] & 0xffffu) | 0x3f800000u;
+          a[3] = (a[3] & 0xffffu) | 0x3f800000u;
+        }
+#pragma unroll
+        for (int j = 0; j < 2; ++j)
+#pragma unroll
+          for (int h = 2; h >= 0; --h) mma_bf16_16816(acc[j], a, bf[ks][j][h]);   // small pieces first
+      }
+      __syncwarp();
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        *reinterpret_cast<float2*>(st + g * SM_STAGE_PITCH + 32 * j + 8 * t) =
+            make_float2(fmaxf(acc[j][0], 0.f), fmaxf(acc[j][1], 0.f));
+        *reinterpret_cast<float2*>(st + (g + 8) * SM_STAGE_PITCH + 32 * j + 8 * t) =
+            make_float2(fmaxf(acc[j][2], 0.f), fmaxf(acc[j][3], 0.f));
+      }
+      __syncwarp();
+#pragma unroll
+      for (int pass = 0; pass < 2; ++pass) {
+        const int r = pass * 8 + rq;
+        const float4 v = *reinterpret_cast<const float4*>(st + r * SM_STAGE_PITCH + 16 * t);
+        *reinterpret_cast<float4*>(orow + (size_t)(16 * m + r) * 16 + 4 * t) = v;
+      }
+    }
+  }
+}
+
 }  // namespace
 
 struct PackedConv {        // device-side packed parameters of one (fused) layer
@@ -1085,6 +1212,7 @@ struct DetModel {
   std::map<std::string, PackedConv> conv;
   float* stem_w = nullptr;
   float* stem_b = nullptr;
+  uint2* stem_bfrag = nullptr;   // stem weights + bias row as m16n8k16 B fragments [kstep][ntile][piece][lane]
   std::vector<void*> allocs;
   int cap = 0;
   std::vector<void*> act_allocs;
@@ -1447,6 +1575,36 @@ int det_model_create(fr_ctx* ctx, const fr_weights* w) {
     m->stem_w = upload(m.get(), sw);
     m->stem_b = upload(m.get(), w->at("stem.b").data);
     ok = ok && m->stem_w && m->stem_b;
+    // B fragments (lane = 4g + t): b0 = W[k0 + 2t, +1][n = 8j + g], b1 = W[k0 + 2t + 8, +9][n]; row 27 = bias;
+    // each fp32 value as three bf16 pieces (hi, mid, lo)
+    const std::vector<float>& sbv = w->at("stem.b").data;
+    auto piece = [&](int k, int nn, int h) -> uint32_t {
+      float v = k < 27 ? sw[(size_t)k * 16 + nn] : (k == 27 ? sbv[nn] : 0.f);
+      __nv_bfloat16 pb = __float2bfloat16_rn(v);
+      for (int i = 0; i < h; ++i) {
+        v -= __bfloat162float(pb);
+        pb = __float2bfloat16_rn(v);
+      }
+      uint16_t u;
+      memcpy(&u, &pb, 2);
+      return u;
+    };
+    std::vector<uint2> frag(2 * 2 * 3 * 32);
+    for (int ks = 0; ks < 2; ++ks)
+      for (int j = 0; j < 2; ++j)
+        for (int h = 0; h < 3; ++h)
+          for (int lane = 0; lane < 32; ++lane) {
+            const int g = lane >> 2, t = lane & 3, k0 = ks * 16 + 2 * t, nn = 8 * j + g;
+            uint2 f;
+            f.x = piece(k0, nn, h) | (piece(k0 + 1, nn, h) << 16);
+            f.y = piece(k0 + 8, nn, h) | (piece(k0 + 9, nn, h) << 16);
+            frag[((ks * 2 + j) * 3 + h) * 32 + lane] = f;
+          }
+    if (cudaMalloc(&m->stem_bfrag, frag.size() * sizeof(uint2)) != cudaSuccess) ok = false;
+    else {
+      cudaMemcpy(m->stem_bfrag, frag.data(), frag.size() * sizeof(uint2), cudaMemcpyHostToDevice);
+      m->allocs.push_back(m->stem_bfrag);
+    }
   }
   dwsep("b0", 1);
   for (int s = 0; s < 4; ++s)
@@ -1508,9 +1666,18 @@ int det_forward(fr_ctx* ctx, const __nv_bfloat16* d_in_chw, int n, HeadPtrs* hea
   FR_CHECK(det_build_acts(ctx, cap));
   // stem: 3x3 s2, 3 -> 16, ReLU (bf16 planar input from K1) -> fp32 NHWC
   {
-    const size_t total = (size_t)n * (DET / 2) * (DET / 2 / 4);
-    stem_conv_kernel<<<(unsigned)((total + 127) / 128), 128, 0, ctx->stream>>>(d_in_chw, m->a_stem, m->stem_w,
-                                                                                m->stem_b, n);
+    static const bool simt_stem = getenv("FR_SCRFD_STEM_SIMT") != nullptr;   // A/B switch: the CUDA-core stem
+    if (simt_stem) {
+      const size_t total = (size_t)n * (DET / 2) * (DET / 2 / 4);
+      stem_conv_kernel<<<(unsigned)((total + 127) / 128), 128, 0, ctx->stream>>>(d_in_chw, m->a_stem, m->stem_w,
+                                                                                  m->stem_b, n);
+    } else {
+      static const cudaError_t attr = cudaFuncSetAttribute(stem_conv_mma_kernel,
+                                                          cudaFuncAttributeMaxDynamicSharedMemorySize, SM_SMEM_BYTES);
+      FR_CUDA_OK(ctx, attr);
+      stem_conv_mma_kernel<<<(unsigned)(n * (DET / (4 * SM_GROUPS))), 128, SM_SMEM_BYTES, ctx->stream>>>(
+          d_in_chw, m->a_stem, m->stem_bfrag);
+    }
     ctx->launches++;
     FR_CUDA_OK(ctx, cudaGetLastError());
   }
