@@ -1191,6 +1191,131 @@ stem_conv_mma_kernel(const __nv_bfloat16* __restrict__ in, float* __restrict__ o
   }
 }
 
+// ---------------------------------------------------------------------------------------
+// b0 (depthwise 3x3 + ReLU -> 1x1 16 -> 16 + ReLU on the 320 x 320 x 16 stem output) on warp-level MMA.
+// K = N = 16: the tcgen05 pipeline above spends its time on hand-offs (348 us for a 0.84 GB
+// stream).  Here a warp owns 16 pixels per step: each thread computes the depthwise outputs of
+// 2 pixels x 4 channels on CUDA cores straight into the A fragment of an m16n8k8 tf32 MMA (the
+// GEMM's k slots are a permutation of the channels so that those 4 channels are one float4 of the
+// NHWC input), splits them hi/lo like the converter warps do, and the three-term product runs with
+// separate small / big accumulators.  The C fragment of a quad is one 32-byte sector per pixel, so
+// it is stored directly.  Block = 8 warps = 8 output rows x 64 pixels per group; the 10 x 66 pixel
+// input tile arrives by cp.async, double buffered over B0_GROUPS groups.
+constexpr int B0_TW = 64, B0_ROWS = 8, B0_TP = B0_TW + 2, B0_TR = B0_ROWS + 2, B0_GROUPS = 4;
+constexpr int B0_TILE_FLOATS = B0_TR * B0_TP * 16;
+constexpr int B0_SMEM_BYTES = 2 * B0_TILE_FLOATS * 4;
+
+__device__ __forceinline__ void mma_tf32_1688(float (&d)[4], const uint32_t (&a)[4], float2 b) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(__float_as_uint(b.x)), "r"(__float_as_uint(b.y)));
+}
+
+__global__ void __launch_bounds__(256, 2)
+b0_dwpw_mma_kernel(const float* __restrict__ in, float* __restrict__ out, const float* __restrict__ dw_w,
+                   const float* __restrict__ dw_b, const float2* __restrict__ bfrag, const float* __restrict__ pw_b,
+                   int hw) {
+  extern __shared__ __align__(16) uint8_t sm_raw[];
+  float* tiles = reinterpret_cast<float*>(sm_raw);                    // [2][B0_TR][B0_TP][16]
+  const int strips = hw / B0_TW, row_blocks = hw / (B0_ROWS * B0_GROUPS);
+  const int n = blockIdx.x / (strips * row_blocks);
+  const int bi = blockIdx.x - n * (strips * row_blocks);
+  const int x0 = (bi % strips) * B0_TW, oyb = (bi / strips) * (B0_ROWS * B0_GROUPS);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, t = lane & 3;
+  const float* ip = in + (size_t)n * hw * hw * 16;
+  // tile[row][px][16] = input (oy0 - 1 + row, x0 - 1 + px); outside the frame: zero (the dw conv's padding)
+  auto fill = [&](int buf, int oy0) {
+    float* tp = tiles + buf * B0_TILE_FLOATS;
+    for (int i = threadIdx.x; i < B0_TR * B0_TP * 4; i += 256) {
+      const int row = i / (B0_TP * 4), rem = i - row * (B0_TP * 4);
+      const int iy = oy0 - 1 + row, ix = x0 - 1 + (rem >> 2);
+      float* dst = tp + (size_t)i * 4;
+      if (iy >= 0 && iy < hw && ix >= 0 && ix < hw) {
+        const uint32_t d = smem_u32(dst);
+        const void* src = ip + ((size_t)iy * hw + ix) * 16 + (rem & 3) * 4;
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(src) : "memory");
+      } else {
+        *reinterpret_cast<float4*>(dst) = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  fill(0, oyb);
+  // per-thread constants: depthwise taps / bias of channels 4t .. 4t+3, 1x1 weight fragments, 1x1 bias
+  float4 wd[9];
+#pragma unroll
+  for (int q = 0; q < 9; ++q) wd[q] = ldg4(dw_w + q * 16 + 4 * t);
+  const float4 bd = ldg4(dw_b + 4 * t);
+  float2 bw[2][2][2];                                   // [k step][n tile][hi / lo]
+#pragma unroll
+  for (int ks = 0; ks < 2; ++ks)
+#pragma unroll
+    for (int j = 0; j < 2; ++j)
+#pragma unroll
+      for (int h = 0; h < 2; ++h) bw[ks][j][h] = __ldg(bfrag + ((ks * 2 + j) * 2 + h) * 32 + lane);
+  float2 pb[2];
+#pragma unroll
+  for (int j = 0; j < 2; ++j) pb[j] = __ldg(reinterpret_cast<const float2*>(pw_b + 8 * j + 2 * t));
+#pragma unroll 1
+  for (int gr = 0; gr < B0_GROUPS; ++gr) {
+    const int oy0 = oyb + B0_ROWS * gr;
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();                                    // this group's tile is complete; the other buffer is free
+    if (gr + 1 < B0_GROUPS) fill((gr + 1) & 1, oy0 + B0_ROWS);
+    const uint32_t tile = smem_u32(tiles + (gr & 1) * B0_TILE_FLOATS);
+    const int oy = oy0 + warp;
+    float* orow = out + (((size_t)n * hw + oy) * hw + x0) * 16;
+#pragma unroll 1
+    for (int m = 0; m < B0_TW / 16; ++m) {
+      // depthwise 3x3 + bias + ReLU of pixels (16m + g) and (16m + g + 8), channels 4t .. 4t+3
+      float4 x[2];
+#pragma unroll
+      for (int hpx = 0; hpx < 2; ++hpx) {
+        float4 a = bd;
+        const uint32_t base = tile + (uint32_t)(((warp * B0_TP) + 16 * m + g + 8 * hpx) * 64 + 16 * t);
+#pragma unroll
+        for (int r = 0; r < 3; ++r)
+#pragma unroll
+          for (int dx = 0; dx < 3; ++dx) fma4(a, lds4(base + (uint32_t)((r * B0_TP + dx) * 64)), wd[r * 3 + dx]);
+        x[hpx] = make_float4(fmaxf(a.x, 0.f), fmaxf(a.y, 0.f), fmaxf(a.z, 0.f), fmaxf(a.w, 0.f));
+      }
+      const float xs[2][4] = {{x[0].x, x[0].y, x[0].z, x[0].w}, {x[1].x, x[1].y, x[1].z, x[1].w}};
+      float accS[2][4], accB[2][4];
+#pragma unroll
+      for (int j = 0; j < 2; ++j)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { accS[j][i] = 0.f; accB[j][i] = 0.f; }
+#pragma unroll
+      for (int ks = 0; ks < 2; ++ks) {
+        // k slot t <-> channel 4t + 2ks, k slot t + 4 <-> channel 4t + 2ks + 1 (the weights are permuted to match)
+        uint32_t ahi[4], alo[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {                     // a0:(g, slot t) a1:(g+8, slot t) a2:(g, t+4) a3:(g+8, t+4)
+          const float v = xs[q & 1][2 * ks + (q >> 1)];
+          const float h = tf32_rna(v);
+          ahi[q] = __float_as_uint(h);
+          alo[q] = __float_as_uint(tf32_rna(v - h));
+        }
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          mma_tf32_1688(accS[j], alo, bw[ks][j][0]);
+          mma_tf32_1688(accS[j], ahi, bw[ks][j][1]);
+          mma_tf32_1688(accB[j], ahi, bw[ks][j][0]);
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const float2 lo = make_float2(fmaxf(accB[j][0] + accS[j][0] + pb[j].x, 0.f), fmaxf(accB[j][1] + accS[j][1] + pb[j].y, 0.f));
+        const float2 hi = make_float2(fmaxf(accB[j][2] + accS[j][2] + pb[j].x, 0.f), fmaxf(accB[j][3] + accS[j][3] + pb[j].y, 0.f));
+        *reinterpret_cast<float2*>(orow + (size_t)(16 * m + g) * 16 + 8 * j + 2 * t) = lo;
+        *reinterpret_cast<float2*>(orow + (size_t)(16 * m + g + 8) * 16 + 8 * j + 2 * t) = hi;
+      }
+    }
+  }
+}
+
 }  // namespace
 
 struct PackedConv {        // device-side packed parameters of one (fused) layer
@@ -1212,6 +1337,7 @@ struct DetModel {
   std::map<std::string, PackedConv> conv;
   float* stem_w = nullptr;
   float* stem_b = nullptr;
+  float2* b0_bfrag = nullptr;    // b0's 1x1 weights as m16n8k8 tf32 B fragments [kstep][ntile][hi/lo][lane]
   uint2* stem_bfrag = nullptr;   // stem weights + bias row as m16n8k16 B fragments [kstep][ntile][piece][lane]
   std::vector<void*> allocs;
   int cap = 0;
@@ -1607,6 +1733,31 @@ int det_model_create(fr_ctx* ctx, const fr_weights* w) {
     }
   }
   dwsep("b0", 1);
+  {
+    // b0's 1x1 for b0_dwpw_mma_kernel: B fragment of lane 4g + t = W[n = 8j + g][channel 4t + 2ks (+1)], hi / lo tf32
+    const fr_tensor& pw = w->at("b0.pw.w");
+    ok = ok && pw.dims[0] == 16 && pw.dims[1] == 16;
+    std::vector<float2> frag(2 * 2 * 2 * 32);
+    for (int ks = 0; ok && ks < 2; ++ks)
+      for (int j = 0; j < 2; ++j)
+        for (int h = 0; h < 2; ++h)
+          for (int lane = 0; lane < 32; ++lane) {
+            const int g = lane >> 2, t = lane & 3, nn = 8 * j + g;
+            float v[2];
+            for (int i = 0; i < 2; ++i) {
+              const float wv = pw.data[(size_t)nn * 16 + 4 * t + 2 * ks + i];
+              const float hi = tf32_rna_host(wv);
+              v[i] = h == 0 ? hi : tf32_rna_host(wv - hi);
+            }
+            frag[((ks * 2 + j) * 2 + h) * 32 + lane] = make_float2(v[0], v[1]);
+          }
+    if (ok && cudaMalloc(&m->b0_bfrag, frag.size() * sizeof(float2)) == cudaSuccess) {
+      cudaMemcpy(m->b0_bfrag, frag.data(), frag.size() * sizeof(float2), cudaMemcpyHostToDevice);
+      m->allocs.push_back(m->b0_bfrag);
+    } else {
+      ok = false;
+    }
+  }
   for (int s = 0; s < 4; ++s)
     for (int b = 0; b < kStages[s][0]; ++b) dwsep("s" + std::to_string(s) + "." + std::to_string(b), b == 0 ? 2 : 1);
   for (int i = 0; i < 3; ++i) dense("lat" + std::to_string(i), 1);
@@ -1686,7 +1837,20 @@ int det_forward(fr_ctx* ctx, const __nv_bfloat16* d_in_chw, int n, HeadPtrs* hea
     io.in = in; io.out = out; io.hin = hin; io.stride = stride; io.relu = 1;
     return launch_layer(ctx, m->conv.at(name), io, n);
   };
-  FR_CHECK(dwsep("b0", m->a_stem, m->a_b0, 320, 1));
+  static const bool b0_tc = getenv("FR_SCRFD_B0_TCGEN05") != nullptr;   // A/B switch: b0 through sep_gemm_kernel
+  if (b0_tc) {
+    FR_CHECK(dwsep("b0", m->a_stem, m->a_b0, 320, 1));
+  } else {
+    const PackedConv& pc = m->conv.at("b0");
+    static const cudaError_t attr = cudaFuncSetAttribute(b0_dwpw_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                        B0_SMEM_BYTES);
+    FR_CUDA_OK(ctx, attr);
+    constexpr int HW = DET / 2;
+    b0_dwpw_mma_kernel<<<(unsigned)(n * (HW / B0_TW) * (HW / (B0_ROWS * B0_GROUPS))), 256, B0_SMEM_BYTES, ctx->stream>>>(
+        m->a_stem, m->a_b0, pc.dw_w, pc.dw_b, m->b0_bfrag, pc.bias, HW);
+    ctx->launches++;
+    FR_CUDA_OK(ctx, cudaGetLastError());
+  }
   const float* cur = m->a_b0;
   int hw = 320, bi = 0;
   const float* feats[3] = {nullptr, nullptr, nullptr};
