@@ -107,6 +107,30 @@ def test_k6_embed_aligned_batch_cosine_and_batch_invariance(ctx, rec_wdict):
                 assert orec.same_person(orec.compare_faces(emb[i], emb[j])) == orec.same_person(s_ref)
 
 
+def test_k6_stem_mma_matches_oracle_and_simt_stem(ctx, rec_wdict):
+    """The u8 hot path runs the stem on warp-level MMA (bf16 hi+lo weights, exact bf16 inputs); the fp32
+    CHW entry point keeps the CUDA-core stem.  Both must give the oracle's stem activation up to the
+    bf16 rounding of the output, and each other's up to one bf16 ulp plus the 16-bit weight split's
+    absolute error (27 products x 2^-17)."""
+    from oracle import recognizer as orec
+    rng = np.random.default_rng(23)
+    n = 5
+    crops = rng.integers(0, 256, (n, 112, 112, 3), dtype=np.uint8)
+    crops[0] = 0
+    crops[1] = 255
+    chw = np.stack([orec.preprocess(c) for c in crops])
+    _, taps = nets.iresnet50_forward(rec_wdict, torch.from_numpy(chw), return_taps=True)
+    ref = taps["stem"].numpy()
+    ctx.embed_aligned(crops)
+    got_mma = ctx.iresnet_tap(0, n, ref.shape[1:])
+    ctx.iresnet_forward(chw)
+    got_simt = ctx.iresnet_tap(0, n, ref.shape[1:])
+    assert _rel(got_mma, ref) < 6e-3 and _rel(got_simt, ref) < 6e-3
+    ulp = np.abs(got_simt) * 2.0 ** -7 + 2e-5
+    assert (np.abs(got_mma - got_simt) <= ulp).all()
+    assert (got_mma != got_simt).mean() < 0.02
+
+
 def test_k2_scrfd_heads_vs_oracle(ctx, det_wdict):
     """tcgen05 tf32 three-term split vs torch fp32: every activation tap and all 9 heads.  The
     bar is north_star's: boxes and landmarks within 1e-3 px after decode, i.e. the bbox / kps
