@@ -85,7 +85,7 @@ def main():
         p = os.path.join(HERE, f"r1_bench_n{n}.json")
         if os.path.exists(p):
             b = json.load(open(p))
-            A(f"* N={n} (`r1_bench_n{n}.json`, captured before the MMA stems / b0 kernel): {b['value']:.0f} faces/s, e2e {b['e2e']['value']:.0f}")
+            A(f"* N={n} (`r1_bench_n{n}.json`, torchrun, `--steps 10 --warmup 3`): {b['value']:.0f} faces/s, e2e {b['e2e']['value']:.0f}")
     A("")
     A("## Kernel shares of one step (`r1_launches_step.csv`: `ncu --metrics gpu__time_duration.sum`)\n")
     A(f"{len(step)} launches, {total:.0f} us summed.\n")
