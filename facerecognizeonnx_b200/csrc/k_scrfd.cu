@@ -228,18 +228,20 @@ __device__ __forceinline__ void ld_sum16(uint32_t taddr, uint32_t small_off, int
   for (int i = 0; i < 16; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) + __uint_as_float(s[i]));
 }
 
-// four partial accumulators at column offsets 0, nt, 2nt, 3nt: (big0 + big1) + (small0 + small1)
-__device__ __forceinline__ void ld_sum16x4(uint32_t taddr, uint32_t nt, uint32_t (&v)[16]) {
-  uint32_t b1[16], s0[16], s1[16];
+// five partial accumulators at column offsets 0 (hi*hi, even k), nt (hi*lo, even k), 2nt (hi*hi, odd k),
+// 3nt (hi*lo, odd k), 4nt (lo*hi): (big0 + big1) + ((small0 + small1) + small2)
+__device__ __forceinline__ void ld_sum16x5(uint32_t taddr, uint32_t nt, uint32_t (&v)[16]) {
+  uint32_t s0[16], b1[16], s1[16], s2[16];
   tmem_ld16_nowait(taddr, v);
-  tmem_ld16_nowait(taddr + nt, b1);
-  tmem_ld16_nowait(taddr + 2 * nt, s0);
+  tmem_ld16_nowait(taddr + nt, s0);
+  tmem_ld16_nowait(taddr + 2 * nt, b1);
   tmem_ld16_nowait(taddr + 3 * nt, s1);
+  tmem_ld16_nowait(taddr + 4 * nt, s2);
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
   for (int i = 0; i < 16; ++i)
     v[i] = __float_as_uint((__uint_as_float(v[i]) + __uint_as_float(b1[i])) +
-                           (__uint_as_float(s0[i]) + __uint_as_float(s1[i])));
+                           ((__uint_as_float(s0[i]) + __uint_as_float(s1[i])) + __uint_as_float(s2[i])));
 }
 
 // tcgen05.mma.kind::tf32 with a compile-time accumulate flag (folds to UPT / !UPT: no predicate
@@ -258,25 +260,26 @@ __device__ __forceinline__ void mma_tf32_c(uint32_t tmem_d, uint64_t adesc, uint
         : "memory");
 }
 
-// One tap (KS k-steps of K = 8) of the halo 3x3 kernel: 3 MMAs per k-step into small0 / small1 /
-// big[k & 1] (column offsets 2nt, 3nt, 0 / nt), fully unrolled, descriptor low words stepped by
-// immediates.  FIRST: the tile's first tap overwrites the accumulators.
+// One tap (KS k-steps of K = 8) of the halo 3x3 kernel: 2 MMAs per k-step.  The B tile of a stage is
+// [w_hi | w_lo] (2nt contiguous rows), so x_hi * [w_hi | w_lo] is ONE MMA of N = 2nt that reads the A
+// tile once for both products (the N <= 32 MMAs are bound by their shared-memory operand reads):
+// columns [0, nt) of its accumulator are hi*hi, [nt, 2nt) hi*lo; k steps alternate between two such
+// accumulators (offsets 0 and 2nt), x_lo * w_hi goes to a fifth region at 4nt.  Fully unrolled,
+// descriptor low words stepped by immediates.  FIRST: the tile's first tap overwrites the accumulators.
 template <int KS, bool FIRST>
 __device__ __forceinline__ void c3_issue_tap(uint32_t d_base, uint32_t nt, uint32_t desc_hi, uint32_t ahi, uint32_t alo,
-                                             uint32_t bhi, uint32_t blo, uint32_t idesc) {
+                                             uint32_t bhi, uint32_t idesc, uint32_t idesc2) {
   auto desc = [&](uint32_t lo) { return ((uint64_t)desc_hi << 32) | (uint64_t)lo; };
 #pragma unroll
   for (int k = 0; k < KS; ++k) {
     const uint32_t o = (uint32_t)(k * 2);
     if (FIRST && k == 0) {
-      mma_tf32_c<false>(d_base + 2 * nt, desc(alo + o), desc(bhi + o), idesc);
-      mma_tf32_c<false>(d_base + 3 * nt, desc(ahi + o), desc(blo + o), idesc);
-      mma_tf32_c<false>(d_base, desc(ahi + o), desc(bhi + o), idesc);
+      mma_tf32_c<false>(d_base + 4 * nt, desc(alo + o), desc(bhi + o), idesc);
+      mma_tf32_c<false>(d_base, desc(ahi + o), desc(bhi + o), idesc2);
     } else {
-      mma_tf32_c<true>(d_base + 2 * nt, desc(alo + o), desc(bhi + o), idesc);
-      mma_tf32_c<true>(d_base + 3 * nt, desc(ahi + o), desc(blo + o), idesc);
-      if (FIRST && k == 1) mma_tf32_c<false>(d_base + nt, desc(ahi + o), desc(bhi + o), idesc);
-      else mma_tf32_c<true>(d_base + (uint32_t)(k & 1) * nt, desc(ahi + o), desc(bhi + o), idesc);
+      mma_tf32_c<true>(d_base + 4 * nt, desc(alo + o), desc(bhi + o), idesc);
+      if (FIRST && k == 1) mma_tf32_c<false>(d_base + 2 * nt, desc(ahi + o), desc(bhi + o), idesc2);
+      else mma_tf32_c<true>(d_base + (uint32_t)(k & 1) * 2 * nt, desc(ahi + o), desc(bhi + o), idesc2);
     }
   }
 }
@@ -813,13 +816,13 @@ conv3_halo_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constan
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------- MMA issuer (warp-uniform)
-    const uint32_t idesc = make_idesc_tf32(TM, p.nt);
+    const uint32_t idesc = make_idesc_tf32(TM, p.nt), idesc2 = make_idesc_tf32(TM, 2 * p.nt);
     const uint64_t d0 = make_smem_desc(s_a);
     const uint32_t desc_hi = (uint32_t)(d0 >> 32);
     const uint32_t a_lo0 = (uint32_t)d0;
     const uint32_t b_lo0 = (uint32_t)make_smem_desc(s_b);
     const uint32_t a_step = (uint32_t)(2 * a_blk) >> 4, a_lo_off = (uint32_t)a_blk >> 4;
-    const uint32_t b_step = (uint32_t)(2 * b_bytes) >> 4, b_lo_off = (uint32_t)b_bytes >> 4;
+    const uint32_t b_step = (uint32_t)(2 * b_bytes) >> 4;   // a stage = w_hi tile + w_lo tile, contiguous
     const uint32_t nt = (uint32_t)p.nt;
     const int ksteps = p.kc >> 3;
     uint32_t tt = 0;
@@ -830,9 +833,9 @@ conv3_halo_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constan
       const uint32_t acc_phase = p.acc_stages == 2 ? ((tt >> 1) & 1u) : (tt & 1u);
       mbar_wait(&tempty[acc], acc_phase ^ 1u, p.err_flag);
       tc_fence_after();
-      // four independent accumulators (big0, big1, small0, small1): consecutive MMAs never target the
-      // same one, so the accumulate-dependency latency of these short (N <= 32) MMAs is hidden
-      const uint32_t d_big = tmem_base + acc * 4u * nt;
+      // three independent accumulator regions ([hh0 | hl0], [hh1 | hl1], lh): consecutive MMAs never
+      // target the same one, so the accumulate-dependency latency of these short MMAs is hidden
+      const uint32_t d_big = tmem_base + acc * 5u * nt;
       int kb = 0;
       for (int i = 0; i < p.n_in; ++i) {
         mbar_wait_spin(&full_a[sa], pa, p.err_flag);
@@ -852,13 +855,13 @@ conv3_halo_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constan
             }
             const uint32_t ahi = ahi0 + (uint32_t)((tap / 3) * p.tw2 + (tap % 3)) * 8u;   // 128-byte rows = 8 units
             const uint32_t bhi = b_lo0 + (uint32_t)bslot * b_step;
-            const uint32_t alo = ahi + a_lo_off, blo = bhi + b_lo_off;
+            const uint32_t alo = ahi + a_lo_off;                                  // w_lo follows w_hi in the stage
             if (ksteps == 4) {
-              if (tap == 0 && i == 0) c3_issue_tap<4, true>(d_big, nt, desc_hi, ahi, alo, bhi, blo, idesc);
-              else c3_issue_tap<4, false>(d_big, nt, desc_hi, ahi, alo, bhi, blo, idesc);
+              if (tap == 0 && i == 0) c3_issue_tap<4, true>(d_big, nt, desc_hi, ahi, alo, bhi, idesc, idesc2);
+              else c3_issue_tap<4, false>(d_big, nt, desc_hi, ahi, alo, bhi, idesc, idesc2);
             } else {
-              if (tap == 0 && i == 0) c3_issue_tap<2, true>(d_big, nt, desc_hi, ahi, alo, bhi, blo, idesc);
-              else c3_issue_tap<2, false>(d_big, nt, desc_hi, ahi, alo, bhi, blo, idesc);
+              if (tap == 0 && i == 0) c3_issue_tap<2, true>(d_big, nt, desc_hi, ahi, alo, bhi, idesc, idesc2);
+              else c3_issue_tap<2, false>(d_big, nt, desc_hi, ahi, alo, bhi, idesc, idesc2);
             }
             if (!p.b_resident) {
               tc_commit(&empty_b[sb_l]);
@@ -895,12 +898,12 @@ conv3_halo_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constan
       const uint32_t acc_phase = p.acc_stages == 2 ? ((tt >> 1) & 1u) : (tt & 1u);
       mbar_wait(&tfull[acc], acc_phase, p.err_flag);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + acc * 4u * (uint32_t)p.nt + ((uint32_t)(q * 32) << 16);
+      const uint32_t taddr = tmem_base + acc * 5u * (uint32_t)p.nt + ((uint32_t)(q * 32) << 16);
       const size_t pix = ((size_t)img * p.h + y) * p.w + x;
       if (p.epi == EPI_HEAD) {
         uint32_t v0[16], v1[16];
-        ld_sum16x4(taddr, (uint32_t)p.nt, v0);
-        ld_sum16x4(taddr + 16, (uint32_t)p.nt, v1);
+        ld_sum16x5(taddr, (uint32_t)p.nt, v0);
+        ld_sum16x5(taddr + 16, (uint32_t)p.nt, v1);
         if (valid) {
           float f[32];
 #pragma unroll
@@ -923,7 +926,7 @@ conv3_halo_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constan
 #pragma unroll 1
         for (int c0 = 0; c0 < p.nt; c0 += 16) {
           uint32_t v[16];
-          ld_sum16x4(taddr + c0, (uint32_t)p.nt, v);
+          ld_sum16x5(taddr + c0, (uint32_t)p.nt, v);
           if (valid) {
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
@@ -1644,7 +1647,7 @@ int launch_conv3_halo(fr_ctx* ctx, const PackedConv& pc, const float* in, float*
   if (used() + p.in_bytes <= budget) p.s_in++;
   if (used() + a2 <= budget) p.s_a++;
   if (used() + p.in_bytes <= budget) p.s_in++;
-  const int slot = 4 * pc.nt;
+  const int slot = 5 * pc.nt;   // hh0 | hl0 | hh1 | hl1 | lh
   p.acc_stages = 2 * slot <= 512 ? 2 : 1;
   int cols = 32;
   while (cols < p.acc_stages * slot) cols *= 2;
