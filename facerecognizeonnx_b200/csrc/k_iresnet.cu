@@ -107,6 +107,8 @@ bool tc_make_map_2d_u64(CUtensorMap* map, const void* base, uint64_t cols, uint6
 struct ConvLaunch {
   CUtensorMap a0, a1, b0, b1;
   CUtensorMap a_halo;      // halo mode: box = (a_rows / a_boxes) x 64
+  CUtensorMap b_small;     // halo mode: the weights with a 64-row box (N-split tail items)
+  bool has_b_small = false;
   tc::Params p;
   int bn = 64;
   int rows_per_img = 1;  // Hp*Wp of the output geometry
@@ -170,7 +172,22 @@ int tc_launch(fr_ctx* ctx, ConvLaunch& L, int m_rows) {
   const int grid = std::min(total, num_sms);
   if (L.halo) {
     const int supers = ceil_div(L.p.num_m_tiles, L.mt) * L.p.n_tiles_n;
-    const int hgrid = std::min(supers, num_sms);
+    // N-split of the last, partial wave (see tc::Params::tail_split)
+    L.p.tail_split = 1;
+    L.p.tail_first = supers;
+    int items = supers;
+    if (L.mt == 1 && !L.resb && L.has_b_small && env_flag("FR_TC_TAILSPLIT", 1)) {
+      const int tail = supers % num_sms;
+      int split = 1;
+      for (int s2 = 2; s2 <= 4 && L.bn / s2 >= 64; s2 *= 2)
+        if (tail > 0 && tail * s2 <= num_sms) split = s2;
+      if (split > 1) {
+        L.p.tail_split = split;
+        L.p.tail_first = supers - tail;
+        items = L.p.tail_first + tail * split;
+      }
+    }
+    const int hgrid = std::min(items, num_sms);
 #define FR_HALO_LAUNCH(BN_, MT_, RB_)                                                              \
   do {                                                                                             \
     static bool set_ = false;                                                                      \
@@ -181,7 +198,8 @@ int tc_launch(fr_ctx* ctx, ConvLaunch& L, int m_rows) {
     }                                                                                              \
     L.p.a_stages = std::min(env_flag("FR_TC_ASTAGES", 2), tc::HaloCfg<BN_, MT_, RB_>::pick_a_stages(L.p.a_rows)); \
     tc::halo_gemm_kernel<BN_, MT_, RB_><<<hgrid, tc::CONV_THREADS,                                  \
-        tc::HaloCfg<BN_, MT_, RB_>::smem_bytes(L.p.a_rows, L.p.a_stages), ctx->stream>>>(L.a_halo, L.b0, L.p);   \
+        tc::HaloCfg<BN_, MT_, RB_>::smem_bytes(L.p.a_rows, L.p.a_stages), ctx->stream>>>(            \
+        L.a_halo, L.b0, L.has_b_small ? L.b_small : L.b0, L.p);                                     \
   } while (0)
     if (L.bn == 64 && L.resb) { if (L.mt == 2) FR_HALO_LAUNCH(64, 2, true); else FR_HALO_LAUNCH(64, 1, true); }
     else if (L.bn == 64) { if (L.mt == 2) FR_HALO_LAUNCH(64, 2, false); else FR_HALO_LAUNCH(64, 1, false); }
@@ -826,6 +844,7 @@ static int rec_build_plan(fr_ctx* ctx, int cap) {
     c1.a1 = c1.a0;
     ok = ok && tc_setup_halo(c1, x.p, x.rows(cap), x.C, x.Wp);
     ok = ok && tc_make_map_2d(&c1.b0, bw.w1, (uint64_t)9 * bw.planes, bw.cin, bw.cin, c1.bn);
+    c1.has_b_small = ok && c1.halo && c1.bn > 64 && tc_make_map_2d(&c1.b_small, bw.w1, (uint64_t)9 * bw.planes, bw.cin, bw.cin, 64);
     c1.b1 = c1.b0;
     // ---- conv2: 3x3 stride s (+ fused 1x1 shortcut conv) + residual -> out
     ConvLaunch& c2 = m->conv2[i];
@@ -859,6 +878,7 @@ static int rec_build_plan(fr_ctx* ctx, int cap) {
       ok = ok && tc_setup_halo(c2, bb.h.p, bb.h.rows(cap), bb.h.C, bb.h.Wp);
     }
     ok = ok && tc_make_map_2d(&c2.b0, bw.w2, (uint64_t)9 * bw.planes, bw.planes, bw.planes, c2.bn);
+    c2.has_b_small = ok && c2.halo && c2.bn > 64 && tc_make_map_2d(&c2.b_small, bw.w2, (uint64_t)9 * bw.planes, bw.planes, bw.planes, 64);
     if (bw.stride != 2) c2.b1 = c2.b0;
     x = bb.out;
     xe = bb.out_even;
@@ -1096,6 +1116,7 @@ int rec_test_conv(fr_ctx* ctx, const float* x, int n, int cin, int h, int w, con
   L.a1 = L.a0;
   L.b1 = L.b0;
   if (ok && ksize == 3) ok = tc_setup_halo(L, d_x, rows, cin, Wp);
+  L.has_b_small = ok && L.halo && L.bn > 64 && tc_make_map_2d(&L.b_small, d_w, (uint64_t)ksize * ksize * cout, cin, cin, 64);
   int status = FR_OK;
   if (!ok) status = fr_fail(ctx, FR_ERR_CUDA, "fr_test_conv: tensor map encode failed");
   if (status == FR_OK) status = tc_launch(ctx, L, (int)rows);

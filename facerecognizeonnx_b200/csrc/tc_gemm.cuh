@@ -76,6 +76,12 @@ struct Params {
   int a_boxes;       // 1 or 2 TMA boxes per A block
   int base_off_mode; // 0: descriptor base_offset = 0; 1: base_offset = (addr >> 7) & 7
   int a_stages;      // halo mode: A blocks in flight
+  // halo mode, MT == 1, streamed weights: the last, partial wave of work items is split along N so that it
+  // takes a fraction of a tile time (900 tiles on 148 CTAs = 6.08 waves used to cost 7).  Items
+  // [0, tail_first) are whole tiles; from tail_first on every tile is tail_split items of BN / tail_split
+  // columns (tail_split in {1, 2, 4}, BN / tail_split >= 64).
+  int tail_first;
+  int tail_split;
   // exact division by multiply-shift: m / (Hp*Wp) = m * ceil(2^40 / (Hp*Wp)) >> 40 for m * Hp*Wp < 2^40,
   // r / Wp = umulhi(r, ceil(2^32 / Wp)) for r < Hp*Wp
   unsigned long long per_img_magic;
@@ -538,7 +544,7 @@ template <int BN, int MT, bool RESB> struct HaloCfg {
 template <int BN, int MT, bool RESB>
 __global__ void __launch_bounds__(CONV_THREADS, 1)
 halo_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                 const __grid_constant__ Params p) {
+                 const __grid_constant__ CUtensorMap tmBs, const __grid_constant__ Params p) {
   using C = HaloCfg<BN, MT, RESB>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
@@ -565,6 +571,7 @@ halo_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     prefetch_tmap(&tmA);
     prefetch_tmap(&tmB);
+    prefetch_tmap(&tmBs);
   }
   if (warp == 2) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
@@ -578,10 +585,25 @@ halo_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const uint32_t tmem_base = *tmem_slot;
 
   const int num_super = (p.num_m_tiles + MT - 1) / MT;
-  const int total_tiles = num_super * p.n_tiles_n;
+  const int tail_split = (MT == 1 && !RESB && p.tail_split > 1) ? p.tail_split : 1;
+  const int tail_first = tail_split > 1 ? p.tail_first : num_super * p.n_tiles_n;
+  const int total_tiles = tail_first + (num_super * p.n_tiles_n - tail_first) * tail_split;   // work items
   const int nkb = p.taps[0].nkb;
   const int wp = p.Wp;
   const int box_rows = p.a_rows / p.a_boxes;
+  // work item -> first output row, first output column, number of columns
+  auto item_coords = [&](int item, int& m0, int& n0, int& nlen) {
+    int tile = item, sub = 0;
+    nlen = BN;
+    if (item >= tail_first) {
+      const int j = item - tail_first;
+      tile = tail_first + j / tail_split;
+      sub = j % tail_split;
+      nlen = BN / tail_split;
+    }
+    m0 = (tile / p.n_tiles_n) * (BM * MT);
+    n0 = (tile % p.n_tiles_n) * BN + sub * nlen;
+  };
 
   if (warp == 0) {
     if (lane == 0) {
@@ -592,8 +614,8 @@ halo_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       int sa = 0, sb = 0;
       uint32_t pa = 0, pb = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int m0 = (tile / p.n_tiles_n) * (BM * MT);
-        const int n0 = (tile % p.n_tiles_n) * BN;
+        int m0, n0, nlen;
+        item_coords(tile, m0, n0, nlen);
         for (int kb = 0; kb < nkb; ++kb) {
           mbar_wait(&aempty[sa], pa ^ 1u, p.err_flag);
           mbar_expect_tx(&afull[sa], (uint32_t)a_bytes);
@@ -604,8 +626,14 @@ halo_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           if (!RESB) {
             for (int t = 0; t < 9; ++t) {
               mbar_wait(&bempty[sb], pb ^ 1u, p.err_flag);
-              mbar_expect_tx(&bfull[sb], C::B_TILE_BYTES);
-              tma_load_2d(sB + sb * C::B_TILE_BYTES, &tmB, &bfull[sb], kb * BK, t * p.cout + n0);
+              if (nlen == BN) {
+                mbar_expect_tx(&bfull[sb], C::B_TILE_BYTES);
+                tma_load_2d(sB + sb * C::B_TILE_BYTES, &tmB, &bfull[sb], kb * BK, t * p.cout + n0);
+              } else {   // a split tail item: nlen / 64 boxes of 64 weight rows
+                mbar_expect_tx(&bfull[sb], (uint32_t)(nlen * BK * 2));
+                for (int r = 0; r < nlen; r += 64)
+                  tma_load_2d(sB + sb * C::B_TILE_BYTES + r * BK * 2, &tmBs, &bfull[sb], kb * BK, t * p.cout + n0 + r);
+              }
               if (++sb == C::B_STAGES) { sb = 0; pb ^= 1u; }
             }
           }
@@ -615,7 +643,8 @@ halo_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   } else if (warp == 1) {
     // warp-uniform loop, one elected lane issues (see shift_gemm_kernel)
     {
-      constexpr uint32_t idesc = make_idesc(BM, BN);
+      constexpr uint32_t idesc_full = make_idesc(BM, BN);
+      const uint32_t idesc_tail = make_idesc(BM, BN / tail_split);
       const uint64_t d0 = make_smem_desc(sA);
       const uint32_t desc_hi = (uint32_t)(d0 >> 32);
       const uint32_t a_lo0 = (uint32_t)d0;
@@ -634,6 +663,7 @@ halo_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         mbar_wait(&tempty[acc], acc_phase ^ 1u, p.err_flag);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * (MT * BN);
+        const uint32_t idesc = tile >= tail_first ? idesc_tail : idesc_full;
         for (int kb = 0; kb < nkb; ++kb) {
           mbar_wait(&afull[sa], pa, p.err_flag);
           tc_fence_after();
@@ -682,8 +712,10 @@ halo_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int c_begin = ((warp - 2) >> 2) * CPS;
     uint32_t it = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
-      const int m0 = (tile / p.n_tiles_n) * (BM * MT);
-      const int n0 = (tile % p.n_tiles_n) * BN;
+      int m0, n0, nlen;
+      item_coords(tile, m0, n0, nlen);
+      const int cps = nlen == BN ? CPS : nlen / 32 / (EPI_WARPS / 4);      // this item's chunks per warp
+      const int cb = nlen == BN ? c_begin : ((warp - 2) >> 2) * cps;
       const uint32_t acc = C::ACC_STAGES == 2 ? (it & 1u) : 0u;
       const uint32_t acc_phase = C::ACC_STAGES == 2 ? ((it >> 1) & 1u) : (it & 1u);
       mbar_wait(&tfull[acc], acc_phase, p.err_flag);
@@ -691,7 +723,7 @@ halo_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll 1
       for (int mt = 0; mt < MT; ++mt) {
         const uint32_t taddr0 = tmem_base + acc * (MT * BN) + mt * BN + ((uint32_t)(q * 32) << 16);
-        epilogue_tile<BN>(p, taddr0, m0 + mt * BM + row, n0, 0, c_begin, c_begin + CPS);
+        epilogue_tile<BN>(p, taddr0, m0 + mt * BM + row, n0, 0, cb, cb + cps);
       }
       tc_fence_before();
       __syncwarp();
