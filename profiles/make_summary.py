@@ -99,7 +99,7 @@ def main():
     dsum = sum(k["dram__bytes_read.sum"] + k["dram__bytes_write.sum"] for k in tc)
     A(f"Sum over the {len(tc)} launches of a step: {tsum:.0f} us, {dsum / 1e9:.2f} GB DRAM traffic "
       f"({dsum / len(tc) / 1e6:.0f} MB per launch).  Launches 16-41 are the 26 identical 256-channel 14x14 convs "
-      "(conv1 / conv2 alternate); these kernels are unchanged since this capture.\n")
+      "(conv1 / conv2 alternate).\n")
     A("| # | kernel | us | DRAM read MB | DRAM write MB | tensor pipe active % | L2 hit % |\n|---|---|---|---|---|---|---|")
     tp = next((m for m in tc[0] if "pipe_tensor" in m), None)
     l2 = next((m for m in tc[0] if "hit_rate" in m), None)
