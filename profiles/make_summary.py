@@ -5,7 +5,7 @@
 Inputs (all produced under gpurun on one B200, ncu passes only after the same command exited 0 without ncu):
   r1_bench.json                     python bench.py                                    (one JSON line)
   r1_bench_reference.json           python bench.py --impl reference
-  r1_bench_n2.json / _n4.json       torchrun ... bench.py --gpus N
+  r1_bench_n2.json / _n4 / _n8      torchrun ... bench.py --gpus N
   r1_launches_step.csv              ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv
                                     python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-gallery
   r1_tc_family_ncu_metrics.csv      ncu --metrics <dram, tensor pipe, L2 hit> -k regex:halo_gemm|shift_gemm (one step)
@@ -81,11 +81,13 @@ def main():
           f"`--impl reference` (all {ref['cpu_baseline']['cores']} host threads): {ref['value']:.1f} faces/s (`r1_bench_reference.json`)")
     A(f"* stage times (ms / step): {bench['detail']['stage_ms_per_step']}")
     A(f"* clocks during the timed region: {bench['clocks']}\n")
-    for n in (2, 4):
+    for n in (2, 4, 8):
         p = os.path.join(HERE, f"r1_bench_n{n}.json")
         if os.path.exists(p):
             b = json.load(open(p))
-            A(f"* N={n} (`r1_bench_n{n}.json`, torchrun, `--steps 10 --warmup 3`): {b['value']:.0f} faces/s, e2e {b['e2e']['value']:.0f}")
+            gal = b.get("gallery_1toN") or {}
+            A(f"* N={n} (`r1_bench_n{n}.json`, torchrun, `--steps 10 --warmup 3`): {b['value']:.0f} faces/s, e2e {b['e2e']['value']:.0f}"
+              + (f"; 1:N {gal['value']:.0f} queries/s over {gal['gallery_rows_total'] / 1e6:.2f} M rows (row-sharded, NCCL all-gather + merge)" if gal else ""))
     A("")
     A("## Kernel shares of one step (`r1_launches_step.csv`: `ncu --metrics gpu__time_duration.sum`)\n")
     A(f"{len(step)} launches, {total:.0f} us summed.\n")
