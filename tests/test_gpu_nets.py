@@ -131,6 +131,18 @@ def test_k6_stem_mma_matches_oracle_and_simt_stem(ctx, rec_wdict):
     assert (got_mma != got_simt).mean() < 0.02
 
 
+def test_k6_embeddings_do_not_depend_on_batch_size_or_tail_split(ctx):
+    """The conv kernel splits the last partial wave of tiles along N (tc::Params::tail_split); which tiles
+    are split depends on the batch size.  A face's embedding must be bit-identical whatever batch it is in
+    (each output element accumulates over K in the same order in a whole tile and in an N slice)."""
+    rng = np.random.default_rng(24)
+    crops = rng.integers(0, 256, (300, 112, 112, 3), dtype=np.uint8)
+    full = ctx.embed_aligned(crops)
+    for lo, hi in ((0, 37), (37, 187), (187, 300), (5, 6)):
+        part = ctx.embed_aligned(crops[lo:hi])
+        assert np.array_equal(part, full[lo:hi]), (lo, hi)
+
+
 def test_k2_scrfd_heads_vs_oracle(ctx, det_wdict):
     """tcgen05 tf32 three-term split vs torch fp32: every activation tap and all 9 heads.  The
     bar is north_star's: boxes and landmarks within 1e-3 px after decode, i.e. the bbox / kps
