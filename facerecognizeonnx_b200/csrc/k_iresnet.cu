@@ -245,6 +245,7 @@ struct BlockW {       // device weights of one IBasicBlock
   bf16* w1 = nullptr;     // [9][planes][cin]   (bn1 scale folded)
   float* b1 = nullptr;    // [9 classes][planes]
   float* prelu = nullptr; // [planes]
+  std::vector<float> prelu_h;   // host copy (goes into the kernel parameters)
   bf16* w2 = nullptr;     // [9][planes][planes]
   bf16* wds = nullptr;    // [planes][cin] or null
   float* b2 = nullptr;    // [planes] (conv2 bias + ds bias)
@@ -714,6 +715,7 @@ int rec_model_create(fr_ctx* ctx, const fr_weights* w) {
       bw.w1 = dev_upload(ctx, m.get(), pack_conv3(w1, &sc));
       bw.b1 = dev_upload(ctx, m.get(), border_bias(w1, w->at(p + ".conv1.b").data, sh));
       bw.prelu = dev_upload(ctx, m.get(), w->at(p + ".prelu").data);
+      bw.prelu_h = w->at(p + ".prelu").data;
       bw.w2 = dev_upload(ctx, m.get(), pack_conv3(w->at(p + ".conv2.w"), nullptr));
       std::vector<float> b2 = w->at(p + ".conv2.b").data;
       if (b == 0) {
@@ -831,6 +833,10 @@ static int rec_build_plan(fr_ctx* ctx, int cap) {
     c1.p.cout = bw.planes;
     c1.p.bias = bw.b1; c1.p.bias_classes = 9;
     c1.p.prelu = bw.prelu;
+    if (bw.prelu_h.size() <= 512 && env_flag("FR_TC_PRELU_PARAMS", 1)) {
+      memcpy(c1.p.prelu_c, bw.prelu_h.data(), bw.prelu_h.size() * sizeof(float));
+      c1.p.prelu_in_params = 1;
+    }
     c1.p.out = bb.h.p;
     c1.p.err_flag = m->err_flag;
     c1.rows_per_img = x.Hp * x.Wp;

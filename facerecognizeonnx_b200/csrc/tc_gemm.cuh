@@ -86,6 +86,10 @@ struct Params {
   // r / Wp = umulhi(r, ceil(2^32 / Wp)) for r < Hp*Wp
   unsigned long long per_img_magic;
   uint32_t wp_magic;
+  // PReLU slopes in the kernel-parameter (constant) bank: every lane of the epilogue reads the same 32
+  // slopes per chunk, so they come through the constant cache instead of 8 L1 loads per thread and chunk
+  int prelu_in_params;
+  __align__(16) float prelu_c[512];
 };
 
 template <int BN> struct Cfg {
@@ -294,8 +298,13 @@ __device__ __forceinline__ void epilogue_tile(const Params& p, uint32_t taddr0, 
 #pragma unroll
       for (int i = 0; i < 8; ++i) b4[i] = __ldg(reinterpret_cast<const float4*>(bias + c * 32 + i * 4));
       if (p.prelu) {
+        if (p.prelu_in_params) {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) s4[i] = __ldg(reinterpret_cast<const float4*>(p.prelu + n0 + c * 32 + i * 4));
+          for (int i = 0; i < 8; ++i) s4[i] = *reinterpret_cast<const float4*>(&p.prelu_c[n0 + c * 32 + i * 4]);
+        } else {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) s4[i] = __ldg(reinterpret_cast<const float4*>(p.prelu + n0 + c * 32 + i * 4));
+        }
       }
       if (has_res) {
         const uint4* r = reinterpret_cast<const uint4*>(p.residual + (size_t)m * p.cout + n0 + c * 32);
