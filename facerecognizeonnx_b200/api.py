@@ -51,6 +51,8 @@ class _Shared:
     rec_w: Optional[capi.Weights] = None
     device: int = 0
     seed: int = 0
+    # random-init weights when the model file is absent are an explicit opt-in (as in host/face_api.cpp)
+    allow_random_init: bool = os.environ.get("FR_ALLOW_RANDOM_INIT", "0") not in ("", "0")
 
     @classmethod
     def rebuild(cls):
@@ -66,8 +68,13 @@ def _load(model: int, path: str, what: str) -> Optional[capi.Weights]:
         except capi.FrError as e:
             print(f"Error loading {what} model: {e}", file=sys.stderr)
             return None
-    print(f"Note: {path} not found, using seeded random-init {what} weights of the same architecture",
-          file=sys.stderr)
+    if not _Shared.allow_random_init:
+        # the reference returns false here (src/face_detector.cpp:86-89); so do we
+        print(f"Error loading {what} model: cannot open {path} "
+              "(set FR_ALLOW_RANDOM_INIT=1 to run with seeded random-init weights)", file=sys.stderr)
+        return None
+    print(f"WARNING: {path} not found; FR_ALLOW_RANDOM_INIT=1 -> seeded random-init {what} weights of the "
+          "same architecture (results are meaningless for real faces)", file=sys.stderr)
     return capi.Weights(model, None, _Shared.seed)
 
 

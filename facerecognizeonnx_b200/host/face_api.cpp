@@ -31,20 +31,28 @@ struct Session {
 };
 
 // loadModel (src/face_detector.cpp:20-90): file present -> parse it (failure => false, like the
-// Ort::Exception branch); file absent -> seeded random-init weights of the same architecture
-// (BASELINE.json north_star) with a notice on cerr, returns true.
+// Ort::Exception branch).  File absent -> false with the message on cerr, exactly like the
+// reference (:86-89; main.cpp then exits with -1): a mistyped path must never produce boxes and
+// same-person decisions from random networks.  Seeded random-init weights of the same
+// architecture (BASELINE.json north_star: benchmarks / tests without model files) are an
+// explicit opt-in: FR_ALLOW_RANDOM_INIT=1 in the environment.
 bool load(Session& s, int model, const std::string& path, const char* what) {
   s.~Session();
   new (&s) Session();
   const bool have = file_exists(path);
+  if (!have && env_int("FR_ALLOW_RANDOM_INIT", 0) == 0) {
+    std::cerr << "Error loading " << what << " model: cannot open " << path
+              << " (set FR_ALLOW_RANDOM_INIT=1 to run with seeded random-init weights)" << std::endl;
+    return false;
+  }
   int st = fr_weights_create(&s.w, model, have ? path.c_str() : nullptr, (uint64_t)env_int("FR_SEED", 1));
   if (st != FR_OK) {
     std::cerr << "Error loading " << what << " model: " << fr_weights_last_error() << std::endl;
     return false;
   }
   if (!have)
-    std::cerr << "Note: " << path << " not found; using seeded random-init " << what
-              << " weights of the same architecture" << std::endl;
+    std::cerr << "WARNING: " << path << " not found; FR_ALLOW_RANDOM_INIT=1 -> seeded random-init " << what
+              << " weights of the same architecture (results are meaningless for real faces)" << std::endl;
   st = fr_create(&s.ctx, env_int("FR_DEVICE", 0), model == FR_MODEL_DET ? s.w : nullptr,
                  model == FR_MODEL_REC ? s.w : nullptr);
   if (st != FR_OK) {

@@ -21,9 +21,14 @@ def _build_host():
     subprocess.run(["make", "-C", os.path.join(PKG, "host")], check=True, capture_output=True)
 
 
-def _run(args, cwd):
+def _run(args, cwd, random_init=True):
+    """random_init: the tests have no model files, so they opt in to seeded random-init weights
+    (FR_ALLOW_RANDOM_INIT=1); without the opt-in a missing model file fails like the reference."""
     env = dict(os.environ)
     env["LD_LIBRARY_PATH"] = PKG + ":" + env.get("LD_LIBRARY_PATH", "")
+    env.pop("FR_ALLOW_RANDOM_INIT", None)
+    if random_init:
+        env["FR_ALLOW_RANDOM_INIT"] = "1"
     return subprocess.run([CLI] + args, cwd=cwd, env=env, capture_output=True, text=True, timeout=300)
 
 
@@ -51,6 +56,47 @@ def test_cli_builds_and_fails_like_the_reference_without_gpu(tmp_path):
     assert r.returncode == 255                      # main returns -1 when a model cannot be loaded
     assert "无法加载人脸检测模型" in r.stderr           # src/main.cpp:275
     assert "所有模型加载成功" not in r.stdout
+
+
+def test_cli_missing_model_file_is_an_error_without_the_opt_in(tmp_path):
+    """a missing / mistyped model path must fail like the reference (loadModel -> false,
+    main -> -1, src/main.cpp:274-277), never fall back to random networks silently.  Holds with or
+    without a GPU: the file check comes first."""
+    _build_host()
+    r = _run(["detect", "x.ppm"], str(tmp_path), random_init=False)
+    assert r.returncode == 255
+    assert "cannot open models/det_500m.onnx" in r.stderr and "无法加载人脸检测模型" in r.stderr
+    assert "检测到" not in r.stdout
+
+
+@pytest.mark.gpu
+def test_cli_loads_real_onnx_files_from_models_dir(tmp_path, capi):
+    """models/det_500m.onnx + models/w600k_r50.onnx present (raw, unfolded synthetic exports): the CLI
+    loads them (no opt-in), and `compare` prints the similarity the C ABI gives with the same files."""
+    import onnx_emit
+    from oracle import weights as ow
+    _build_host()
+    os.makedirs(tmp_path / "models")
+    pd, pr = str(tmp_path / "models" / "det_500m.onnx"), str(tmp_path / "models" / "w600k_r50.onnx")
+    onnx_emit.emit_det_full(ow.trained_like_det(5), pd, raw=True, bbox_scales=(0.9, 1.7, 3.1))
+    onnx_emit.emit_rec_full(ow.trained_like_rec(5), pr, raw=True)
+    rng = np.random.default_rng(8)
+    a = rng.integers(0, 256, (640, 640, 3), dtype=np.uint8)
+    b = rng.integers(0, 256, (640, 640, 3), dtype=np.uint8)
+    pa, pb = str(tmp_path / "a.ppm"), str(tmp_path / "b.ppm")
+    _write_ppm(pa, a)
+    _write_ppm(pb, b)
+    r = _run(["compare", pa, pb], str(tmp_path), random_init=False)
+    assert r.returncode == 0, r.stderr
+    assert "所有模型加载成功" in r.stdout and "random-init" not in r.stderr
+    c = capi.Context(0, capi.Weights(capi.FR_MODEL_DET, pd), capi.Weights(capi.FR_MODEL_REC, pr))
+    fa, fb = c.detect(a, cap=1024), c.detect(b, cap=1024)
+    assert len(fa) and len(fb)
+    (ea,), _ = c.embed_faces([a], fa[:1], [0])
+    (eb,), _ = c.embed_faces([b], fb[:1], [0])
+    sim_cli = float(re.search(r"相似度: ([0-9.]+)", r.stdout).group(1))
+    assert abs(sim_cli - capi.compare(ea, eb)) < 2e-6
+    c.close()
 
 
 @pytest.mark.gpu

@@ -4,6 +4,7 @@ import pytest
 import torch
 
 from conftest import SEED, faces_from_landmarks, synth_landmarks
+import parity
 from oracle import detector as odet
 from oracle import recognizer as orec
 
@@ -14,27 +15,29 @@ def _frames(rng, n, h=640, w=640):
     return [rng.integers(0, 256, (h, w, 3), dtype=np.uint8) for _ in range(n)]
 
 
-def _match_dets(got, exp, thr):
-    """Kept detections must agree except for candidates whose score is within 1e-4 of the
-    threshold (fp32 summation order differs between the CUDA cores and oneDNN)."""
-    e = {(f.x, f.y, f.w, f.h): f for f in exp}
-    g = {(int(r["x"]), int(r["y"]), int(r["w"]), int(r["h"])): r for r in got}
-    common = set(e) & set(g)
-    assert len(common) >= 0.9 * max(len(e), 1), (len(common), len(e), len(g))
-    for k in common:
-        assert abs(float(g[k]["score"]) - float(e[k].score)) < 1e-4
-        assert np.abs(np.array(g[k]["lm"]) - e[k].landmarks.reshape(10)).max() < 1e-3
-
-
 def test_detect_end_to_end_vs_oracle(ctx, det_wdict):
+    """fr_detect vs the oracle's detect (src/face_detector.cpp:139-222).  Every difference between the two
+    lists must be EXPLAINED by a boundary event of the reference's arithmetic (tests/parity.py); and the
+    list must be bit-identical to the oracle's decode + postprocess + NMS run on the GPU's own heads."""
     rng = np.random.default_rng(41)
     det = odet.FaceDetector(det_wdict)
-    for im in _frames(rng, 2) + _frames(rng, 1, 480, 640):
-        got = ctx.detect(im, 0.5, 0.4, cap=1024)
-        exp = det.detect(im, 0.5, 0.4)
-        _match_dets(got, exp, 0.5)
-        sc = got["score"]
-        assert np.all(sc[:-1] >= sc[1:])   # sorted by score, descending (nms() output order)
+    for thr in (0.5, 0.02):          # 0.02: hundreds of candidates per frame reach NMS with the seeded weights
+        for im in _frames(rng, 2) + _frames(rng, 1, 480, 640):
+            got = ctx.detect(im, thr, 0.4, cap=4096)
+            chw, scale = odet.preprocess(im)
+            heads = det.run_network(chw)
+            st = parity.assert_detections_explained(got, heads, scale, thr, 0.4)
+            assert st["common"] >= 1 or thr == 0.5
+            # same frame through the stage hooks: K1 (bit-exact) -> K2 -> oracle decode/NMS on the GPU heads
+            g_chw, g_scale = ctx.det_preprocess([im])
+            assert np.array_equal(g_chw[0], chw) and g_scale[0] == scale
+            g_heads = [h[0] for h in ctx.scrfd_forward(g_chw)]
+            exp = odet.postprocess(odet.scrfd_decode(g_heads), scale, thr, 0.4)
+            assert len(exp) == len(got)
+            for r, e in zip(got, exp):
+                assert (int(r["x"]), int(r["y"]), int(r["w"]), int(r["h"])) == (e.x, e.y, e.w, e.h)
+                assert float(r["score"]) == float(e.score)
+                assert np.array_equal(np.asarray(r["lm"], np.float32), e.landmarks.reshape(10))
 
 
 def test_detect_batch_equals_single(ctx):
@@ -60,6 +63,36 @@ def test_extract_feature_end_to_end_vs_oracle(ctx, capi, rec_wdict):
         assert float((emb[i] * ref).sum()) >= 0.999
 
 
+def test_extract_feature_simple_vs_oracle(ctx, rec_wdict):
+    """fr_embed_simple vs FaceRecognizer::extractFeatureSimple (src/face_recognizer.cpp:152-234): the
+    cv::resize(image -> 112x112) crop is bit-exact, the embedding within cosine 0.999, and the 0.6
+    decision on pairs agrees (src/main.cpp:169-178)."""
+    import cv2
+    rng = np.random.default_rng(46)
+    rec = orec.FaceRecognizer(rec_wdict)
+    embs, refs = [], []
+    for shape in ((480, 640, 3), (112, 112, 3), (37, 53, 3), (1000, 333, 3), (224, 224, 3)):
+        img = rng.integers(0, 256, shape, dtype=np.uint8)
+        if shape[0] > 200:
+            img = cv2.GaussianBlur(img, (0, 0), 2.0)
+        assert np.array_equal(ctx.resize_linear(img, 112, 112), cv2.resize(img, (112, 112)))
+        e = ctx.embed_simple(img)
+        r = rec.extract_feature_simple(img)
+        assert abs(float(np.linalg.norm(e)) - 1.0) < 1e-5
+        assert float((e * r).sum()) >= 0.999
+        # the strided view a cv::Mat ROI would be (step != cols*3)
+        big = np.zeros((shape[0] + 6, shape[1] + 10, 3), np.uint8)
+        big[3:3 + shape[0], 5:5 + shape[1]] = img
+        assert np.array_equal(ctx.embed_simple(big[3:3 + shape[0], 5:5 + shape[1]]), e)
+        embs.append(e)
+        refs.append(r)
+    for i in range(len(embs)):
+        for j in range(i + 1, len(embs)):
+            s_ref = orec.compare_faces(refs[i], refs[j])
+            if abs(float(s_ref) - 0.6) > 2e-3:
+                assert orec.same_person(orec.compare_faces(embs[i], embs[j])) == orec.same_person(s_ref)
+
+
 def test_pipeline_matches_staged_calls(ctx, capi):
     rng = np.random.default_rng(44)
     ims = _frames(rng, 4)
@@ -83,7 +116,11 @@ def test_api_mirror_compare_mode(capi, tmp_path):
     api._Shared.seed = SEED
     det, rec = api.FaceDetector(), api.FaceRecognizer()
     assert det.detect(np.zeros((10, 10, 3), np.uint8)) == []          # "Model not loaded!"
-    assert det.loadModel(str(tmp_path / "det_500m.onnx"))               # absent -> random init, True
+    assert not det.loadModel(str(tmp_path / "det_500m.onnx"))           # absent -> false, like the reference
+    assert not rec.loadModel(str(tmp_path / "w600k_r50.onnx"))          # (src/face_detector.cpp:86-89)
+    assert det.detect(np.zeros((10, 10, 3), np.uint8)) == []            # still "Model not loaded!"
+    api._Shared.allow_random_init = True                                # explicit opt-in (FR_ALLOW_RANDOM_INIT=1)
+    assert det.loadModel(str(tmp_path / "det_500m.onnx"))
     assert rec.loadModel(str(tmp_path / "w600k_r50.onnx"))
     assert det.detect(np.zeros((0, 0, 3), np.uint8)) == []             # "Input image is empty!"
     rng = np.random.default_rng(45)
