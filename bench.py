@@ -66,12 +66,15 @@ def _env_int(name, default):
         return default
 
 
+# fr_face / FaceBox record (include/fr_capi.h); restated here so the CPU arm never touches the product package
+FACE_DTYPE = np.dtype([("x", "<i4"), ("y", "<i4"), ("w", "<i4"), ("h", "<i4"), ("score", "<f4"), ("lm", "<f4", (10,))])
+
+
 def synth_pad_faces(rng, n_img, k, size=FRAME):
     """Seeded synthetic landmark sets (template x random similarity), SURVEY 8d config 4."""
-    from facerecognizeonnx_b200 import capi
     tmpl = np.array([[38.2946, 51.6963], [73.5318, 51.5014], [56.0252, 71.7366],
                      [41.5493, 92.3655], [70.7299, 92.2041]], np.float32)
-    f = np.zeros((n_img, k), capi.FACE_DTYPE)
+    f = np.zeros((n_img, k), FACE_DTYPE)
     for i in range(n_img):
         for j in range(k):
             s = rng.uniform(0.5, 4.0)
@@ -155,14 +158,14 @@ class CpuPipeline:
         import cv2
         import torch
 
-        from facerecognizeonnx_b200 import capi   # host-only weight generator (no GPU work)
         from oracle import detector as odet
         from oracle import recognizer as orec
+        from oracle import weights as ow      # NumPy twin of the seeded init: no product library on this arm
         torch.set_num_threads(threads)
         cv2.setNumThreads(threads)
-        self.odet = odet
-        self.det = odet.FaceDetector(capi.Weights(capi.FR_MODEL_DET, None, seed).to_dict())
-        self.rec = orec.FaceRecognizer(capi.Weights(capi.FR_MODEL_REC, None, seed).to_dict())
+        self.odet, self.orec = odet, orec
+        self.det = odet.FaceDetector(ow.seeded(ow.MODEL_DET, seed))
+        self.rec = orec.FaceRecognizer(ow.seeded(ow.MODEL_REC, seed))
         # untimed warm-up of both graphs
         self.det.detect(np.zeros((FRAME, FRAME, 3), np.uint8))
         self.rec.embed_chw(np.zeros((1, 3, 112, 112), np.float32))
@@ -187,6 +190,29 @@ class CpuPipeline:
                 emb = self.rec.extract_feature(fr, fb)
                 faces_done += int(emb.size == 512)
         return faces_done, time.perf_counter() - t0
+
+    def compare_latency(self, reps: int = 3):
+        """BASELINE.json configs[0]: compare mode on two images, batch 1 (src/main.cpp:67-123):
+        detect x2, extractFeature of the first face x2, compareFaces.  Seconds per compare."""
+        rng = np.random.default_rng(7)
+        a, b = (rng.integers(0, 256, (FRAME, FRAME, 3), dtype=np.uint8) for _ in range(2))
+        pad = synth_pad_faces(np.random.default_rng(8), 2, 1)
+        ts = []
+        for _ in range(reps):
+            t0 = time.perf_counter()
+            embs = []
+            for i, im in enumerate((a, b)):
+                dets = self.det.detect(im, 0.5, 0.4)
+                if dets:
+                    fb = dets[0]
+                else:
+                    r = pad[i, 0]
+                    fb = self.odet.FaceBox(int(r["x"]), int(r["y"]), int(r["w"]), int(r["h"]), 0.9,
+                                           np.array(r["lm"], np.float32).reshape(5, 2))
+                embs.append(self.rec.extract_feature(im, fb))
+            self.orec.compare_faces(embs[0], embs[1])
+            ts.append(time.perf_counter() - t0)
+        return min(ts)
 
 
 def run_reference(args, rank, world):
@@ -368,6 +394,8 @@ def run_gpu(args, rank, world, local_rank):
              "k5_align_gbs_lower_bound": k5_bytes / (stage_ms["align"] / 1e3) / 1e9 if stage_ms["align"] > 0 else None,
              "hbm_peak_gbs": peaks["hbm_gbs"], "n_det_per_frame": n_det_mean, "valid_frac": valid_frac}
 
+    extra["configs"] = bench_configs_1_to_3(ctx, capi, torch, dev, stream, dev_frames[0], pad_np, rank)
+
     # ---- secondary metric: 1:N cosine search (BASELINE.json configs[4]), row-sharded gallery
     gallery = None
     if not args.no_gallery:
@@ -376,7 +404,9 @@ def run_gpu(args, rank, world, local_rank):
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         frames_sample = 48
-        f, t = CpuPipeline(4).run(frames_sample, 100)
+        cpu = CpuPipeline(4)
+        f, t = cpu.run(frames_sample, 100)
+        extra["configs"]["config1_compare_batch1"]["cpu_port_ms_per_compare_4threads"] = 1e3 * cpu.compare_latency()
         cpu_baseline = {"value": f / t, "unit": UNIT, "cores": 4, "kind": "port",
                         "host_cores_available": len(os.sched_getaffinity(0)),
                         "sample": f"{frames_sample} frames x (det + 8 faces align+embed) = {f} faces in {t:.1f} s; "
@@ -395,6 +425,78 @@ def run_gpu(args, rank, world, local_rank):
     ctx.close()
     if world > 1:
         dist.destroy_process_group()
+
+
+def bench_configs_1_to_3(ctx, capi, torch, dev, stream, frames_dev, pad_np, rank):
+    """BASELINE.json configs[0..2], each measured on its own (per GPU, this rank):
+    (1) compare mode, batch 1, through the C ABI with HOST buffers: fr_detect x2 + fr_embed x2 +
+        fr_compare (src/main.cpp:67-123) -- wall-clock latency per compare, median of 20;
+    (2) SCRFD det only, batch 64 device-resident frames (fr_detect_batch, K1+K2+K3/K4), CUDA events;
+    (3) ArcFace embed only, batch 1024 aligned crops device-resident (fr_embed_aligned_batch), CUDA events."""
+    out = {}
+    rng = np.random.default_rng(7 + rank)
+    a, b = (rng.integers(0, 256, (FRAME, FRAME, 3), dtype=np.uint8) for _ in range(2))
+    pad1 = synth_pad_faces(np.random.default_rng(8), 2, 1)
+
+    def compare_once():
+        embs = []
+        for i, im in enumerate((a, b)):
+            dets = ctx.detect(im, 0.5, 0.4, cap=64)
+            face = dets[:1] if len(dets) else pad1[i]
+            e, v = ctx.embed_faces([im], face, [0])
+            embs.append(e[0])
+        return capi.compare(embs[0], embs[1])
+
+    for _ in range(3):
+        compare_once()
+    ts = []
+    for _ in range(20):
+        t0 = time.perf_counter()
+        compare_once()
+        ts.append(time.perf_counter() - t0)
+    out["config1_compare_batch1"] = {"ms_per_compare_median": 1e3 * statistics.median(ts), "ms_per_compare_min": 1e3 * min(ts),
+                                     "what": "2 x (fr_detect + fr_embed) + fr_compare, host buffers, H2D/D2H inside",
+                                     "compares_per_s": 1.0 / statistics.median(ts)}
+    # (2) det only, batch 64
+    n_img = FRAMES_PER_STEP
+    fb = FRAME * FRAME * 3
+    ptrs = [frames_dev.data_ptr() + j * fb for j in range(n_img)]
+    cap = 64
+    d_faces = torch.empty((n_img * cap, 60), dtype=torch.uint8, device=dev)
+    d_n = torch.empty(n_img, dtype=torch.int32, device=dev)
+    import ctypes as C
+    from facerecognizeonnx_b200.capi import _ImageBatch, FR_MEM_DEVICE, lib
+    ib = _ImageBatch([(p, FRAME, FRAME, FRAME * 3) for p in ptrs], FR_MEM_DEVICE)
+
+    def det_once():
+        ctx._check(lib().fr_detect_batch(ctx.h, ib.ptrs, ib.rows, ib.cols, ib.step, n_img, FR_MEM_DEVICE, 0.5, 0.4,
+                                         d_faces.data_ptr(), cap, d_n.data_ptr()))
+
+    def timed(fn, iters):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(iters):
+            fn()
+        e1.record(stream)
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / iters
+
+    ms2 = timed(det_once, 20)
+    out["config2_det_only_batch64"] = {"ms_per_batch": ms2, "frames_per_s": n_img / (ms2 / 1e3),
+                                       "what": "fr_detect_batch, 64 device-resident 640x640 frames, thr 0.5 / 0.4"}
+    # (3) embed only, batch 1024
+    n3 = 1024
+    g = torch.Generator(device="cpu").manual_seed(1)
+    crops = torch.randint(0, 256, (n3, 112, 112, 3), dtype=torch.uint8, generator=g).to(dev)
+    emb = torch.empty((n3, 512), dtype=torch.float32, device=dev)
+    ms3 = timed(lambda: ctx.embed_aligned_dev(crops.data_ptr(), n3, emb.data_ptr()), 10)
+    out["config3_embed_only_batch1024"] = {"ms_per_batch": ms3, "faces_per_s": n3 / (ms3 / 1e3),
+                                           "tflops": n3 * GFLOP_PER_FACE_TOTAL / ms3,
+                                           "what": "fr_embed_aligned_batch, 1024 device-resident 112x112 crops, bf16"}
+    return out
 
 
 def bench_gallery(ctx, capi, torch, dist, dev, rank, world, stream, peaks, rows_per_gpu=1_250_000, nq=4096, k=10,

@@ -6,7 +6,7 @@ import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from facerecognizeonnx_b200 import capi
 
-L = capi.lib()
+L = C.CDLL(os.path.join(os.path.dirname(capi.LIB_PATH), "libfr_dev.so"))   # developer micro-benchmarks live outside the product library
 L.fr_debug_tma_tiles.argtypes = [C.c_void_p] + [C.c_int] * 10 + [C.c_void_p, C.c_void_p]
 ctx = capi.Context(0, capi.Weights(capi.FR_MODEL_DET, None, 1), capi.Weights(capi.FR_MODEL_REC, None, 1))
 rows, pitch8 = 64 * 320, 320 * 8

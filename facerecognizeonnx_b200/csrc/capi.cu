@@ -164,6 +164,16 @@ int prepare_images(fr_ctx* ctx, const uint8_t* const* bgr, const int* rows, cons
   return FR_OK;
 }
 
+// Host -> device scratch upload, ordered on ctx->stream like every kernel that reads the scratch
+// (a blocking cudaMemcpy would run on the legacy stream, which does not order against a
+// non-blocking stream: a device-memspace call returns without synchronising, so the next call's
+// upload could overwrite flags the previous batch is still reading).  The source may be pageable:
+// the runtime stages it before returning, so locals are fine.
+int upload(fr_ctx* ctx, void* d_dst, const void* h_src, size_t bytes) {
+  FR_CUDA_OK(ctx, cudaMemcpyAsync(d_dst, h_src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  return FR_OK;
+}
+
 int copy_out(fr_ctx* ctx, void* dst, const void* d_src, size_t bytes, int memspace) {
   if (!dst || bytes == 0) return FR_OK;
   FR_CUDA_OK(ctx, cudaMemcpyAsync(dst, d_src, bytes,
@@ -192,7 +202,7 @@ int run_detect(fr_ctx* ctx, const ImgDesc* d_desc, int n_img, float score_thr, f
 }
 
 // align + embed for n_faces faces already on the device.
-int run_embed(fr_ctx* ctx, const ImgDesc* d_desc, const fr_face* d_faces, const int* d_face_img,
+int run_embed(fr_ctx* ctx, const ImgDesc* d_desc, int n_img, const fr_face* d_faces, const int* d_face_img,
               int n_faces, int* d_valid, float* d_emb) {
   if (!ctx->misc[B_ALIGN].reserve(sizeof(AlignRec) * n_faces) ||
       !ctx->misc[B_CROPS].reserve((size_t)n_faces * FR_REC_SIZE * FR_REC_SIZE * 3) ||
@@ -201,7 +211,7 @@ int run_embed(fr_ctx* ctx, const ImgDesc* d_desc, const fr_face* d_faces, const 
   AlignRec* d_rec = ctx->misc[B_ALIGN].as<AlignRec>();
   uint8_t* d_crops = ctx->misc[B_CROPS].as<uint8_t>();
   ctx->stage_begin(FR_STAGE_ALIGN);
-  FR_CHECK(k_align_estimate(ctx, d_faces, d_face_img, n_faces, d_desc, d_rec));
+  FR_CHECK(k_align_estimate(ctx, d_faces, d_face_img, n_faces, d_desc, n_img, d_rec));
   FR_CHECK(k_align_warp(ctx, d_rec, n_faces, d_desc, d_crops, d_valid));
   ctx->stage_end();
   return rec_forward_crops(ctx, d_crops, n_faces, ctx->misc[B_EMB_RAW].as<float>(), d_emb, d_valid);
@@ -229,6 +239,7 @@ int fr_create(fr_ctx** out, int device, const fr_weights* det, const fr_weights*
   }
   std::unique_ptr<fr_ctx> ctx(new fr_ctx());
   ctx->device = device;
+  ctx->num_sms = prop.multiProcessorCount;
   if (cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) != cudaSuccess) return FR_ERR_CUDA;
   ctx->stream = ctx->own_stream;
   int s = FR_OK;
@@ -366,9 +377,9 @@ int fr_embed_faces_batch(fr_ctx* ctx, const uint8_t* const* bgr, const int* rows
   if (face_img && memspace == FR_MEM_DEVICE)
     FR_CUDA_OK(ctx, cudaMemcpyAsync(ctx->misc[B_FACE_IMG].p, face_img, sizeof(int) * n_faces, kin, ctx->stream));
   else
-    FR_CUDA_OK(ctx, cudaMemcpy(ctx->misc[B_FACE_IMG].p, fi.data(), sizeof(int) * n_faces, cudaMemcpyHostToDevice));
-  FR_CUDA_OK(ctx, cudaMemcpy(ctx->misc[B_VALID].p, ones.data(), sizeof(int) * n_faces, cudaMemcpyHostToDevice));
-  FR_CHECK(run_embed(ctx, d_desc, ctx->misc[B_SEL].as<fr_face>(), ctx->misc[B_FACE_IMG].as<int>(),
+    FR_CHECK(upload(ctx, ctx->misc[B_FACE_IMG].p, fi.data(), sizeof(int) * n_faces));
+  FR_CHECK(upload(ctx, ctx->misc[B_VALID].p, ones.data(), sizeof(int) * n_faces));
+  FR_CHECK(run_embed(ctx, d_desc, n_img, ctx->misc[B_SEL].as<fr_face>(), ctx->misc[B_FACE_IMG].as<int>(),
                      n_faces, ctx->misc[B_VALID].as<int>(), ctx->misc[B_EMB].as<float>()));
   FR_CHECK(copy_out(ctx, out, ctx->misc[B_EMB].p, (size_t)n_faces * FR_FEAT_DIM * 4, memspace));
   FR_CHECK(copy_out(ctx, valid, ctx->misc[B_VALID].p, sizeof(int) * n_faces, memspace));
@@ -485,7 +496,7 @@ static int pipeline_enqueue(fr_ctx* ctx, const ImgDesc* d_desc, int n_img, int m
   int* d_valid = ctx->misc[B_VALID].as<int>();
   FR_CHECK(k_align_select(ctx, d_det, d_ndet, det_cap, d_pad, n_img, K, d_sel, d_fimg, d_valid));
   float* d_emb = memspace == FR_MEM_DEVICE ? out_emb : ctx->misc[B_EMB].as<float>();
-  FR_CHECK(run_embed(ctx, d_desc, d_sel, d_fimg, n_faces, d_valid, d_emb));
+  FR_CHECK(run_embed(ctx, d_desc, n_img, d_sel, d_fimg, n_faces, d_valid, d_emb));
   if (memspace != FR_MEM_DEVICE) FR_CHECK(copy_out(ctx, out_emb, d_emb, (size_t)n_faces * FR_FEAT_DIM * 4, memspace));
   FR_CHECK(copy_out(ctx, out_faces, d_sel, sizeof(fr_face) * n_faces, memspace));
   FR_CHECK(copy_out(ctx, out_n_det, d_ndet, sizeof(int) * n_img, memspace));
@@ -641,13 +652,13 @@ int fr_estimate_alignment(fr_ctx* ctx, const float* landmarks, int n, double* M_
   if (!ctx->misc[B_SEL].reserve(sizeof(fr_face) * n) || !ctx->misc[B_ALIGN].reserve(sizeof(AlignRec) * n) ||
       !ctx->img_desc.reserve(sizeof(ImgDesc)))
     return fr_fail(ctx, FR_ERR_CUDA, "allocation failed");
-  FR_CUDA_OK(ctx, cudaMemcpy(ctx->misc[B_SEL].p, faces.data(), sizeof(fr_face) * n, cudaMemcpyHostToDevice));
-  FR_CUDA_OK(ctx, cudaMemcpy(ctx->img_desc.p, &d, sizeof(d), cudaMemcpyHostToDevice));
-  FR_CHECK(k_align_estimate(ctx, ctx->misc[B_SEL].as<fr_face>(), nullptr, n, ctx->img_desc.as<ImgDesc>(),
+  FR_CHECK(upload(ctx, ctx->misc[B_SEL].p, faces.data(), sizeof(fr_face) * n));
+  FR_CHECK(upload(ctx, ctx->img_desc.p, &d, sizeof(d)));
+  FR_CHECK(k_align_estimate(ctx, ctx->misc[B_SEL].as<fr_face>(), nullptr, n, ctx->img_desc.as<ImgDesc>(), 1,
                             ctx->misc[B_ALIGN].as<AlignRec>()));
   std::vector<AlignRec> recs(n);
+  FR_CHECK(copy_out(ctx, recs.data(), ctx->misc[B_ALIGN].p, sizeof(AlignRec) * n, FR_MEM_HOST));
   FR_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
-  FR_CUDA_OK(ctx, cudaMemcpy(recs.data(), ctx->misc[B_ALIGN].p, sizeof(AlignRec) * n, cudaMemcpyDeviceToHost));
   for (int i = 0; i < n; ++i) {
     ok[i] = recs[i].mode == 0;
     for (int k = 0; k < 6; ++k) M_out[(size_t)i * 6 + k] = recs[i].fwd[k];
@@ -668,9 +679,9 @@ int fr_align_faces(fr_ctx* ctx, const uint8_t* bgr, int rows, int cols, size_t s
   if (!ctx->misc[B_SEL].reserve(sizeof(fr_face) * n_faces) || !ctx->misc[B_ALIGN].reserve(sizeof(AlignRec) * n_faces) ||
       !ctx->misc[B_CROPS].reserve(cb) || !ctx->misc[B_VALID].reserve(sizeof(int) * n_faces))
     return fr_fail(ctx, FR_ERR_CUDA, "allocation failed");
-  FR_CUDA_OK(ctx, cudaMemcpy(ctx->misc[B_SEL].p, faces, sizeof(fr_face) * n_faces, cudaMemcpyHostToDevice));
-  FR_CUDA_OK(ctx, cudaMemcpy(ctx->misc[B_VALID].p, ones.data(), sizeof(int) * n_faces, cudaMemcpyHostToDevice));
-  FR_CHECK(k_align_estimate(ctx, ctx->misc[B_SEL].as<fr_face>(), nullptr, n_faces, d_desc, ctx->misc[B_ALIGN].as<AlignRec>()));
+  FR_CHECK(upload(ctx, ctx->misc[B_SEL].p, faces, sizeof(fr_face) * n_faces));
+  FR_CHECK(upload(ctx, ctx->misc[B_VALID].p, ones.data(), sizeof(int) * n_faces));
+  FR_CHECK(k_align_estimate(ctx, ctx->misc[B_SEL].as<fr_face>(), nullptr, n_faces, d_desc, 1, ctx->misc[B_ALIGN].as<AlignRec>()));
   FR_CHECK(k_align_warp(ctx, ctx->misc[B_ALIGN].as<AlignRec>(), n_faces, d_desc, ctx->misc[B_CROPS].as<uint8_t>(),
                         ctx->misc[B_VALID].as<int>()));
   FR_CHECK(copy_out(ctx, out_crops, ctx->misc[B_CROPS].p, cb, FR_MEM_HOST));
@@ -699,7 +710,7 @@ int fr_warp_affine(fr_ctx* ctx, const uint8_t* bgr, int rows, int cols, size_t s
   const size_t cb = (size_t)FR_REC_SIZE * FR_REC_SIZE * 3;
   if (!ctx->misc[B_ALIGN].reserve(sizeof(AlignRec)) || !ctx->misc[B_CROPS].reserve(cb))
     return fr_fail(ctx, FR_ERR_CUDA, "allocation failed");
-  FR_CUDA_OK(ctx, cudaMemcpy(ctx->misc[B_ALIGN].p, &r, sizeof(r), cudaMemcpyHostToDevice));
+  FR_CHECK(upload(ctx, ctx->misc[B_ALIGN].p, &r, sizeof(r)));
   FR_CHECK(k_align_warp(ctx, ctx->misc[B_ALIGN].as<AlignRec>(), 1, d_desc, ctx->misc[B_CROPS].as<uint8_t>(), nullptr));
   FR_CHECK(copy_out(ctx, out_crop, ctx->misc[B_CROPS].p, cb, FR_MEM_HOST));
   FR_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));

@@ -8,6 +8,7 @@
 #include <cstdio>
 #include <map>
 #include <memory>
+#include <set>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -75,6 +76,10 @@ struct fr_ctx {
   std::string err;
   std::mutex mu;
   uint64_t launches = 0;
+  // per-device launch state: cudaFuncSetAttribute and the SM count belong to a device, and a
+  // process may hold contexts on several (never cache them in function-level statics)
+  int num_sms = 0;
+  std::set<const void*> smem_opt_in;
   DetModel* det = nullptr;
   RecModel* rec = nullptr;
   // generic staging buffers (device) + pinned host staging
@@ -131,6 +136,16 @@ static inline int fr_fail(fr_ctx* ctx, int code, const std::string& msg) {
 
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 
+// Opt a kernel in to `bytes` of dynamic shared memory on ctx's device, once per ctx.
+template <typename F>
+static inline cudaError_t fr_opt_in_smem(fr_ctx* ctx, F* func, int bytes) {
+  const void* key = reinterpret_cast<const void*>(func);
+  if (ctx->smem_opt_in.count(key)) return cudaSuccess;
+  const cudaError_t e = cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e == cudaSuccess) ctx->smem_opt_in.insert(key);
+  return e;
+}
+
 // ------------------------------------------------------------ stage launchers
 // k_preprocess.cu
 int k_det_preprocess(fr_ctx* ctx, const ImgDesc* d_desc, int n_img, __nv_bfloat16* d_out_chw);
@@ -160,7 +175,7 @@ struct AlignRec {       // per-face alignment record (device)
   int pad;
 };
 int k_align_estimate(fr_ctx* ctx, const fr_face* d_faces, const int* d_face_img, int n_faces,
-                     const ImgDesc* d_desc, AlignRec* d_rec);
+                     const ImgDesc* d_desc, int n_img, AlignRec* d_rec);
 int k_align_select(fr_ctx* ctx, const fr_face* d_det, const int* d_n_det, int cap_per_img,
                    const fr_face* d_pad, int n_img, int k, fr_face* d_sel, int* d_face_img,
                    int* d_valid);

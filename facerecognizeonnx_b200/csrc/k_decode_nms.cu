@@ -235,12 +235,7 @@ int k_scrfd_decode_nms(fr_ctx* ctx, NmsScratch& s, const HeadPtrs& heads, int n_
   if (!s.keys.reserve((size_t)n_img * KEY_STRIDE * 8) || !s.counts.reserve((size_t)n_img * 4) ||
       !s.boxes.reserve((size_t)n_img * NA * 16))
     return fr_fail(ctx, FR_ERR_CUDA, "nms scratch allocation failed");
-  static bool attr_set = false;
-  if (!attr_set) {
-    FR_CUDA_OK(ctx, cudaFuncSetAttribute(nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)NMS_SMEM));
-    attr_set = true;
-  }
+  FR_CUDA_OK(ctx, fr_opt_in_smem(ctx, nms_kernel, (int)NMS_SMEM));
   FR_CUDA_OK(ctx, cudaMemsetAsync(s.counts.p, 0, (size_t)n_img * 4, ctx->stream));
   DecodeArgs args;
   args.h = heads;

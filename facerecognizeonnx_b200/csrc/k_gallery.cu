@@ -470,13 +470,8 @@ int fr_gallery_search(fr_gallery* g, const float* queries, int nq, int k, int me
   if (!g || !queries || !out_scores || !out_idx || nq <= 0 || k <= 0 || k > TOPK) return FR_ERR_INVALID_ARG;
   fr_ctx* ctx = g->ctx;
   GGuard gg(ctx);
-  static bool attr = false;
-  static int num_sms = 148;
-  if (!attr) {
-    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, ctx->device);
-    FR_CUDA_OK(ctx, cudaFuncSetAttribute(gallery_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, G_SMEM));
-    attr = true;
-  }
+  const int num_sms = ctx->num_sms;
+  FR_CUDA_OK(ctx, fr_opt_in_smem(ctx, gallery_topk_kernel, G_SMEM));
   const int num_m_tiles = ceil_div(nq, tc::BM);
   const int nq_pad = num_m_tiles * tc::BM;
   const int n_tiles = (int)((g->size + GN - 1) / GN);

@@ -154,21 +154,10 @@ int tc_launch(fr_ctx* ctx, ConvLaunch& L, int m_rows) {
   L.p.num_m_tiles = ceil_div(m_rows, tc::BM);
   const int total = L.p.num_m_tiles * L.p.n_tiles_n * (L.p.k_splits > 1 ? L.p.k_splits : 1);
   if (total <= 0) return FR_OK;
-  static int num_sms = 0;
-  static bool attrs = false;
-  if (!attrs) {
-    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, ctx->device);
-    FR_CUDA_OK(ctx, cudaFuncSetAttribute(tc::shift_gemm_kernel<64>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         tc::Cfg<64>::SMEM_BYTES));
-    FR_CUDA_OK(ctx, cudaFuncSetAttribute(tc::shift_gemm_kernel<128>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         tc::Cfg<128>::SMEM_BYTES));
-    FR_CUDA_OK(ctx, cudaFuncSetAttribute(tc::shift_gemm_kernel<256>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         tc::Cfg<256>::SMEM_BYTES));
-    attrs = true;
-  }
+  const int num_sms = ctx->num_sms;
+  FR_CUDA_OK(ctx, fr_opt_in_smem(ctx, tc::shift_gemm_kernel<64>, tc::Cfg<64>::SMEM_BYTES));
+  FR_CUDA_OK(ctx, fr_opt_in_smem(ctx, tc::shift_gemm_kernel<128>, tc::Cfg<128>::SMEM_BYTES));
+  FR_CUDA_OK(ctx, fr_opt_in_smem(ctx, tc::shift_gemm_kernel<256>, tc::Cfg<256>::SMEM_BYTES));
   const int grid = std::min(total, num_sms);
   if (L.halo) {
     const int supers = ceil_div(L.p.num_m_tiles, L.mt) * L.p.n_tiles_n;
@@ -190,12 +179,7 @@ int tc_launch(fr_ctx* ctx, ConvLaunch& L, int m_rows) {
     const int hgrid = std::min(items, num_sms);
 #define FR_HALO_LAUNCH(BN_, MT_, RB_)                                                              \
   do {                                                                                             \
-    static bool set_ = false;                                                                      \
-    if (!set_) {                                                                                   \
-      FR_CUDA_OK(ctx, cudaFuncSetAttribute(tc::halo_gemm_kernel<BN_, MT_, RB_>,                    \
-                                           cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); \
-      set_ = true;                                                                                 \
-    }                                                                                              \
+    FR_CUDA_OK(ctx, fr_opt_in_smem(ctx, tc::halo_gemm_kernel<BN_, MT_, RB_>, 227 * 1024));         \
     L.p.a_stages = std::min(env_flag("FR_TC_ASTAGES", 2), tc::HaloCfg<BN_, MT_, RB_>::pick_a_stages(L.p.a_rows)); \
     tc::halo_gemm_kernel<BN_, MT_, RB_><<<hgrid, tc::CONV_THREADS,                                  \
         tc::HaloCfg<BN_, MT_, RB_>::smem_bytes(L.p.a_rows, L.p.a_stages), ctx->stream>>>(            \

@@ -1826,9 +1826,7 @@ int det_forward(fr_ctx* ctx, const __nv_bfloat16* d_in_chw, int n, HeadPtrs* hea
       stem_conv_kernel<<<(unsigned)((total + 127) / 128), 128, 0, ctx->stream>>>(d_in_chw, m->a_stem, m->stem_w,
                                                                                   m->stem_b, n);
     } else {
-      static const cudaError_t attr = cudaFuncSetAttribute(stem_conv_mma_kernel,
-                                                          cudaFuncAttributeMaxDynamicSharedMemorySize, SM_SMEM_BYTES);
-      FR_CUDA_OK(ctx, attr);
+      FR_CUDA_OK(ctx, fr_opt_in_smem(ctx, stem_conv_mma_kernel, SM_SMEM_BYTES));
       stem_conv_mma_kernel<<<(unsigned)(n * (DET / (4 * SM_GROUPS))), 128, SM_SMEM_BYTES, ctx->stream>>>(
           d_in_chw, m->a_stem, m->stem_bfrag);
     }
@@ -1845,9 +1843,7 @@ int det_forward(fr_ctx* ctx, const __nv_bfloat16* d_in_chw, int n, HeadPtrs* hea
     FR_CHECK(dwsep("b0", m->a_stem, m->a_b0, 320, 1));
   } else {
     const PackedConv& pc = m->conv.at("b0");
-    static const cudaError_t attr = cudaFuncSetAttribute(b0_dwpw_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                        B0_SMEM_BYTES);
-    FR_CUDA_OK(ctx, attr);
+    FR_CUDA_OK(ctx, fr_opt_in_smem(ctx, b0_dwpw_mma_kernel, B0_SMEM_BYTES));
     constexpr int HW = DET / 2;
     b0_dwpw_mma_kernel<<<(unsigned)(n * (HW / B0_TW) * (HW / (B0_ROWS * B0_GROUPS))), 256, B0_SMEM_BYTES, ctx->stream>>>(
         m->a_stem, m->a_b0, pc.dw_w, pc.dw_b, m->b0_bfrag, pc.bias, HW);

@@ -33,11 +33,22 @@ struct CvRng {
 
 __global__ void align_estimate_kernel(const fr_face* __restrict__ faces,
                                       const int* __restrict__ face_img, int n_faces,
-                                      const ImgDesc* __restrict__ descs, AlignRec* __restrict__ recs) {
+                                      const ImgDesc* __restrict__ descs, int n_img,
+                                      AlignRec* __restrict__ recs) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_faces) return;
   const fr_face f = faces[i];
   const int img = face_img ? face_img[i] : 0;
+  if ((unsigned)img >= (unsigned)n_img) {   // a device-side face->image map is caller data: never index with it unchecked
+    AlignRec bad;
+    bad.img = 0;
+    bad.pad = 0;
+    bad.mode = 2;
+    bad.cx = bad.cy = bad.cw = bad.ch = 0;
+    for (int k = 0; k < 6; ++k) bad.inv[k] = bad.fwd[k] = 0.0;
+    recs[i] = bad;
+    return;
+  }
   float sx[5], sy[5], tx[5], ty[5];
 #pragma unroll
   for (int p = 0; p < 5; ++p) {
@@ -225,10 +236,10 @@ align_warp_kernel(const AlignRec* __restrict__ recs, const ImgDesc* __restrict__
 }  // namespace
 
 int k_align_estimate(fr_ctx* ctx, const fr_face* d_faces, const int* d_face_img, int n_faces,
-                     const ImgDesc* d_desc, AlignRec* d_rec) {
+                     const ImgDesc* d_desc, int n_img, AlignRec* d_rec) {
   if (n_faces <= 0) return FR_OK;
   align_estimate_kernel<<<ceil_div(n_faces, 64), 64, 0, ctx->stream>>>(d_faces, d_face_img,
-                                                                       n_faces, d_desc, d_rec);
+                                                                       n_faces, d_desc, n_img, d_rec);
   ctx->launches++;
   FR_CUDA_OK(ctx, cudaGetLastError());
   return FR_OK;
