@@ -913,9 +913,63 @@ static int rec_build_plan(fr_ctx* ctx, int cap) {
   return FR_OK;
 }
 
-static int rec_run_trunk(fr_ctx* ctx, int n, float* d_out_raw) {
+// The residual stream of layer 0 is 1.6 MB per face at 112^2 (0.4 MB at 56^2): at the bench's 512
+// faces those tensors are 213-835 MB, stream through HBM between launches, and the launches that
+// touch them are DRAM-bound (the stride-2 conv of block 0 reads 1.07 GB).  Running the stem and the
+// first FR_REC_CHUNK_BLOCKS blocks depth-first over chunks of FR_REC_CHUNK faces keeps each chunk's
+// tensors (<= 100 MB) resident in the 126 MB L2: every chunk reuses the same rows [0, chunk) of the
+// plan's buffers, and only the last chunked block writes its output at the chunk's offset in the
+// full-batch tensor.  29 faces: 29 * 57 * 57 / 128 = 736.1 -> 737 tiles = 4.98 waves of 148 CTAs.
+// Same kernels, same per-element accumulation order: results are bit-identical to the unchunked run.
+static int rec_chunk_faces() { static const int v = env_flag("FR_REC_CHUNK", 29); return v; }
+static int rec_chunk_blocks() { static const int v = env_flag("FR_REC_CHUNK_BLOCKS", 3); return v; }
+
+static int rec_launch_stem(fr_ctx* ctx, const uint8_t* d_crops, int n) {
   RecModel* m = ctx->rec;
-  for (size_t i = 0; i < m->blocks.size(); ++i) {
+  ctx->stage_begin(FR_STAGE_STEM);
+  static const bool simt_stem = getenv("FR_STEM_SIMT") != nullptr;   // A/B switch: the CUDA-core stem
+  if (simt_stem) {
+    const long long threads = (long long)n * REC * (REC / 4);
+    stem_kernel<true><<<(unsigned)((threads + 127) / 128), 128, 0, ctx->stream>>>(
+        d_crops, n, m->stem_w, m->stem_b, m->stem_prelu, m->x0.p, m->x0e.p);
+  } else {
+    stem_mma_kernel<<<(unsigned)(n * (REC / (STEM_WARPS * STEM_GROUPS))), STEM_WARPS * 32, 0, ctx->stream>>>(
+        d_crops, m->stem_bfrag, m->stem_prelu, m->x0.p, m->x0e.p);
+  }
+  ctx->stage_end();
+  ctx->launches++;
+  FR_CUDA_OK(ctx, cudaGetLastError());
+  return FR_OK;
+}
+
+// stem + blocks [0, nb) for faces [f0, f0 + nf), computed in rows [0, nf) of the plan's buffers;
+// block nb-1 writes its output (and the even-pixel copy) at face offset f0
+static int rec_run_front_chunk(fr_ctx* ctx, const uint8_t* d_crops, int f0, int nf, int nb) {
+  RecModel* m = ctx->rec;
+  FR_CHECK(rec_launch_stem(ctx, d_crops + (size_t)f0 * REC * REC * 3, nf));
+  ctx->stage_begin(FR_STAGE_TRUNK);
+  for (int i = 0; i < nb; ++i) {
+    FR_CHECK(tc_launch(ctx, m->conv1[i], nf * m->conv1[i].rows_per_img));
+    ConvLaunch& c2 = m->conv2[i];
+    bf16* const out0 = c2.p.out;
+    bf16* const even0 = c2.p.out_even;
+    if (i == nb - 1) {
+      const RecModel::BlockBufs& bb = m->bufs[i];
+      c2.p.out = out0 + bb.out.rows(f0) * bb.out.C;
+      if (even0) c2.p.out_even = even0 + bb.out_even.rows(f0) * bb.out_even.C;
+    }
+    const int s = tc_launch(ctx, c2, nf * c2.rows_per_img);
+    c2.p.out = out0;
+    c2.p.out_even = even0;
+    FR_CHECK(s);
+  }
+  ctx->stage_end();
+  return FR_OK;
+}
+
+static int rec_run_trunk(fr_ctx* ctx, int n, float* d_out_raw, size_t first_block = 0) {
+  RecModel* m = ctx->rec;
+  for (size_t i = first_block; i < m->blocks.size(); ++i) {
     FR_CHECK(tc_launch(ctx, m->conv1[i], n * m->conv1[i].rows_per_img));
     FR_CHECK(tc_launch(ctx, m->conv2[i], n * m->conv2[i].rows_per_img));
   }
@@ -940,22 +994,18 @@ int rec_forward_crops(fr_ctx* ctx, const uint8_t* d_crops, int n, float* d_out_r
   if (!m) return fr_fail(ctx, FR_ERR_NOT_LOADED, "Model not loaded!");
   if (n <= 0) return FR_OK;
   FR_CHECK(rec_build_plan(ctx, rec_plan_cap(n)));
-  ctx->stage_begin(FR_STAGE_STEM);
-  static const bool simt_stem = getenv("FR_STEM_SIMT") != nullptr;   // A/B switch: the CUDA-core stem
-  if (simt_stem) {
-    const long long threads = (long long)n * REC * (REC / 4);
-    stem_kernel<true><<<(unsigned)((threads + 127) / 128), 128, 0, ctx->stream>>>(
-        d_crops, n, m->stem_w, m->stem_b, m->stem_prelu, m->x0.p, m->x0e.p);
-  } else {
-    stem_mma_kernel<<<(unsigned)(n * (REC / (STEM_WARPS * STEM_GROUPS))), STEM_WARPS * 32, 0, ctx->stream>>>(
-        d_crops, m->stem_bfrag, m->stem_prelu, m->x0.p, m->x0e.p);
-  }
-  ctx->stage_end();
-  ctx->launches++;
-  FR_CUDA_OK(ctx, cudaGetLastError());
   float* raw = d_out_raw ? d_out_raw : m->fc_out;
+  const int chunk = rec_chunk_faces();
+  const int cb = std::min<int>(rec_chunk_blocks(), (int)m->blocks.size());
+  size_t first_block = 0;
+  if (chunk > 0 && cb > 0 && n > chunk) {
+    for (int f0 = 0; f0 < n; f0 += chunk) FR_CHECK(rec_run_front_chunk(ctx, d_crops, f0, std::min(chunk, n - f0), cb));
+    first_block = (size_t)cb;
+  } else {
+    FR_CHECK(rec_launch_stem(ctx, d_crops, n));
+  }
   ctx->stage_begin(FR_STAGE_TRUNK);
-  FR_CHECK(rec_run_trunk(ctx, n, raw));
+  FR_CHECK(rec_run_trunk(ctx, n, raw, first_block));
   ctx->stage_end();
   if (d_out_norm) {
     ctx->stage_begin(FR_STAGE_L2NORM);

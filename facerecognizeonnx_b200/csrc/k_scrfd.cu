@@ -1811,6 +1811,73 @@ void det_model_destroy(fr_ctx* ctx) {
   ctx->det = nullptr;
 }
 
+static int env_int(const char* name, int dflt) {
+  const char* v = getenv(name);
+  return v ? atoi(v) : dflt;
+}
+
+// The 320^2 / 160^2 activations are 6.5 / 4.1 MB per frame in fp32: at 64 frames every early layer
+// streams 260-840 MB through HBM.  The first FR_DET_CHUNK_LAYERS layers (stem, b0, s0.0, s0.1, ...)
+// therefore run depth-first over chunks of FR_DET_CHUNK frames whose tensors stay in the 126 MB L2:
+// each chunk uses frames [0, chunk) of the activation buffers and the last chunked layer writes its
+// output at the chunk's offset of the full-batch tensor.  Per-frame results do not depend on the
+// batch around a frame, so this is bit-identical to the unchunked run.
+static int det_front(fr_ctx* ctx, const __nv_bfloat16* d_in_chw, int n, int n_layers, size_t out_frame_off) {
+  DetModel* m = ctx->det;
+  // last front layer writes at frame offset `out_frame_off` of its (full-batch) output tensor
+  auto dst = [&](int layer, float* base, size_t per_frame) {
+    return layer == n_layers - 1 ? base + out_frame_off * per_frame : base;
+  };
+  // stem: 3x3 s2, 3 -> 16, ReLU (bf16 planar input from K1) -> fp32 NHWC
+  float* o_stem = dst(0, m->a_stem, (size_t)16 * 320 * 320);
+  {
+    static const bool simt_stem = getenv("FR_SCRFD_STEM_SIMT") != nullptr;   // A/B switch: the CUDA-core stem
+    if (simt_stem) {
+      const size_t total = (size_t)n * (DET / 2) * (DET / 2 / 4);
+      stem_conv_kernel<<<(unsigned)((total + 127) / 128), 128, 0, ctx->stream>>>(d_in_chw, o_stem, m->stem_w,
+                                                                                  m->stem_b, n);
+    } else {
+      FR_CUDA_OK(ctx, fr_opt_in_smem(ctx, stem_conv_mma_kernel, SM_SMEM_BYTES));
+      stem_conv_mma_kernel<<<(unsigned)(n * (DET / (4 * SM_GROUPS))), 128, SM_SMEM_BYTES, ctx->stream>>>(
+          d_in_chw, o_stem, m->stem_bfrag);
+    }
+    ctx->launches++;
+    FR_CUDA_OK(ctx, cudaGetLastError());
+  }
+  if (n_layers == 1) return FR_OK;
+  auto dwsep = [&](const std::string& name, const float* in, float* out, int hin, int stride) -> int {
+    LayerIO io;
+    io.in = in; io.out = out; io.hin = hin; io.stride = stride; io.relu = 1;
+    return launch_layer(ctx, m->conv.at(name), io, n);
+  };
+  float* o_b0 = dst(1, m->a_b0, (size_t)16 * 320 * 320);
+  static const bool b0_tc = getenv("FR_SCRFD_B0_TCGEN05") != nullptr;   // A/B switch: b0 through sep_gemm_kernel
+  if (b0_tc) {
+    FR_CHECK(dwsep("b0", m->a_stem, o_b0, 320, 1));
+  } else {
+    const PackedConv& pc = m->conv.at("b0");
+    FR_CUDA_OK(ctx, fr_opt_in_smem(ctx, b0_dwpw_mma_kernel, B0_SMEM_BYTES));
+    constexpr int HW = DET / 2;
+    b0_dwpw_mma_kernel<<<(unsigned)(n * (HW / B0_TW) * (HW / (B0_ROWS * B0_GROUPS))), 256, B0_SMEM_BYTES, ctx->stream>>>(
+        m->a_stem, o_b0, pc.dw_w, pc.dw_b, m->b0_bfrag, pc.bias, HW);
+    ctx->launches++;
+    FR_CUDA_OK(ctx, cudaGetLastError());
+  }
+  const float* cur = m->a_b0;
+  int hw = 320, bi = 0;
+  for (int s = 0; s < 4; ++s)
+    for (int b = 0; b < kStages[s][0]; ++b, ++bi) {
+      if (bi + 2 >= n_layers) return FR_OK;
+      const int stride = b == 0 ? 2 : 1;
+      const int ho = hw / stride;
+      FR_CHECK(dwsep("s" + std::to_string(s) + "." + std::to_string(b), cur,
+                     dst(bi + 2, m->a_stage[bi], (size_t)kStages[s][1] * ho * ho), hw, stride));
+      hw = ho;
+      cur = m->a_stage[bi];
+    }
+  return FR_OK;
+}
+
 int det_forward(fr_ctx* ctx, const __nv_bfloat16* d_in_chw, int n, HeadPtrs* heads) {
   DetModel* m = ctx->det;
   if (!m) return fr_fail(ctx, FR_ERR_NOT_LOADED, "Model not loaded!");
@@ -1818,45 +1885,31 @@ int det_forward(fr_ctx* ctx, const __nv_bfloat16* d_in_chw, int n, HeadPtrs* hea
   int cap = 1;
   while (cap < n) cap *= 2;
   FR_CHECK(det_build_acts(ctx, cap));
-  // stem: 3x3 s2, 3 -> 16, ReLU (bf16 planar input from K1) -> fp32 NHWC
-  {
-    static const bool simt_stem = getenv("FR_SCRFD_STEM_SIMT") != nullptr;   // A/B switch: the CUDA-core stem
-    if (simt_stem) {
-      const size_t total = (size_t)n * (DET / 2) * (DET / 2 / 4);
-      stem_conv_kernel<<<(unsigned)((total + 127) / 128), 128, 0, ctx->stream>>>(d_in_chw, m->a_stem, m->stem_w,
-                                                                                  m->stem_b, n);
-    } else {
-      FR_CUDA_OK(ctx, fr_opt_in_smem(ctx, stem_conv_mma_kernel, SM_SMEM_BYTES));
-      stem_conv_mma_kernel<<<(unsigned)(n * (DET / (4 * SM_GROUPS))), 128, SM_SMEM_BYTES, ctx->stream>>>(
-          d_in_chw, m->a_stem, m->stem_bfrag);
-    }
-    ctx->launches++;
-    FR_CUDA_OK(ctx, cudaGetLastError());
+  static const int chunk = env_int("FR_DET_CHUNK", 8);
+  static const int chunk_layers = std::min(std::max(env_int("FR_DET_CHUNK_LAYERS", 4), 1), 15);
+  const int n_backbone = 15;   // stem, b0, 13 dw-separable blocks
+  int front = n_backbone;      // layers run by det_front
+  if (chunk > 0 && n > chunk) {
+    for (int f0 = 0; f0 < n; f0 += chunk)
+      FR_CHECK(det_front(ctx, d_in_chw + (size_t)f0 * 3 * DET * DET, std::min(chunk, n - f0), chunk_layers, (size_t)f0));
+    front = chunk_layers;
+  } else {
+    FR_CHECK(det_front(ctx, d_in_chw, n, n_backbone, 0));
   }
   auto dwsep = [&](const std::string& name, const float* in, float* out, int hin, int stride) -> int {
     LayerIO io;
     io.in = in; io.out = out; io.hin = hin; io.stride = stride; io.relu = 1;
     return launch_layer(ctx, m->conv.at(name), io, n);
   };
-  static const bool b0_tc = getenv("FR_SCRFD_B0_TCGEN05") != nullptr;   // A/B switch: b0 through sep_gemm_kernel
-  if (b0_tc) {
-    FR_CHECK(dwsep("b0", m->a_stem, m->a_b0, 320, 1));
-  } else {
-    const PackedConv& pc = m->conv.at("b0");
-    FR_CUDA_OK(ctx, fr_opt_in_smem(ctx, b0_dwpw_mma_kernel, B0_SMEM_BYTES));
-    constexpr int HW = DET / 2;
-    b0_dwpw_mma_kernel<<<(unsigned)(n * (HW / B0_TW) * (HW / (B0_ROWS * B0_GROUPS))), 256, B0_SMEM_BYTES, ctx->stream>>>(
-        m->a_stem, m->a_b0, pc.dw_w, pc.dw_b, m->b0_bfrag, pc.bias, HW);
-    ctx->launches++;
-    FR_CUDA_OK(ctx, cudaGetLastError());
-  }
+  // the rest of the backbone on the whole batch
   const float* cur = m->a_b0;
   int hw = 320, bi = 0;
   const float* feats[3] = {nullptr, nullptr, nullptr};
   for (int s = 0; s < 4; ++s) {
     for (int b = 0; b < kStages[s][0]; ++b, ++bi) {
       const int stride = b == 0 ? 2 : 1;
-      FR_CHECK(dwsep("s" + std::to_string(s) + "." + std::to_string(b), cur, m->a_stage[bi], hw, stride));
+      if (bi + 2 >= front)
+        FR_CHECK(dwsep("s" + std::to_string(s) + "." + std::to_string(b), cur, m->a_stage[bi], hw, stride));
       hw /= stride;
       cur = m->a_stage[bi];
     }

@@ -122,7 +122,7 @@ class FullGraph(GraphBuilder):
 
     def __init__(self, opset: int = 11):
         super().__init__()
-        self.inputs, self.outputs, self.opset = [], [], opset
+        self.inputs, self.outputs, self.opset, self.edges = [], [], opset, []
 
     def init_i64(self, vals) -> str:
         nm = self.name()
@@ -134,10 +134,6 @@ class FullGraph(GraphBuilder):
         self.inits.append(tensor_f32_empty(nm))
         return nm
 
-    def add_named(self, op, inputs, out_name, attrs=()):
-        self.nodes.append(node(op, inputs, [out_name], attrs))
-        return out_name
-
     def conv(self, x, wt, b=None, stride=1, group=1):
         k = wt.shape[-1]
         ins = [x, self.init(wt)] + ([self.init(b)] if b is not None else [])
@@ -145,9 +141,42 @@ class FullGraph(GraphBuilder):
                                       attr_ints("kernel_shape", [k, k]), attr_ints("pads", [k // 2] * 4),
                                       attr_ints("strides", [stride, stride])])
 
-    def model(self, shuffle_seed=None) -> bytes:
+    def add_named(self, op, inputs, out_name, attrs=()):
+        self.nodes.append(node(op, inputs, [out_name], attrs))
+        self.edges.append((list(inputs), out_name))
+        return out_name
+
+    def add(self, op, inputs, attrs=()) -> str:
+        out = super().add(op, inputs, attrs)
+        self.edges.append((list(inputs), out))
+        return out
+
+    def _random_topological_order(self, seed):
+        """A random VALID node order (ONNX requires producers before consumers; any such order is a
+        legal export): Kahn's algorithm picking a random ready node each time."""
+        rng = np.random.default_rng(seed)
+        produced_by = {out: i for i, (_, out) in enumerate(self.edges)}
+        deps = [{produced_by[x] for x in ins if x in produced_by} for ins, _ in self.edges]
+        done, order = set(), []
+        ready = [i for i, d in enumerate(deps) if not d]
+        while ready:
+            i = ready.pop(int(rng.integers(0, len(ready))))
+            order.append(i)
+            done.add(i)
+            for j, d in enumerate(deps):
+                if j not in done and j not in ready and d <= done:
+                    ready.append(j)
+        assert len(order) == len(self.nodes)
+        return order
+
+    def model(self, shuffle_seed=None, topological: bool = True) -> bytes:
+        """shuffle_seed: permute the stored node order -- a random valid topological order by default
+        (what a different exporter / optimizer may emit), or with topological=False an arbitrary
+        permutation (not valid ONNX; only the product's reader is expected to cope)."""
         nodes = list(self.nodes)
-        if shuffle_seed is not None:
+        if shuffle_seed is not None and topological:
+            nodes = [self.nodes[i] for i in self._random_topological_order(shuffle_seed)]
+        elif shuffle_seed is not None:
             np.random.default_rng(shuffle_seed).shuffle(nodes)
         g = b"".join(_ld(1, n) for n in nodes) + _ld(2, b"g") + b"".join(_ld(5, t) for t in self.inits)
         g += b"".join(_ld(11, v) for v in self.inputs) + b"".join(_ld(12, v) for v in self.outputs)
@@ -185,7 +214,8 @@ class _RawBN:
         return w_raw.astype(np.float32), [a.astype(np.float32) for a in (gamma, beta, mean, var)]
 
 
-def emit_rec_full(w: dict, path: str, raw: bool = True, seed: int = 0, batch: int = 1, shuffle_seed=None):
+def emit_rec_full(w: dict, path: str, raw: bool = True, seed: int = 0, batch: int = 1, shuffle_seed=None,
+                  topological: bool = True):
     """w600k_r50-shaped graph.  raw=True: Conv (no bias) -> BatchNormalization everywhere the
     training graph has one (arcface_torch iresnet: bn after the stem conv, bn2 / bn3 inside every
     IBasicBlock, bn after the downsample conv); raw=False: the form torch.onnx leaves after its
@@ -226,14 +256,14 @@ def emit_rec_full(w: dict, path: str, raw: bool = True, seed: int = 0, batch: in
     out = g.add_named("BatchNormalization", [x] + [g.init(p) for p in params], "683",
                       [attr_f("epsilon", eps), attr_f("momentum", 0.9)])
     g.outputs.append(value_info(out, (batch, 512)))
-    open(path, "wb").write(g.model(shuffle_seed))
+    open(path, "wb").write(g.model(shuffle_seed, topological))
 
 
 DET_OUT_NAMES = ["score_8", "score_16", "score_32", "bbox_8", "bbox_16", "bbox_32", "kps_8", "kps_16", "kps_32"]
 
 
 def emit_det_full(w: dict, path: str, raw: bool = True, seed: int = 0, bbox_scales=(1.0, 1.0, 1.0), batch: int = 1,
-                  size: int = 640, flatten_outputs: bool = True, shuffle_seed=None):
+                  size: int = 640, flatten_outputs: bool = True, shuffle_seed=None, topological: bool = True):
     """det_500m-shaped graph (mmdet SCRFD: MobileNetV1-style backbone with Conv-BN-ReLU, PAFPN with
     biased convs and no norm, depthwise-separable head towers with BN, biased 3x3 predictors, Scale
     on the bbox branch, sigmoid on the scores inside the graph).  With flatten_outputs the nine
@@ -311,4 +341,4 @@ def emit_det_full(w: dict, path: str, raw: bool = True, seed: int = 0, bbox_scal
             results[oname] = value_info(oname, shape)
     for nm in DET_OUT_NAMES:
         g.outputs.append(results[nm])
-    open(path, "wb").write(g.model(shuffle_seed))
+    open(path, "wb").write(g.model(shuffle_seed, topological))

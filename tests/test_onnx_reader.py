@@ -45,8 +45,8 @@ def test_same_shape_layers_are_bound_by_edges_not_by_file_order(capi, det_wdict,
     """fpn0..2 / pafpn0..1 / down0..1 / the three head towers have identical weight shapes: a
     reader that walks nodes in file order permutes them silently when an exporter reorders nodes."""
     p = str(tmp_path / "det.onnx")
-    for seed in (1, 2, 3):
-        onnx_emit.emit_det_full(det_wdict, p, raw=False, shuffle_seed=seed)
+    for seed, topo in ((1, True), (2, True), (3, False), (4, False)):
+        onnx_emit.emit_det_full(det_wdict, p, raw=False, shuffle_seed=seed, topological=topo)
         got = capi.Weights(capi.FR_MODEL_DET, p).to_dict()
         for k in ("fpn0.w", "fpn1.w", "fpn2.w", "pafpn0.w", "pafpn1.w", "down0.w", "down1.w",
                   "h0.t1.pw.w", "h1.t1.pw.w", "h2.t1.pw.w", "h0.kps.b", "h2.kps.b"):
