@@ -519,21 +519,19 @@ def bench_gallery(ctx, capi, torch, dist, dev, rank, world, stream, peaks, rows_
         q[:64] = pl
     else:
         q[:64] = torch.from_numpy(planted).to(dev)
-    ls = torch.empty(nq, k, dtype=torch.float32, device=dev)
-    li = torch.empty(nq, k, dtype=torch.int64, device=dev)
-    gs = torch.empty(world * nq, k, dtype=torch.float32, device=dev)
-    gi = torch.empty(world * nq, k, dtype=torch.int64, device=dev)
+    lrec = torch.empty(nq, k, dtype=torch.int64, device=dev)           # packed {score, global index} records
+    grec = torch.empty(world * nq, k, dtype=torch.int64, device=dev)
     ms_ = torch.empty(nq, k, dtype=torch.float32, device=dev)
     mi = torch.empty(nq, k, dtype=torch.int64, device=dev)
 
     def one():
-        gal.search_dev(q.data_ptr(), nq, k, ls.data_ptr(), li.data_ptr())
+        # local fused GEMM + top-k -> ONE all-gather of 8-byte records -> rank merge
+        gal.search_packed_dev(q.data_ptr(), nq, k, lrec.data_ptr())
         if world > 1:
-            dist.all_gather_into_tensor(gs, ls)
-            dist.all_gather_into_tensor(gi, li)
-            capi.topk_merge_dev(ctx, gs.data_ptr(), gi.data_ptr(), world, nq, k, ms_.data_ptr(), mi.data_ptr())
+            dist.all_gather_into_tensor(grec, lrec)
+            capi.topk_merge_packed_dev(ctx, grec.data_ptr(), world, nq, k, ms_.data_ptr(), mi.data_ptr())
         else:
-            capi.topk_merge_dev(ctx, ls.data_ptr(), li.data_ptr(), 1, nq, k, ms_.data_ptr(), mi.data_ptr())
+            capi.topk_merge_packed_dev(ctx, lrec.data_ptr(), 1, nq, k, ms_.data_ptr(), mi.data_ptr())
 
     for _ in range(3):
         one()
@@ -558,7 +556,8 @@ def bench_gallery(ctx, capi, torch, dist, dev, rank, world, stream, peaks, rows_
             "gallery_rows_total": rows_per_gpu * world, "rows_per_gpu": rows_per_gpu, "queries_per_batch": nq,
             "ms_per_batch": ms / iters, "gemm_tflops_per_gpu": tflops,
             "frac_of_sustained_bf16_peak": tflops / peaks["tflops_sustained"], "planted_top1_ok": top1_ok,
-            "merge": "NCCL all_gather_into_tensor + fr_topk_merge" if world > 1 else "fr_topk_merge (1 shard)"}
+            "merge": "one NCCL all_gather_into_tensor of packed 8-byte {score, index} records + fr_topk_merge_packed"
+                     if world > 1 else "fr_topk_merge_packed (1 shard)"}
 
 
 _JSON_FD = None

@@ -40,6 +40,7 @@ SYMBOLS = [
     "fr_compare", "fr_compare_batch", "fr_pipeline_batch", "fr_pipeline_submit", "fr_pipeline_wait",
     "fr_gallery_create", "fr_gallery_destroy", "fr_gallery_add", "fr_gallery_fill_synthetic",
     "fr_gallery_get_rows", "fr_gallery_size", "fr_gallery_search", "fr_topk_merge",
+    "fr_gallery_search_sharded", "fr_gallery_search_packed", "fr_topk_merge_packed",
     "fr_gallery_save", "fr_gallery_load", "fr_gallery_remove",
     "fr_det_preprocess", "fr_scrfd_forward", "fr_scrfd_decode_nms", "fr_estimate_alignment",
     "fr_align_faces", "fr_warp_affine", "fr_resize_linear", "fr_iresnet_forward", "fr_iresnet_tap",
@@ -116,6 +117,9 @@ def _declare(L: C.CDLL) -> None:
     L.fr_gallery_remove.argtypes = [vp, i64]
     L.fr_gallery_search.argtypes = [vp, vp, i32, i32, i32, vp, vp]
     L.fr_topk_merge.argtypes = [vp, vp, vp, i32, i32, i32, i32, vp, vp]
+    L.fr_gallery_search_sharded.argtypes = [vp, vp, i32, vp, i32, i32, i32, vp, vp]
+    L.fr_gallery_search_packed.argtypes = [vp, vp, i32, i32, i32, vp]
+    L.fr_topk_merge_packed.argtypes = [vp, vp, i32, i32, i32, i32, vp, vp]
     L.fr_det_preprocess.argtypes = [vp, vp, vp, vp, vp, i32, i32, vp, vp]
     L.fr_scrfd_forward.argtypes = [vp, vp, i32, vp]
     L.fr_scrfd_decode_nms.argtypes = [vp, vp, i32, vp, f32, f32, vp, i32, vp]
@@ -520,6 +524,16 @@ class Gallery:
     def search_dev(self, q_ptr: int, nq: int, k: int, out_s_ptr: int, out_i_ptr: int):
         self.ctx._check(lib().fr_gallery_search(self.h, q_ptr, nq, k, FR_MEM_DEVICE, out_s_ptr, out_i_ptr))
 
+    def search_packed(self, queries: np.ndarray, k: int = 10) -> np.ndarray:
+        """Local top-k as packed records (uint64: low word fp32 score bits, high word global index)."""
+        q = np.ascontiguousarray(queries, np.float32)
+        rec = np.zeros((q.shape[0], k), np.uint64)
+        self.ctx._check(lib().fr_gallery_search_packed(self.h, q.ctypes.data, q.shape[0], k, FR_MEM_HOST, rec.ctypes.data))
+        return rec
+
+    def search_packed_dev(self, q_ptr: int, nq: int, k: int, out_rec_ptr: int):
+        self.ctx._check(lib().fr_gallery_search_packed(self.h, q_ptr, nq, k, FR_MEM_DEVICE, out_rec_ptr))
+
 
 def topk_merge(ctx: Context, scores: np.ndarray, idx: np.ndarray, k: int):
     """scores/idx: [parts, nq, k] host arrays -> merged [nq, k]."""
@@ -532,6 +546,21 @@ def topk_merge(ctx: Context, scores: np.ndarray, idx: np.ndarray, k: int):
     ctx._check(lib().fr_topk_merge(ctx.h, s.ctypes.data, i.ctypes.data, parts, nq, k, FR_MEM_HOST,
                                    os_.ctypes.data, oi.ctypes.data))
     return os_, oi
+
+
+def topk_merge_packed(ctx: Context, records: np.ndarray, k: int):
+    """records: [parts, nq, k] uint64 host array -> merged (scores [nq,k], idx [nq,k])."""
+    r = np.ascontiguousarray(records, np.uint64)
+    parts, nq, kk = r.shape
+    assert kk == k
+    os_ = np.zeros((nq, k), np.float32)
+    oi = np.zeros((nq, k), np.int64)
+    ctx._check(lib().fr_topk_merge_packed(ctx.h, r.ctypes.data, parts, nq, k, FR_MEM_HOST, os_.ctypes.data, oi.ctypes.data))
+    return os_, oi
+
+
+def topk_merge_packed_dev(ctx: Context, rec_ptr: int, parts: int, nq: int, k: int, os_ptr: int, oi_ptr: int):
+    ctx._check(lib().fr_topk_merge_packed(ctx.h, rec_ptr, parts, nq, k, FR_MEM_DEVICE, os_ptr, oi_ptr))
 
 
 def topk_merge_dev(ctx: Context, s_ptr: int, i_ptr: int, parts: int, nq: int, k: int, os_ptr: int, oi_ptr: int):

@@ -203,10 +203,20 @@ gallery_topk_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
 
 // Merge `parts` sorted lists of `kin` candidates per query into the top `kout`
 // (score desc, global index asc).  idx32 (local, + base) or idx64 (already global) input.
+// Packed candidate record for the rank exchange: low word = fp32 score bits, high word = global row
+// index (0xffffffff = empty slot).  One 8-byte record per candidate makes the multi-GPU exchange a
+// single all-gather.
+__device__ __forceinline__ unsigned long long pack_rec(float s, long long i) {
+  return (unsigned long long)__float_as_uint(s) | ((unsigned long long)(i < 0 ? 0xffffffffu : (uint32_t)i) << 32);
+}
+
+// rec_in (packed lists) replaces s_in / i32_in / i64_in when non-null; rec_out replaces s_out / i_out.
 __global__ void topk_merge_kernel(const float* __restrict__ s_in, const int* __restrict__ i32_in,
                                   const long long* __restrict__ i64_in, int parts, int nq, int part_stride,
                                   int kin, int kout, long long base, float* __restrict__ s_out,
-                                  long long* __restrict__ i_out) {
+                                  long long* __restrict__ i_out,
+                                  const unsigned long long* __restrict__ rec_in = nullptr,
+                                  unsigned long long* __restrict__ rec_out = nullptr) {
   const int qi = blockIdx.x * blockDim.x + threadIdx.x;
   if (qi >= nq) return;
   float ts[TOPK];
@@ -216,10 +226,18 @@ __global__ void topk_merge_kernel(const float* __restrict__ s_in, const int* __r
   for (int pt = 0; pt < parts; ++pt)
     for (int c = 0; c < kin; ++c) {
       const size_t o = ((size_t)pt * part_stride + qi) * kin + c;
-      float cs = s_in[o];
+      float cs;
       long long ci;
-      if (i64_in) ci = i64_in[o];
-      else { const int l = i32_in[o]; ci = l < 0 ? -1 : base + l; }
+      if (rec_in) {
+        const unsigned long long r = rec_in[o];
+        cs = __uint_as_float((uint32_t)r);
+        const uint32_t hi = (uint32_t)(r >> 32);
+        ci = hi == 0xffffffffu ? -1 : (long long)hi;
+      } else {
+        cs = s_in[o];
+        if (i64_in) ci = i64_in[o];
+        else { const int l = i32_in[o]; ci = l < 0 ? -1 : base + l; }
+      }
       if (ci < 0) continue;
       bool ins = false;
 #pragma unroll
@@ -233,8 +251,12 @@ __global__ void topk_merge_kernel(const float* __restrict__ s_in, const int* __r
       }
     }
   for (int j = 0; j < kout; ++j) {
-    s_out[(size_t)qi * kout + j] = ts[j];
-    i_out[(size_t)qi * kout + j] = ti[j];
+    if (rec_out) {
+      rec_out[(size_t)qi * kout + j] = pack_rec(ts[j], ti[j]);
+    } else {
+      s_out[(size_t)qi * kout + j] = ts[j];
+      i_out[(size_t)qi * kout + j] = ti[j];
+    }
   }
 }
 
@@ -285,7 +307,7 @@ struct fr_gallery {
   fr_ctx* ctx = nullptr;
   bf16* rows = nullptr;
   int64_t cap = 0, size = 0, base = 0;
-  DevBuf q_bf16, q_f32, part_s, part_i, out_s, out_i;
+  DevBuf q_bf16, q_f32, part_s, part_i, out_s, out_i, rec_local, rec_all;
   int* err_flag = nullptr;
 };
 
@@ -324,7 +346,7 @@ void fr_gallery_destroy(fr_gallery* g) {
     cudaFree(g->rows);
     cudaFree(g->err_flag);
     g->q_bf16.release(); g->q_f32.release(); g->part_s.release(); g->part_i.release();
-    g->out_s.release(); g->out_i.release();
+    g->out_s.release(); g->out_i.release(); g->rec_local.release(); g->rec_all.release();
   }
   delete g;
 }
@@ -465,11 +487,13 @@ int fr_gallery_remove(fr_gallery* g, int64_t row) {
   return FR_OK;
 }
 
-int fr_gallery_search(fr_gallery* g, const float* queries, int nq, int k, int memspace, float* out_scores,
-                      int64_t* out_idx) {
-  if (!g || !queries || !out_scores || !out_idx || nq <= 0 || k <= 0 || k > TOPK) return FR_ERR_INVALID_ARG;
+}  // extern "C"
+
+// Local search of one shard, everything enqueued on ctx->stream (caller holds the ctx lock).
+// Results: (d_os, d_oi) device arrays, or packed records d_rec (then d_os / d_oi are ignored).
+static int gallery_search_local(fr_gallery* g, const float* queries, int nq, int k, int memspace, float* d_os,
+                                long long* d_oi, unsigned long long* d_rec) {
   fr_ctx* ctx = g->ctx;
-  GGuard gg(ctx);
   const int num_sms = ctx->num_sms;
   FR_CUDA_OK(ctx, fr_opt_in_smem(ctx, gallery_topk_kernel, G_SMEM));
   const int num_m_tiles = ceil_div(nq, tc::BM);
@@ -494,14 +518,6 @@ int fr_gallery_search(fr_gallery* g, const float* queries, int nq, int k, int me
     FR_CUDA_OK(ctx, cudaMemsetAsync(g->q_bf16.as<bf16>() + (size_t)nq * DIM, 0, (size_t)(nq_pad - nq) * DIM * 2, ctx->stream));
   rows_to_bf16_kernel<<<148 * 2, 256, 0, ctx->stream>>>(d_q, g->q_bf16.as<bf16>(), (size_t)nq * DIM);
   ctx->launches++;
-  float* d_os = out_scores;
-  long long* d_oi = reinterpret_cast<long long*>(out_idx);
-  if (memspace != FR_MEM_DEVICE) {
-    if (!g->out_s.reserve((size_t)nq * k * 4) || !g->out_i.reserve((size_t)nq * k * 8))
-      return fr_fail(ctx, FR_ERR_CUDA, "search allocation failed");
-    d_os = g->out_s.as<float>();
-    d_oi = g->out_i.as<long long>();
-  }
   if (n_tiles > 0) {
     CUtensorMap tmQ, tmG;
     const uint64_t g_rows = (uint64_t)((g->cap + GN - 1) / GN * GN);
@@ -524,10 +540,131 @@ int fr_gallery_search(fr_gallery* g, const float* queries, int nq, int k, int me
   }
   topk_merge_kernel<<<ceil_div(nq, 128), 128, 0, ctx->stream>>>(
       g->part_s.as<float>(), g->part_i.as<int>(), nullptr, n_tiles > 0 ? splits : 0, nq, nq_pad, TOPK, k,
-      (long long)g->base, d_os, d_oi);
+      (long long)g->base, d_os, d_oi, nullptr, d_rec);
   ctx->launches++;
   FR_CUDA_OK(ctx, cudaGetLastError());
   ctx->stage_end();
+  return FR_OK;
+}
+
+// ncclAllGather, resolved at run time: the library does not link NCCL.  A C++ host that links
+// libnccl (or a process that already loaded it globally) is found through RTLD_DEFAULT, so the
+// communicator the caller created and the collective we call belong to the same NCCL instance;
+// otherwise libnccl.so.2 is opened.
+#include <dlfcn.h>
+typedef int (*NcclAllGatherFn)(const void*, void*, size_t, int, void*, cudaStream_t);
+static NcclAllGatherFn resolve_nccl_allgather() {
+  static NcclAllGatherFn fn = [] {
+    void* s = dlsym(RTLD_DEFAULT, "ncclAllGather");
+    if (!s) {
+      void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+      if (h) s = dlsym(h, "ncclAllGather");
+    }
+    return reinterpret_cast<NcclAllGatherFn>(s);
+  }();
+  return fn;
+}
+
+extern "C" {
+
+int fr_gallery_search(fr_gallery* g, const float* queries, int nq, int k, int memspace, float* out_scores,
+                      int64_t* out_idx) {
+  if (!g || !queries || !out_scores || !out_idx || nq <= 0 || k <= 0 || k > TOPK) return FR_ERR_INVALID_ARG;
+  fr_ctx* ctx = g->ctx;
+  GGuard gg(ctx);
+  float* d_os = out_scores;
+  long long* d_oi = reinterpret_cast<long long*>(out_idx);
+  if (memspace != FR_MEM_DEVICE) {
+    if (!g->out_s.reserve((size_t)nq * k * 4) || !g->out_i.reserve((size_t)nq * k * 8))
+      return fr_fail(ctx, FR_ERR_CUDA, "search allocation failed");
+    d_os = g->out_s.as<float>();
+    d_oi = g->out_i.as<long long>();
+  }
+  FR_CHECK(gallery_search_local(g, queries, nq, k, memspace, d_os, d_oi, nullptr));
+  if (memspace != FR_MEM_DEVICE) {
+    FR_CUDA_OK(ctx, cudaMemcpyAsync(out_scores, d_os, (size_t)nq * k * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    FR_CUDA_OK(ctx, cudaMemcpyAsync(out_idx, d_oi, (size_t)nq * k * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    FR_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+  }
+  return FR_OK;
+}
+
+int fr_gallery_search_packed(fr_gallery* g, const float* queries, int nq, int k, int memspace, uint64_t* out_records) {
+  if (!g || !queries || !out_records || nq <= 0 || k <= 0 || k > TOPK) return FR_ERR_INVALID_ARG;
+  fr_ctx* ctx = g->ctx;
+  GGuard gg(ctx);
+  if (g->base + g->size > 0xfffffffeLL) return fr_fail(ctx, FR_ERR_UNSUPPORTED, "packed records hold 32-bit row indices");
+  unsigned long long* d_rec = reinterpret_cast<unsigned long long*>(out_records);
+  if (memspace != FR_MEM_DEVICE) {
+    if (!g->rec_local.reserve((size_t)nq * k * 8)) return fr_fail(ctx, FR_ERR_CUDA, "search allocation failed");
+    d_rec = g->rec_local.as<unsigned long long>();
+  }
+  FR_CHECK(gallery_search_local(g, queries, nq, k, memspace, nullptr, nullptr, d_rec));
+  if (memspace != FR_MEM_DEVICE) {
+    FR_CUDA_OK(ctx, cudaMemcpyAsync(out_records, d_rec, (size_t)nq * k * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    FR_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+  }
+  return FR_OK;
+}
+
+int fr_topk_merge_packed(fr_ctx* ctx, const uint64_t* records, int parts, int nq, int k, int memspace,
+                         float* out_scores, int64_t* out_idx) {
+  if (!ctx || !records || !out_scores || !out_idx || parts <= 0 || nq <= 0 || k <= 0 || k > TOPK)
+    return fr_fail(ctx, FR_ERR_INVALID_ARG, "bad merge arguments");
+  GGuard gg(ctx);
+  const size_t n_in = (size_t)parts * nq * k;
+  const unsigned long long* d_r = reinterpret_cast<const unsigned long long*>(records);
+  float* d_os = out_scores;
+  long long* d_oi = reinterpret_cast<long long*>(out_idx);
+  if (memspace != FR_MEM_DEVICE) {
+    if (!ctx->misc[11].reserve(n_in * 8) || !ctx->misc[8].reserve((size_t)nq * k * 4) ||
+        !ctx->misc[9].reserve((size_t)nq * k * 8))
+      return fr_fail(ctx, FR_ERR_CUDA, "merge allocation failed");
+    FR_CUDA_OK(ctx, cudaMemcpyAsync(ctx->misc[11].p, records, n_in * 8, cudaMemcpyHostToDevice, ctx->stream));
+    d_r = ctx->misc[11].as<unsigned long long>();
+    d_os = ctx->misc[8].as<float>();
+    d_oi = ctx->misc[9].as<long long>();
+  }
+  topk_merge_kernel<<<ceil_div(nq, 128), 128, 0, ctx->stream>>>(nullptr, nullptr, nullptr, parts, nq, nq, k, k, 0, d_os,
+                                                               d_oi, d_r, nullptr);
+  ctx->launches++;
+  FR_CUDA_OK(ctx, cudaGetLastError());
+  if (memspace != FR_MEM_DEVICE) {
+    FR_CUDA_OK(ctx, cudaMemcpyAsync(out_scores, d_os, (size_t)nq * k * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    FR_CUDA_OK(ctx, cudaMemcpyAsync(out_idx, d_oi, (size_t)nq * k * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    FR_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+  }
+  return FR_OK;
+}
+
+int fr_gallery_search_sharded(fr_gallery* g, void* nccl_comm, int world, const float* queries, int nq, int k,
+                              int memspace, float* out_scores, int64_t* out_idx) {
+  if (!g || !nccl_comm || world <= 0 || !queries || !out_scores || !out_idx || nq <= 0 || k <= 0 || k > TOPK)
+    return FR_ERR_INVALID_ARG;
+  fr_ctx* ctx = g->ctx;
+  GGuard gg(ctx);
+  if (g->base + g->size > 0xfffffffeLL) return fr_fail(ctx, FR_ERR_UNSUPPORTED, "packed records hold 32-bit row indices");
+  NcclAllGatherFn all_gather = resolve_nccl_allgather();
+  if (!all_gather) return fr_fail(ctx, FR_ERR_UNSUPPORTED, "ncclAllGather not found (libnccl.so.2 is not loadable)");
+  const size_t rec_bytes = (size_t)nq * k * 8;
+  if (!g->rec_local.reserve(rec_bytes) || !g->rec_all.reserve(rec_bytes * world))
+    return fr_fail(ctx, FR_ERR_CUDA, "search allocation failed");
+  float* d_os = out_scores;
+  long long* d_oi = reinterpret_cast<long long*>(out_idx);
+  if (memspace != FR_MEM_DEVICE) {
+    if (!g->out_s.reserve((size_t)nq * k * 4) || !g->out_i.reserve((size_t)nq * k * 8))
+      return fr_fail(ctx, FR_ERR_CUDA, "search allocation failed");
+    d_os = g->out_s.as<float>();
+    d_oi = g->out_i.as<long long>();
+  }
+  FR_CHECK(gallery_search_local(g, queries, nq, k, memspace, nullptr, nullptr, g->rec_local.as<unsigned long long>()));
+  // ONE all-gather of 8-byte {score, global index} records over NVLink / NVSwitch (rank-major result)
+  const int nccl_status = all_gather(g->rec_local.p, g->rec_all.p, rec_bytes, /*ncclUint8*/ 1, nccl_comm, ctx->stream);
+  if (nccl_status != 0) return fr_fail(ctx, FR_ERR_CUDA, "ncclAllGather failed with status " + std::to_string(nccl_status));
+  topk_merge_kernel<<<ceil_div(nq, 128), 128, 0, ctx->stream>>>(nullptr, nullptr, nullptr, world, nq, nq, k, k, 0, d_os,
+                                                               d_oi, g->rec_all.as<unsigned long long>(), nullptr);
+  ctx->launches++;
+  FR_CUDA_OK(ctx, cudaGetLastError());
   if (memspace != FR_MEM_DEVICE) {
     FR_CUDA_OK(ctx, cudaMemcpyAsync(out_scores, d_os, (size_t)nq * k * 4, cudaMemcpyDeviceToHost, ctx->stream));
     FR_CUDA_OK(ctx, cudaMemcpyAsync(out_idx, d_oi, (size_t)nq * k * 8, cudaMemcpyDeviceToHost, ctx->stream));

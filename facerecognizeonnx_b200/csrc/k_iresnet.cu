@@ -921,7 +921,7 @@ static int rec_build_plan(fr_ctx* ctx, int cap) {
 // plan's buffers, and only the last chunked block writes its output at the chunk's offset in the
 // full-batch tensor.  29 faces: 29 * 57 * 57 / 128 = 736.1 -> 737 tiles = 4.98 waves of 148 CTAs.
 // Same kernels, same per-element accumulation order: results are bit-identical to the unchunked run.
-static int rec_chunk_faces() { static const int v = env_flag("FR_REC_CHUNK", 29); return v; }
+static int rec_chunk_faces() { static const int v = env_flag("FR_REC_CHUNK", 0); return v; }
 static int rec_chunk_blocks() { static const int v = env_flag("FR_REC_CHUNK_BLOCKS", 3); return v; }
 
 static int rec_launch_stem(fr_ctx* ctx, const uint8_t* d_crops, int n) {

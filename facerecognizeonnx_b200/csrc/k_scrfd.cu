@@ -1885,7 +1885,7 @@ int det_forward(fr_ctx* ctx, const __nv_bfloat16* d_in_chw, int n, HeadPtrs* hea
   int cap = 1;
   while (cap < n) cap *= 2;
   FR_CHECK(det_build_acts(ctx, cap));
-  static const int chunk = env_int("FR_DET_CHUNK", 8);
+  static const int chunk = env_int("FR_DET_CHUNK", 0);
   static const int chunk_layers = std::min(std::max(env_int("FR_DET_CHUNK_LAYERS", 4), 1), 15);
   const int n_backbone = 15;   // stem, b0, 13 dw-separable blocks
   int front = n_backbone;      // layers run by det_front

@@ -175,62 +175,109 @@ __device__ __forceinline__ int tap(const uint8_t* base, long long step, int rows
   return base[(long long)y * step + x * 3 + ch];
 }
 
-// grid (REC/4, n_faces), block (REC, 4): one thread per output pixel.
-__global__ void __launch_bounds__(REC * 4)
-align_warp_kernel(const AlignRec* __restrict__ recs, const ImgDesc* __restrict__ descs,
-                  uint8_t* __restrict__ crops, int* __restrict__ valid) {
-  const int face = blockIdx.y;
-  const AlignRec& r = recs[face];
-  const int mode = r.mode;
-  const int x = threadIdx.x, y = blockIdx.x * 4 + threadIdx.y;
-  uint8_t* o = crops + ((size_t)face * REC * REC + (size_t)y * REC + x) * 3;
-  if (valid && valid[face] == 0) {
-    o[0] = o[1] = o[2] = 0;
-    return;
-  }
-  if (mode == 2) {
-    o[0] = o[1] = o[2] = 0;
-    if (x == 0 && y == 0 && valid) valid[face] = 0;
-    return;
-  }
-  const ImgDesc d = descs[r.img];
-  if (mode == 1) {
-    const uint8_t* src = d.ptr + (long long)r.cy * d.step + (long long)r.cx * 3;
-    if (r.cw == REC && r.ch == REC) {
-      const uint8_t* p = src + (long long)y * d.step + x * 3;
-      o[0] = p[0]; o[1] = p[1]; o[2] = p[2];
-      return;
-    }
-    const AxisCoef cy = axis_coef(y, REC, r.ch, false);
-    const AxisCoef cx = axis_coef(x, REC, r.cw, true);
-    const uint8_t* r0 = src + (long long)cy.i0 * d.step;
-    const uint8_t* r1 = src + (long long)cy.i1 * d.step;
-#pragma unroll
-    for (int ch = 0; ch < 3; ++ch) o[ch] = (uint8_t)resize_px(r0, r1, cx, cy, ch);
-    return;
-  }
-  // mode 0: fixed-point affine warp
-  const double A11 = r.inv[0], A12 = r.inv[1], b1 = r.inv[2];
-  const double A21 = r.inv[3], A22 = r.inv[4], b2 = r.inv[5];
-  const int adelta = __double2int_rn(A11 * (double)x * 1024.0);
-  const int bdelta = __double2int_rn(A21 * (double)x * 1024.0);
-  const int X0 = __double2int_rn((A12 * (double)y + b1) * 1024.0) + 16;
-  const int Y0 = __double2int_rn((A22 * (double)y + b2) * 1024.0) + 16;
-  const int X = (int)((unsigned)X0 + (unsigned)adelta) >> 5;
-  const int Y = (int)((unsigned)Y0 + (unsigned)bdelta) >> 5;
-  const int ix = min(max(X >> 5, -32768), 32767);
-  const int iy = min(max(Y >> 5, -32768), 32767);
-  const int fx = X & 31, fy = Y & 31;
+// Six consecutive source bytes (two BGR pixels) starting at `p`, fetched with three aligned 32-bit
+// loads and funnel shifts: lo = bytes 0..3, hi = bytes 4..7 (4 and 5 are used).
+__device__ __forceinline__ void load6(const uint8_t* p, uint32_t& lo, uint32_t& hi) {
+  const uintptr_t a = reinterpret_cast<uintptr_t>(p);
+  const uint32_t* w = reinterpret_cast<const uint32_t*>(a & ~(uintptr_t)3);
+  const uint32_t sh = (uint32_t)(a & 3) * 8;
+  const uint32_t w0 = __ldg(w), w1 = __ldg(w + 1), w2 = __ldg(w + 2);
+  lo = __funnelshift_r(w0, w1, sh);
+  hi = __funnelshift_r(w1, w2, sh);
+}
+
+// One output pixel of cv::warpAffine (INTER_LINEAR, BORDER_CONSTANT 0) given its fixed-point source
+// coordinate: returns B | G << 8 | R << 16.
+__device__ __forceinline__ uint32_t warp_px(const ImgDesc& d, int ix, int iy, int fx, int fy) {
   const int w00 = (32 - fx) * (32 - fy) * 32, w10 = fx * (32 - fy) * 32;
   const int w01 = (32 - fx) * fy * 32, w11 = fx * fy * 32;
+  uint32_t out = 0;
+  if (ix >= 1 && iy >= 0 && ix + 3 < d.cols && iy + 1 < d.rows) {
+    // interior: the 2 x 2 taps are 2 rows x 6 contiguous bytes (the aligned 12-byte windows stay inside the row)
+    const uint8_t* p0 = d.ptr + (long long)iy * d.step + ix * 3;
+    uint32_t lo0, hi0, lo1, hi1;
+    load6(p0, lo0, hi0);
+    load6(p0 + d.step, lo1, hi1);
+#pragma unroll
+    for (int ch = 0; ch < 3; ++ch) {
+      const int t00 = (lo0 >> (8 * ch)) & 0xff, t01 = (lo1 >> (8 * ch)) & 0xff;
+      const int t10 = ch == 0 ? (lo0 >> 24) : (hi0 >> (8 * (ch - 1))) & 0xff;
+      const int t11 = ch == 0 ? (lo1 >> 24) : (hi1 >> (8 * (ch - 1))) & 0xff;
+      const int acc = w00 * t00 + w10 * t10 + w01 * t01 + w11 * t11;
+      out |= (uint32_t)((acc + (1 << 14)) >> 15) << (8 * ch);
+    }
+    return out;
+  }
 #pragma unroll
   for (int ch = 0; ch < 3; ++ch) {
     const int acc = w00 * tap(d.ptr, d.step, d.rows, d.cols, iy, ix, ch) +
                     w10 * tap(d.ptr, d.step, d.rows, d.cols, iy, ix + 1, ch) +
                     w01 * tap(d.ptr, d.step, d.rows, d.cols, iy + 1, ix, ch) +
                     w11 * tap(d.ptr, d.step, d.rows, d.cols, iy + 1, ix + 1, ch);
-    o[ch] = (uint8_t)((acc + (1 << 14)) >> 15);
+    out |= (uint32_t)((acc + (1 << 14)) >> 15) << (8 * ch);
   }
+  return out;
+}
+
+// grid (REC / WARP_ROWS, n_faces), block (REC / 4, WARP_ROWS): one thread = 4 consecutive output
+// pixels of a row = 12 output bytes, written as three 32-bit words (a warp's stores are contiguous).
+constexpr int WARP_ROWS = 8;
+__global__ void __launch_bounds__((REC / 4) * WARP_ROWS)
+align_warp_kernel(const AlignRec* __restrict__ recs, const ImgDesc* __restrict__ descs,
+                  uint8_t* __restrict__ crops, int* __restrict__ valid) {
+  const int face = blockIdx.y;
+  const AlignRec& r = recs[face];
+  const int mode = r.mode;
+  const int x0 = threadIdx.x * 4, y = blockIdx.x * WARP_ROWS + threadIdx.y;
+  uint32_t* o = reinterpret_cast<uint32_t*>(crops + ((size_t)face * REC * REC + (size_t)y * REC + x0) * 3);
+  uint32_t px[4] = {0u, 0u, 0u, 0u};   // B | G << 8 | R << 16 per pixel
+  const bool dead = (valid && valid[face] == 0) || mode == 2;
+  if (mode == 2 && x0 == 0 && y == 0 && valid && valid[face] != 0) valid[face] = 0;
+  if (!dead) {
+    const ImgDesc d = descs[r.img];
+    if (mode == 1) {
+      // crop (box & image) + cv::resize (src/face_recognizer.cpp:116-127)
+      const uint8_t* src = d.ptr + (long long)r.cy * d.step + (long long)r.cx * 3;
+      if (r.cw == REC && r.ch == REC) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const uint8_t* p = src + (long long)y * d.step + (x0 + j) * 3;
+          px[j] = p[0] | (p[1] << 8) | (p[2] << 16);
+        }
+      } else {
+        const AxisCoef cy = axis_coef(y, REC, r.ch, false);
+        const uint8_t* r0 = src + (long long)cy.i0 * d.step;
+        const uint8_t* r1 = src + (long long)cy.i1 * d.step;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const AxisCoef cx = axis_coef(x0 + j, REC, r.cw, true);
+#pragma unroll
+          for (int ch = 0; ch < 3; ++ch) px[j] |= (uint32_t)(resize_px(r0, r1, cx, cy, ch) & 0xff) << (8 * ch);
+        }
+      }
+    } else {
+      // mode 0: fixed-point affine warp (10-bit coordinates, 5-bit sub-pixel)
+      const double A11 = r.inv[0], A12 = r.inv[1], b1 = r.inv[2];
+      const double A21 = r.inv[3], A22 = r.inv[4], b2 = r.inv[5];
+      const int X0 = __double2int_rn((A12 * (double)y + b1) * 1024.0) + 16;
+      const int Y0 = __double2int_rn((A22 * (double)y + b2) * 1024.0) + 16;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int x = x0 + j;
+        const int adelta = __double2int_rn(A11 * (double)x * 1024.0);
+        const int bdelta = __double2int_rn(A21 * (double)x * 1024.0);
+        const int X = (int)((unsigned)X0 + (unsigned)adelta) >> 5;
+        const int Y = (int)((unsigned)Y0 + (unsigned)bdelta) >> 5;
+        const int ix = min(max(X >> 5, -32768), 32767);
+        const int iy = min(max(Y >> 5, -32768), 32767);
+        px[j] = warp_px(d, ix, iy, X & 31, Y & 31);
+      }
+    }
+  }
+  // 4 pixels x 3 bytes -> 3 words
+  o[0] = px[0] | (px[1] << 24);
+  o[1] = (px[1] >> 8) | (px[2] << 16);
+  o[2] = (px[2] >> 16) | (px[3] << 8);
 }
 
 }  // namespace
@@ -261,7 +308,7 @@ int k_align_select(fr_ctx* ctx, const fr_face* d_det, const int* d_n_det, int ca
 int k_align_warp(fr_ctx* ctx, const AlignRec* d_rec, int n_faces, const ImgDesc* d_desc,
                  uint8_t* d_crops, int* d_valid) {
   if (n_faces <= 0) return FR_OK;
-  dim3 grid(REC / 4, n_faces), block(REC, 4);
+  dim3 grid(REC / WARP_ROWS, n_faces), block(REC / 4, WARP_ROWS);
   align_warp_kernel<<<grid, block, 0, ctx->stream>>>(d_rec, d_desc, d_crops, d_valid);
   ctx->launches++;
   FR_CUDA_OK(ctx, cudaGetLastError());

@@ -251,11 +251,19 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
   return *reinterpret_cast<uint32_t*>(&h);
 }
 
-// Epilogue of one output tile for one thread (= one accumulator row): TMEM -> registers ->
-// bias / PReLU / residual -> global.  All 32 lanes of the warp must call it (tcgen05.ld).
-template <int BN>
-__device__ __forceinline__ void epilogue_tile(const Params& p, uint32_t taddr0, int m, int n0, int split,
-                                              int c_begin, int c_end) {
+// Per-row epilogue geometry (one thread = one accumulator row).  Depends only on the tile
+// coordinates, not on the accumulator, so it -- and the first residual loads -- are issued BEFORE the
+// epilogue warp waits for the tile's MMAs: on the 64 / 128-channel conv2 layers the residual comes from
+// DRAM (~1 us) while a tile's MMAs take 0.9 us, and with only two TMEM buffers that latency was exposed.
+struct EpiRow {
+  bool valid, write_even, has_res;
+  int cls;
+  size_t out_off, even_off;
+  const __nv_bfloat16* res;   // residual row (this thread's row, column n0), or null
+};
+
+__device__ __forceinline__ EpiRow epi_row(const Params& p, int m, int n0, int split) {
+  EpiRow r;
   bool valid = m < p.m_rows;
   int img = 0, hp = 0, wp = 0;
   if (valid && p.out_mode != OUT_F32) {
@@ -266,25 +274,51 @@ __device__ __forceinline__ void epilogue_tile(const Params& p, uint32_t taddr0, 
     wp = rem - hp * p.Wp;
     valid = hp < p.H && wp < p.W;
   }
-  int cls = 0;
+  r.cls = 0;
   if (p.bias_classes == 9)
-    cls = (hp == 0 ? 0 : (hp == p.H - 1 ? 2 : 1)) * 3 + (wp == 0 ? 0 : (wp == p.W - 1 ? 2 : 1));
-  const float* bias = p.bias + (size_t)cls * p.cout + n0;
-  const float bias_on = split == 0 ? 1.f : 0.f;
-  size_t out_off = 0, even_off = 0;
-  bool write_even = false;
+    r.cls = (hp == 0 ? 0 : (hp == p.H - 1 ? 2 : 1)) * 3 + (wp == 0 ? 0 : (wp == p.W - 1 ? 2 : 1));
+  r.out_off = 0;
+  r.even_off = 0;
+  r.write_even = false;
   if (p.out_mode == OUT_STD) {
-    out_off = (size_t)m * p.cout + n0;
+    r.out_off = (size_t)m * p.cout + n0;
     if (p.out_even && valid && !(hp & 1) && !(wp & 1)) {
-      write_even = true;
-      even_off = ((size_t)(img * p.Hp2 + (hp >> 1)) * p.Wp2 + (wp >> 1)) * p.cout + n0;
+      r.write_even = true;
+      r.even_off = ((size_t)(img * p.Hp2 + (hp >> 1)) * p.Wp2 + (wp >> 1)) * p.cout + n0;
     }
   } else if (p.out_mode == OUT_S2D) {
-    out_off = (((size_t)(img * p.Hp2 + (hp >> 1)) * p.Wp2 + (wp >> 1)) * 4 +
-               (size_t)((hp & 1) * 2 + (wp & 1))) * p.cout + n0;
+    r.out_off = (((size_t)(img * p.Hp2 + (hp >> 1)) * p.Wp2 + (wp >> 1)) * 4 +
+                 (size_t)((hp & 1) * 2 + (wp & 1))) * p.cout + n0;
   } else {
-    out_off = (size_t)split * p.split_stride + (size_t)m * p.cout + n0;
+    r.out_off = (size_t)split * p.split_stride + (size_t)m * p.cout + n0;
   }
+  r.valid = valid;
+  r.has_res = valid && p.residual != nullptr && p.out_mode != OUT_F32;
+  r.res = r.has_res ? p.residual + (size_t)m * p.cout + n0 : nullptr;
+  return r;
+}
+
+// the 32 residual values (64 bytes) of chunk c of this thread's row; streaming: keep L1 for the bias rows
+__device__ __forceinline__ void epi_load_res(const EpiRow& r, int c, uint4 (&rv)[4]) {
+  if (r.has_res) {
+    const uint4* g = reinterpret_cast<const uint4*>(r.res + c * 32);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) rv[i] = __ldcs(g + i);
+  }
+}
+
+// Epilogue of one output tile for one thread (= one accumulator row): TMEM -> registers ->
+// bias / PReLU / residual -> global.  All 32 lanes of the warp must call it (tcgen05.ld).
+// rv holds the residual of chunk c_begin (epi_load_res, issued by the caller before its wait).
+template <int BN>
+__device__ __forceinline__ void epilogue_tile(const Params& p, const EpiRow& er, uint32_t taddr0, int n0, int split,
+                                              int c_begin, int c_end, uint4 (&rv)[4]) {
+  const bool valid = er.valid;
+  const float* bias = p.bias + (size_t)er.cls * p.cout + n0;
+  const float bias_on = split == 0 ? 1.f : 0.f;
+  const size_t out_off = er.out_off, even_off = er.even_off;
+  const bool write_even = er.write_even;
+  const bool has_res = er.has_res;
 #pragma unroll 1
   for (int c = c_begin; c < c_end; ++c) {
     // TMEM load first, then every global load the chunk needs (bias, PReLU slopes, residual:
@@ -292,8 +326,8 @@ __device__ __forceinline__ void epilogue_tile(const Params& p, uint32_t taddr0, 
     uint32_t v[32];
     tmem_ld32<false>(taddr0 + c * 32, v);
     float4 b4[8], s4[8];
-    uint4 rv[4];
-    const bool has_res = valid && p.residual != nullptr && p.out_mode != OUT_F32;
+    uint4 rn[4];
+    if (c + 1 < c_end) epi_load_res(er, c + 1, rn);   // next chunk's residual under this chunk's work
     if (valid) {
 #pragma unroll
       for (int i = 0; i < 8; ++i) b4[i] = __ldg(reinterpret_cast<const float4*>(bias + c * 32 + i * 4));
@@ -305,11 +339,6 @@ __device__ __forceinline__ void epilogue_tile(const Params& p, uint32_t taddr0, 
 #pragma unroll
           for (int i = 0; i < 8; ++i) s4[i] = __ldg(reinterpret_cast<const float4*>(p.prelu + n0 + c * 32 + i * 4));
         }
-      }
-      if (has_res) {
-        const uint4* r = reinterpret_cast<const uint4*>(p.residual + (size_t)m * p.cout + n0 + c * 32);
-#pragma unroll
-        for (int i = 0; i < 4; ++i) rv[i] = __ldcs(r + i);   // streaming: keep L1 for the bias / PReLU rows
       }
     }
     tmem_wait_ld();
@@ -364,6 +393,10 @@ __device__ __forceinline__ void epilogue_tile(const Params& p, uint32_t taddr0, 
           for (int i = 0; i < 4; ++i) __stcs(oe + i, pk[i]);
         }
       }
+    }
+    if (c + 1 < c_end && has_res) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) rv[i] = rn[i];
     }
   }
 }
@@ -505,10 +538,13 @@ shift_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
       tile_coords(p, tile, m_tile, n_tile, split);
       const uint32_t acc = it & 1u;
       const uint32_t acc_phase = (it >> 1) & 1u;
+      const EpiRow er = epi_row(p, m_tile * BM + row, n_tile * BN, split);
+      uint4 rv[4];
+      epi_load_res(er, c_begin, rv);
       mbar_wait(&tfull[acc], acc_phase, p.err_flag);
       tc_fence_after();
       const uint32_t taddr0 = tmem_base + acc * BN + ((uint32_t)(q * 32) << 16);
-      epilogue_tile<BN>(p, taddr0, m_tile * BM + row, n_tile * BN, split, c_begin, c_begin + CPS);
+      epilogue_tile<BN>(p, er, taddr0, n_tile * BN, split, c_begin, c_begin + CPS, rv);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty[acc]);
@@ -727,12 +763,20 @@ halo_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const int cb = nlen == BN ? c_begin : ((warp - 2) >> 2) * cps;
       const uint32_t acc = C::ACC_STAGES == 2 ? (it & 1u) : 0u;
       const uint32_t acc_phase = C::ACC_STAGES == 2 ? ((it >> 1) & 1u) : (it & 1u);
+      // row geometry + the first residual loads go out before the wait for this tile's MMAs
+      EpiRow er = epi_row(p, m0 + row, n0, 0);
+      uint4 rv[4];
+      epi_load_res(er, cb, rv);
       mbar_wait(&tfull[acc], acc_phase, p.err_flag);
       tc_fence_after();
 #pragma unroll 1
       for (int mt = 0; mt < MT; ++mt) {
         const uint32_t taddr0 = tmem_base + acc * (MT * BN) + mt * BN + ((uint32_t)(q * 32) << 16);
-        epilogue_tile<BN>(p, taddr0, m0 + mt * BM + row, n0, 0, cb, cb + cps);
+        epilogue_tile<BN>(p, er, taddr0, n0, 0, cb, cb + cps, rv);
+        if (mt + 1 < MT) {
+          er = epi_row(p, m0 + (mt + 1) * BM + row, n0, 0);
+          epi_load_res(er, cb, rv);
+        }
       }
       tc_fence_before();
       __syncwarp();

@@ -46,3 +46,20 @@ def sharded_search(local_search: Callable, merge: Callable, queries, k: int, gro
     dist.all_gather_into_tensor(gs, s.contiguous(), group=group)   # rank-major concatenation
     dist.all_gather_into_tensor(gi, i.contiguous(), group=group)
     return merge(gs.view(world, nq, -1), gi.view(world, nq, -1), k)
+
+
+def sharded_search_packed(local_search_packed: Callable, merge_packed: Callable, queries, k: int, group=None):
+    """The same exchange with ONE collective: local_search_packed(queries, k) -> int64 tensor [nq, k]
+    of packed records (low word fp32 score bits, high word global row index; include/fr_capi.h
+    fr_gallery_search_packed), all-gathered rank-major, then merge_packed(records [W, nq, k], k)."""
+    import torch
+    import torch.distributed as dist
+
+    rec = local_search_packed(queries, k)
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    if world == 1:
+        return merge_packed(rec.unsqueeze(0), k)
+    nq = rec.shape[0]
+    gathered = torch.empty((world * nq, rec.shape[1]), dtype=rec.dtype, device=rec.device)
+    dist.all_gather_into_tensor(gathered, rec.contiguous(), group=group)
+    return merge_packed(gathered.view(world, nq, -1), k)

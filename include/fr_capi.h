@@ -173,6 +173,24 @@ FR_API int fr_gallery_search(fr_gallery* g, const float* queries, int nq, int k,
 /* Merge `parts` per-shard top-k lists [parts][nq][k] (as gathered over NCCL) into [nq][k]. */
 FR_API int fr_topk_merge(fr_ctx* ctx, const float* scores, const int64_t* idx, int parts, int nq,
                          int k, int memspace, float* out_scores, int64_t* out_idx);
+/* Row-sharded search across GPUs (one rank per GPU, each holding rows [index_base, index_base +
+ * size) of the global gallery).  Every rank calls this with the same queries:
+ * local fused GEMM + top-k with global indices -> ONE ncclAllGather of packed 8-byte
+ * {fp32 score, uint32 global index} records over NVLink -> rank merge (score desc, global index
+ * asc) on every rank, so the result is identical on all ranks and independent of `world`.
+ * `nccl_comm` is the caller's ncclComm_t for ctx's device (void* so this header needs no nccl.h);
+ * the library resolves ncclAllGather from the NCCL already in the process (else libnccl.so.2).
+ * Asynchronous on ctx's stream when memspace == FR_MEM_DEVICE. */
+FR_API int fr_gallery_search_sharded(fr_gallery* g, void* nccl_comm, int world, const float* queries,
+                                     int nq, int k, int memspace, float* out_scores,
+                                     int64_t* out_idx);
+/* The two halves of the above for hosts whose collective layer is not raw NCCL (e.g.
+ * torch.distributed): the local search emitting packed records [nq][k], and the merge of
+ * gathered records [parts][nq][k]. */
+FR_API int fr_gallery_search_packed(fr_gallery* g, const float* queries, int nq, int k, int memspace,
+                                    uint64_t* out_records);
+FR_API int fr_topk_merge_packed(fr_ctx* ctx, const uint64_t* records, int parts, int nq, int k,
+                                int memspace, float* out_scores, int64_t* out_idx);
 
 /* -------------------------------------------------------- instrumentation --
  * CUDA-event timing of each stage on the ctx stream (what bench.py's roofline block uses).

@@ -283,9 +283,11 @@ def trained_like_det(seed: int = 0, probe: int = 1, pos_frac: float = 2.5e-3) ->
     for i in range(3):
         h = f"h{i}"
         t1 = taps[len(taps) - 3 + i]
-        w[h + ".reg.w"] *= np.float32(0.3)
+        # distances / landmark offsets in stride units, sized like a trained head's (a face spans a few
+        # strides; its landmarks lie inside the box): |bbox| <~ 3, |kps| <~ 3
+        w[h + ".reg.w"] *= np.float32(0.2)
         w[h + ".reg.b"] = (rng.normal(1.5, 0.3, 8)).astype(np.float32)
-        w[h + ".kps.w"] *= np.float32(0.5)
+        w[h + ".kps.w"] *= np.float32(0.2)
         w[h + ".kps.b"] = rng.normal(0, 0.3, 20).astype(np.float32)
         # score logits: std 1.5, bias at the (1 - pos_frac) quantile so that fraction exceeds 0.5
         logit = F.conv2d(t1, torch.from_numpy(w[h + ".cls.w"]), None, padding=1)

@@ -61,6 +61,22 @@ def main():
 
     s, i = sharding.sharded_search(local_search, merge, qd, k)
     torch.cuda.synchronize()
+
+    # the single-all-gather exchange (packed 8-byte records) must give the same answer
+    def local_packed(queries, kk):
+        rec = torch.empty(nq, kk, dtype=torch.int64, device=dev)
+        gal.search_packed_dev(queries.data_ptr(), nq, kk, rec.data_ptr())
+        return rec
+
+    def merge_packed(rec, kk):
+        ss = torch.empty(nq, kk, dtype=torch.float32, device=dev)
+        ii = torch.empty(nq, kk, dtype=torch.int64, device=dev)
+        capi.topk_merge_packed_dev(ctx, rec.contiguous().data_ptr(), rec.shape[0], nq, kk, ss.data_ptr(), ii.data_ptr())
+        return ss, ii
+
+    s2, i2 = sharding.sharded_search_packed(local_packed, merge_packed, qd, k)
+    torch.cuda.synchronize()
+    assert torch.equal(s, s2) and torch.equal(i, i2)
     s, i = s.cpu().numpy(), i.cpu().numpy()
     ref_s, ref_i = ogal.topk(q, g, k)
     assert np.allclose(s, ref_s, atol=2e-5), float(np.abs(s - ref_s).max())

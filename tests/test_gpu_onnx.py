@@ -51,9 +51,20 @@ def test_scrfd_heads_from_onnx_file_vs_cv2_dnn(onnx_models):
     ref = dnn_det.heads(x)
     errs = [float(np.abs(g - r).max()) for g, r in zip(got, ref)]
     print(kind, "head max abs err vs cv2.dnn:", errs)
-    assert max(errs[:3]) < 1e-5, errs                                  # sigmoid scores
+    assert max(errs[:3]) < 2e-5, errs                                  # sigmoid scores
     px = [e * s for e, s in zip(errs[3:], (8, 16, 32, 8, 16, 32))]
     assert max(px) < 1e-3, px                                          # boxes / landmarks in pixels
+    # the yardstick: how far are the two fp32 engines from the float64 evaluation of the same graph?
+    import torch
+    from oracle import nets
+    w = ow.seeded(ow.MODEL_DET, SEED) if kind == "seeded" else ow.trained_like_det(7)
+    with nets.reference_precision():
+        ref64 = [h.numpy() for h in nets.scrfd_forward(w, torch.from_numpy(x.astype(np.float64)))]
+    e_gpu = [float(np.abs(g - r).max()) for g, r in zip(got, ref64)]
+    e_dnn = [float(np.abs(g - r).max()) for g, r in zip(ref, ref64)]
+    print(kind, "err vs float64: gpu", e_gpu, "cv2.dnn", e_dnn)
+    for k in range(9):   # fp32-grade: within 4x of the fp32 CPU engine's own rounding error (+ 1 ulp-ish floor)
+        assert e_gpu[k] <= 4 * e_dnn[k] + 2e-6, (k, e_gpu[k], e_dnn[k])
 
 
 def test_detect_from_onnx_file_vs_cv2_dnn(onnx_models):
