@@ -71,3 +71,74 @@ def test_sharded_search_is_rank_count_invariant():
         s, i = out[r]
         assert np.array_equal(i, ref_i)
         assert np.allclose(s, ref_s, atol=1e-6)
+
+
+# ------------------------------------------------------------------ rebalancing --
+class _NumpyShard:
+    """CPU stand-in for capi.Gallery with the same add / get_rows / remove semantics (bf16 storage,
+    remove = move the last row into the hole)."""
+
+    def __init__(self):
+        self.rows = np.zeros((0, 512), np.float32)
+
+    def __len__(self):
+        return self.rows.shape[0]
+
+    def add(self, rows):
+        self.rows = np.concatenate([self.rows, ogal.to_bf16_f32(rows)])
+
+    def get_rows(self, first, n):
+        return self.rows[first:first + n].copy()
+
+    def remove(self, row):
+        self.rows[row] = self.rows[-1]
+        self.rows = self.rows[:-1]
+
+
+def test_rebalance_plan_properties():
+    rng = np.random.default_rng(0)
+    for _ in range(200):
+        w = int(rng.integers(1, 9))
+        sizes = [int(x) for x in rng.integers(0, 1000, w)]
+        moves = sharding.rebalance_plan(sizes)
+        after = list(sizes)
+        for s, d, n in moves:
+            assert n > 0 and s != d and after[s] >= n
+            after[s] -= n
+            after[d] += n
+        assert sum(after) == sum(sizes) and max(after) - min(after) <= 1
+        assert len(moves) <= max(w - 1, 0)
+        # minimal traffic: exactly the surplus over the balanced sizes moves
+        assert sum(n for _, _, n in moves) == sum(max(0, a - b) for a, b in zip(sizes, after))
+    assert sharding.rebalance_plan([5, 5, 5]) == []
+
+
+def test_sharded_index_remove_and_rebalance_keep_search_results():
+    """Enrol -> remove many records from one shard -> rebalance: shard sizes even out, every surviving
+    record is still found as its own top-1 with the right id, removed ids never come back."""
+    rng = np.random.default_rng(1)
+    world, per = 4, 120
+    rows = rng.normal(size=(world * per, 512)).astype(np.float32)
+    rows /= np.linalg.norm(rows, axis=1, keepdims=True)
+    bases = [r * 1000 for r in range(world)]
+    idx = sharding.ShardedGalleryIndex([_NumpyShard() for _ in range(world)], bases)
+    for r in range(world):
+        idx.add(r, rows[r * per:(r + 1) * per], list(range(r * per, (r + 1) * per)))
+    removed = [int(i) for i in rng.choice(np.arange(0, per), 90, replace=False)] + [130, 250]   # mostly shard 0
+    for rid in removed:
+        assert idx.remove_id(rid)
+    assert not idx.remove_id(removed[0])
+    assert idx.sizes() == [30, 119, 119, 120]
+    moves = idx.rebalance()
+    assert moves and max(idx.sizes()) - min(idx.sizes()) <= 1 and sum(idx.sizes()) == world * per - 92
+
+    def search(q, k):
+        parts = [ogal.topk(q, s.rows, k, index_base=b) for s, b in zip(idx.shards, bases)]
+        return ogal.merge_topk([p[0] for p in parts], [p[1] for p in parts], k)
+
+    alive = [i for i in range(world * per) if i not in set(removed)]
+    s, gi = search(rows[alive], 3)
+    found = [idx.resolve(int(g)) for g in gi[:, 0]]
+    assert found == alive and np.all(s[:, 0] > 0.99)
+    s, gi = search(rows[removed], 1)
+    assert all(idx.resolve(int(g)) not in set(removed) for g in gi[:, 0]) and np.all(s[:, 0] < 0.5)

@@ -139,3 +139,39 @@ def test_gallery_save_load_remove_roundtrip(ctx, capi, tmp_path):
     open(bad, "wb").write(b"not a gallery")
     with pytest.raises(capi.FrError):
         c.load(bad)
+
+
+def test_remove_then_rebalance_across_shards_keeps_results(ctx, capi):
+    """enrolment with removal + shard rebalancing on real galleries (four shards on one
+    GPU standing in for four ranks): after the plan runs, sizes differ by <= 1 row, every surviving
+    record is its own top-1 under its id, moved rows are bit-identical, removed ids are gone."""
+    from facerecognizeonnx_b200 import sharding
+    rng = np.random.default_rng(11)
+    world, per = 4, 300
+    rows = rng.normal(size=(world * per, 512)).astype(np.float32)
+    rows /= np.linalg.norm(rows, axis=1, keepdims=True)
+    bases = [r * 100000 for r in range(world)]
+    shards = [capi.Gallery(ctx, 2 * per, index_base=b) for b in bases]
+    idx = sharding.ShardedGalleryIndex(shards, bases)
+    for r in range(world):
+        idx.add(r, rows[r * per:(r + 1) * per], list(range(r * per, (r + 1) * per)))
+    removed = set(int(i) for i in rng.choice(np.arange(0, per), 250, replace=False)) | {per + 7, 3 * per + 1}
+    for rid in removed:
+        assert idx.remove_id(rid)
+    before = {rid: shards[r].get_rows(j, 1)[0] for r, t in enumerate(idx.ids) for j, rid in enumerate(t)}
+    assert [len(s) for s in shards] == idx.sizes() == [50, 299, 300, 299]
+    moves = idx.rebalance()
+    assert moves and max(idx.sizes()) - min(idx.sizes()) <= 1 and [len(s) for s in shards] == idx.sizes()
+    after = {rid: shards[r].get_rows(j, 1)[0] for r, t in enumerate(idx.ids) for j, rid in enumerate(t)}
+    assert set(after) == set(before) and all(np.array_equal(after[k], before[k]) for k in after)   # bit-exact moves
+    alive = sorted(after)
+    k = 3
+    parts = [s.search(rows[alive], k) for s in shards]
+    ms, mi = capi.topk_merge(ctx, np.stack([p[0] for p in parts]), np.stack([p[1] for p in parts]), k)
+    assert [idx.resolve(int(g)) for g in mi[:, 0]] == alive and np.all(ms[:, 0] > 0.99)
+    gone = sorted(removed)
+    parts = [s.search(rows[gone], 1) for s in shards]
+    ms, mi = capi.topk_merge(ctx, np.stack([p[0] for p in parts]), np.stack([p[1] for p in parts]), 1)
+    assert all(idx.resolve(int(g)) not in removed for g in mi[:, 0]) and np.all(ms[:, 0] < 0.5)
+    for s in shards:
+        s.close()
