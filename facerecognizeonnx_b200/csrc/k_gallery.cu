@@ -18,11 +18,15 @@
 #include <cstring>
 #include <vector>
 
+#include <cuda_fp8.h>
+
 #include "common.h"
 #include "tc_gemm.cuh"
 
 bool tc_make_map_2d(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols,
                     uint64_t pitch_elems, uint32_t box_rows);
+bool tc_make_map_2d_u8(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols,
+                       uint64_t pitch_bytes, uint32_t box_rows);
 
 namespace {
 
@@ -35,6 +39,13 @@ constexpr int G_STAGES = 3;
 constexpr int G_B_BYTES = GN * tc::BK * 2;             // 32 KB
 constexpr int G_A_BYTES = KB * tc::A_TILE_BYTES;       // 128 KB
 constexpr int G_SMEM = G_A_BYTES + G_STAGES * G_B_BYTES + 256 + 1024;
+// e4m3 coarse pass (kind::f8f6f4, K = 32 per MMA): a 128-byte swizzle row holds 128 elements, so the
+// 512-d rows are 4 K blocks; operand tiles have the same byte sizes, the resident query tile is half.
+// Values are stored as e4m3(x * 2^6): unit-norm 512-d rows have |x| ~ 0.044, which would sit on e4m3's
+// subnormal edge (min normal 2^-6); the power-of-two scale is undone exactly on the accumulator.
+constexpr int KB8 = DIM / 128;
+constexpr float FP8_SCALE = 64.f;
+constexpr float FP8_INV_SCALE2 = 1.f / (FP8_SCALE * FP8_SCALE);
 
 struct GParams {
   int n_rows;           // gallery rows in this shard
@@ -48,10 +59,38 @@ struct GParams {
   int* err_flag;
 };
 
+// Packed candidate record for the rank exchange: low word = fp32 score bits, high word = global row
+// index (0xffffffff = empty slot).  One 8-byte record per candidate makes the multi-GPU exchange a
+// single all-gather.
+__device__ __forceinline__ unsigned long long pack_rec(float s, long long i) {
+  return (unsigned long long)__float_as_uint(s) | ((unsigned long long)(i < 0 ? 0xffffffffu : (uint32_t)i) << 32);
+}
+
+// kind::f8f6f4 instruction descriptor: e4m3 x e4m3 -> fp32, both operands K-major (a_format = b_format = 0)
+__host__ __device__ constexpr uint32_t make_idesc_e4m3(int m, int n) {
+  return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+__device__ __forceinline__ void mma_e4m3(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                         uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f8f6f4 [%0], %1, %2, %3, p;\n\t}"
+      :
+      : "r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+// FP8 = false: bf16 operands (kind::f16, 8 K blocks of 64); FP8 = true: e4m3 operands (kind::f8f6f4, 4 K
+// blocks of 128), scores rescaled by 2^-12 on the way out.
+template <bool FP8>
 __global__ void __launch_bounds__(tc::NUM_THREADS, 1)
 gallery_topk_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmG,
                     const __grid_constant__ GParams p) {
   using namespace tc;
+  constexpr int KB = FP8 ? KB8 : ::KB;                 // K blocks per row
+  constexpr int KSTEP = FP8 ? 128 : BK;                // elements per K block (128 bytes either way)
+  constexpr int G_A_BYTES = KB * tc::A_TILE_BYTES;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
@@ -92,20 +131,20 @@ gallery_topk_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   if (warp == 0) {
     if (lane == 0) {
       mbar_expect_tx(afull, G_A_BYTES);
-      for (int kb = 0; kb < KB; ++kb) tma_load_2d(sA + kb * A_TILE_BYTES, &tmQ, afull, kb * BK, m_tile * BM);
+      for (int kb = 0; kb < KB; ++kb) tma_load_2d(sA + kb * A_TILE_BYTES, &tmQ, afull, kb * KSTEP, m_tile * BM);
       int stage = 0;
       uint32_t phase = 0;
       for (int t = t_begin; t < t_end; ++t)
         for (int kb = 0; kb < KB; ++kb) {
           mbar_wait(&empty[stage], phase ^ 1u, p.err_flag);
           mbar_expect_tx(&full[stage], G_B_BYTES);
-          tma_load_2d(sB + stage * G_B_BYTES, &tmG, &full[stage], kb * BK, t * GN);
+          tma_load_2d(sB + stage * G_B_BYTES, &tmG, &full[stage], kb * KSTEP, t * GN);
           if (++stage == G_STAGES) { stage = 0; phase ^= 1u; }
         }
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc(BM, GN);
+      constexpr uint32_t idesc = FP8 ? make_idesc_e4m3(BM, GN) : make_idesc(BM, GN);
       mbar_wait(afull, 0, p.err_flag);
       tc_fence_after();
       int stage = 0;
@@ -120,9 +159,12 @@ gallery_topk_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
           tc_fence_after();
           const uint64_t adesc = make_smem_desc(sA + kb * A_TILE_BYTES);
           const uint64_t bdesc = make_smem_desc(sB + stage * G_B_BYTES);
+          // four MMAs per K block either way: K = 16 bf16 or K = 32 e4m3 = 32 bytes = +2 descriptor units
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k)
-            mma_bf16(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | k) ? 1u : 0u);
+          for (int k = 0; k < 4; ++k) {
+            if (FP8) mma_e4m3(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | k) ? 1u : 0u);
+            else mma_bf16(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | k) ? 1u : 0u);
+          }
           tc_commit(&empty[stage]);
           if (++stage == G_STAGES) { stage = 0; phase ^= 1u; }
         }
@@ -190,7 +232,7 @@ gallery_topk_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       float* os = p.out_s + ((size_t)split * p.nq_pad + row) * TOPK;
       int* oi = p.out_i + ((size_t)split * p.nq_pad + row) * TOPK;
 #pragma unroll
-      for (int j = 0; j < TOPK; ++j) { os[j] = ts[j]; oi[j] = ti[j]; }
+      for (int j = 0; j < TOPK; ++j) { os[j] = FP8 ? ts[j] * FP8_INV_SCALE2 : ts[j]; oi[j] = ti[j]; }
     }
   }
   tc_fence_before();
@@ -201,15 +243,135 @@ gallery_topk_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   }
 }
 
-// Merge `parts` sorted lists of `kin` candidates per query into the top `kout`
-// (score desc, global index asc).  idx32 (local, + base) or idx64 (already global) input.
-// Packed candidate record for the rank exchange: low word = fp32 score bits, high word = global row
-// index (0xffffffff = empty slot).  One 8-byte record per candidate makes the multi-GPU exchange a
-// single all-gather.
-__device__ __forceinline__ unsigned long long pack_rec(float s, long long i) {
-  return (unsigned long long)__float_as_uint(s) | ((unsigned long long)(i < 0 ? 0xffffffffu : (uint32_t)i) << 32);
+// fp32 / bf16 rows -> e4m3(x * 2^6), saturating
+__global__ void rows_to_e4m3_kernel(const float* __restrict__ in_f32, const bf16* __restrict__ in_bf16,
+                                    uint8_t* __restrict__ out, size_t n) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) {
+    const float v = in_f32 ? in_f32[i] : __bfloat162float(in_bf16[i]);
+    out[i] = (uint8_t)__nv_cvt_float_to_fp8(v * FP8_SCALE, __NV_SATFINITE, __NV_E4M3);
+  }
 }
 
+// Reduce `parts` per-split candidate lists to `groups` lists (group g merges parts [g*ppg, (g+1)*ppg)) by
+// coarse score, keeping local indices: bounds the re-rank's candidate set at groups * TOPK when a small
+// query batch is spread over many splits.
+__global__ void coarse_group_merge_kernel(const float* __restrict__ s_in, const int* __restrict__ i_in, int parts,
+                                          int ppg, int nq, int part_stride, float* __restrict__ s_out,
+                                          int* __restrict__ i_out) {
+  const int qi = blockIdx.x * blockDim.x + threadIdx.x;
+  const int g = blockIdx.y;
+  if (qi >= nq) return;
+  float ts[TOPK];
+  int ti[TOPK];
+#pragma unroll
+  for (int j = 0; j < TOPK; ++j) { ts[j] = -INFINITY; ti[j] = -1; }
+  for (int pt = g * ppg; pt < min((g + 1) * ppg, parts); ++pt)
+    for (int c = 0; c < TOPK; ++c) {
+      const size_t o = ((size_t)pt * part_stride + qi) * TOPK + c;
+      float cs = s_in[o];
+      int ci = i_in[o];
+      if (ci < 0) continue;
+      bool ins = false;
+#pragma unroll
+      for (int j = 0; j < TOPK; ++j) {
+        const bool better = ins || ti[j] < 0 || cs > ts[j] || (cs == ts[j] && ci < ti[j]);
+        if (better) {
+          const float fs = ts[j]; ts[j] = cs; cs = fs;
+          const int fi = ti[j]; ti[j] = ci; ci = fi;
+          ins = true;
+        }
+      }
+    }
+  const size_t o = ((size_t)g * part_stride + qi) * TOPK;
+#pragma unroll
+  for (int j = 0; j < TOPK; ++j) { s_out[o + j] = ts[j]; i_out[o + j] = ti[j]; }
+}
+
+// Exact re-rank of the coarse candidates: one warp per query.  The candidate set is the union of
+// `parts` (<= RERANK_MAX_PARTS) top-16 lists of the e4m3 pass (local row indices, -1 = empty).  Each
+// candidate's score is recomputed from the bf16 row and the bf16 query with fp32 accumulation, then the
+// top `kout` are selected by (score desc, global index asc).
+constexpr int RERANK_MAX_PARTS = 8;      // 128 candidates = 4 per lane
+__global__ void __launch_bounds__(256)
+rerank_kernel(const bf16* __restrict__ q, const bf16* __restrict__ rows, const int* __restrict__ cand, int parts,
+              int nq, int part_stride, int kout, long long base, float* __restrict__ s_out,
+              long long* __restrict__ i_out, unsigned long long* __restrict__ rec_out) {
+  const int qi = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (qi >= nq) return;
+  // this lane's 16 query values (2 x 16-byte loads): dims [lane*8, +8) and [256 + lane*8, +8)
+  float qv[16];
+  {
+    const uint4 a = *reinterpret_cast<const uint4*>(q + (size_t)qi * DIM + lane * 8);
+    const uint4 b = *reinterpret_cast<const uint4*>(q + (size_t)qi * DIM + 256 + lane * 8);
+    const uint32_t w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      qv[2 * j] = __uint_as_float(w[j] << 16);
+      qv[2 * j + 1] = __uint_as_float(w[j] & 0xffff0000u);
+    }
+  }
+  const int n_cand = parts * TOPK;
+  float my_s[4];
+  long long my_i[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) { my_s[j] = -INFINITY; my_i[j] = -1; }
+  for (int c = 0; c < n_cand; ++c) {
+    const int pt = c / TOPK, e = c - pt * TOPK;
+    const int l = cand[((size_t)pt * part_stride + qi) * TOPK + e];
+    if (l < 0) continue;                    // warp-uniform
+    const bf16* r = rows + (size_t)l * DIM;
+    const uint4 a = __ldg(reinterpret_cast<const uint4*>(r + lane * 8));
+    const uint4 b = __ldg(reinterpret_cast<const uint4*>(r + 256 + lane * 8));
+    const uint32_t w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+    float acc = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      acc = fmaf(qv[2 * j], __uint_as_float(w[j] << 16), acc);
+      acc = fmaf(qv[2 * j + 1], __uint_as_float(w[j] & 0xffff0000u), acc);
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+    if ((c & 31) == lane) {
+      const int slot = c >> 5;
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (j == slot) { my_s[j] = acc; my_i[j] = base + l; }
+    }
+  }
+  // kout rounds of warp arg-max over (score desc, index asc)
+  for (int k = 0; k < kout; ++k) {
+    float bs = -INFINITY;
+    long long bi = -1;
+    int bj = -1;
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if (my_i[j] >= 0 && (bi < 0 || my_s[j] > bs || (my_s[j] == bs && my_i[j] < bi))) { bs = my_s[j]; bi = my_i[j]; bj = j; }
+    float ws = bs;
+    long long wi = bi;
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+      const float os = __shfl_xor_sync(0xffffffffu, ws, off);
+      const long long oi = __shfl_xor_sync(0xffffffffu, wi, off);
+      if (oi >= 0 && (wi < 0 || os > ws || (os == ws && oi < wi))) { ws = os; wi = oi; }
+    }
+    if (wi >= 0 && wi == bi) {            // the winner's owner retires it (candidate indices are unique)
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (j == bj) my_i[j] = -1;
+    }
+    if (lane == 0) {
+      const float fs = wi < 0 ? -INFINITY : ws;
+      if (rec_out) rec_out[(size_t)qi * kout + k] = pack_rec(fs, wi);
+      else { s_out[(size_t)qi * kout + k] = fs; i_out[(size_t)qi * kout + k] = wi; }
+    }
+  }
+}
+
+// Merge `parts` sorted lists of `kin` candidates per query into the top `kout`
+// (score desc, global index asc).  idx32 (local, + base) or idx64 (already global) input.
 // rec_in (packed lists) replaces s_in / i32_in / i64_in when non-null; rec_out replaces s_out / i_out.
 __global__ void topk_merge_kernel(const float* __restrict__ s_in, const int* __restrict__ i32_in,
                                   const long long* __restrict__ i64_in, int parts, int nq, int part_stride,
@@ -305,9 +467,12 @@ __global__ void bf16_rows_to_f32_kernel(const bf16* __restrict__ in, float* __re
 
 struct fr_gallery {
   fr_ctx* ctx = nullptr;
-  bf16* rows = nullptr;
+  bf16* rows = nullptr;        // bf16 rows: HBM, or mapped pinned host memory (FR_GALLERY_BF16_ON_HOST)
+  uint8_t* rows8 = nullptr;    // e4m3(x * 64) rows for the coarse pass (FR_GALLERY_FP8), HBM
+  void* rows_host = nullptr;   // the host allocation behind `rows` in BF16_ON_HOST mode
+  int flags = 0;
   int64_t cap = 0, size = 0, base = 0;
-  DevBuf q_bf16, q_f32, part_s, part_i, out_s, out_i, rec_local, rec_all;
+  DevBuf q_bf16, q_f32, q_e4m3, part_s, part_i, grp_s, grp_i, out_s, out_i, rec_local, rec_all;
   int* err_flag = nullptr;
 };
 

@@ -57,6 +57,21 @@ bool tc_make_map_2d(CUtensorMap* map, const void* base, uint64_t rows, uint64_t 
   return r == CUDA_SUCCESS;
 }
 
+// 2-D byte tensor map [rows, cols] (e4m3 operands), box = box_rows x 128 (128-byte rows), SW128.
+bool tc_make_map_2d_u8(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols,
+                       uint64_t pitch_bytes, uint32_t box_rows) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return false;
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {pitch_bytes};
+  cuuint32_t box[2] = {128, box_rows};
+  cuuint32_t es[2] = {1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void*>(base), dims, strides,
+                  box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
+}
+
 // 2-D fp32 tensor map [rows, cols], box = box_rows x 32 (128-byte rows), SW128 (tf32 operands).
 bool tc_make_map_2d_f32(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols,
                         uint64_t pitch_elems, uint32_t box_rows) {
