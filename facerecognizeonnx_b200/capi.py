@@ -41,6 +41,7 @@ SYMBOLS = [
     "fr_gallery_create", "fr_gallery_destroy", "fr_gallery_add", "fr_gallery_fill_synthetic",
     "fr_gallery_get_rows", "fr_gallery_size", "fr_gallery_search", "fr_topk_merge",
     "fr_gallery_search_sharded", "fr_gallery_search_packed", "fr_topk_merge_packed",
+    "fr_gallery_create_ex", "fr_gallery_search_fp8", "fr_gallery_search_packed_fp8",
     "fr_gallery_save", "fr_gallery_load", "fr_gallery_remove",
     "fr_det_preprocess", "fr_scrfd_forward", "fr_scrfd_decode_nms", "fr_estimate_alignment",
     "fr_align_faces", "fr_warp_affine", "fr_resize_linear", "fr_iresnet_forward", "fr_iresnet_tap",
@@ -120,6 +121,9 @@ def _declare(L: C.CDLL) -> None:
     L.fr_gallery_search_sharded.argtypes = [vp, vp, i32, vp, i32, i32, i32, vp, vp]
     L.fr_gallery_search_packed.argtypes = [vp, vp, i32, i32, i32, vp]
     L.fr_topk_merge_packed.argtypes = [vp, vp, i32, i32, i32, i32, vp, vp]
+    L.fr_gallery_create_ex.argtypes = [vp, C.POINTER(vp), i64, i64, i32]
+    L.fr_gallery_search_fp8.argtypes = [vp, vp, i32, i32, i32, vp, vp]
+    L.fr_gallery_search_packed_fp8.argtypes = [vp, vp, i32, i32, i32, vp]
     L.fr_det_preprocess.argtypes = [vp, vp, vp, vp, vp, i32, i32, vp, vp]
     L.fr_scrfd_forward.argtypes = [vp, vp, i32, vp]
     L.fr_scrfd_decode_nms.argtypes = [vp, vp, i32, vp, f32, f32, vp, i32, vp]
@@ -473,10 +477,12 @@ class Gallery:
     """1:N gallery shard on one GPU (fr_gallery_*).  index_base is the global index of local
     row 0, so search results carry global indices."""
 
-    def __init__(self, ctx: Context, capacity_rows: int, index_base: int = 0):
+    FP8, BF16_ON_HOST = 1, 2     # include/fr_capi.h FR_GALLERY_*
+
+    def __init__(self, ctx: Context, capacity_rows: int, index_base: int = 0, flags: int = 0):
         h = C.c_void_p()
-        ctx._check(lib().fr_gallery_create(ctx.h, C.byref(h), capacity_rows, index_base))
-        self.h, self.ctx, self.index_base = h, ctx, index_base
+        ctx._check(lib().fr_gallery_create_ex(ctx.h, C.byref(h), capacity_rows, index_base, flags))
+        self.h, self.ctx, self.index_base, self.flags = h, ctx, index_base, flags
 
     def close(self):
         if getattr(self, "h", None):
@@ -523,6 +529,21 @@ class Gallery:
 
     def search_dev(self, q_ptr: int, nq: int, k: int, out_s_ptr: int, out_i_ptr: int):
         self.ctx._check(lib().fr_gallery_search(self.h, q_ptr, nq, k, FR_MEM_DEVICE, out_s_ptr, out_i_ptr))
+
+    def search_fp8(self, queries: np.ndarray, k: int = 10):
+        """e4m3 coarse pass + exact bf16 re-rank (gallery created with Gallery.FP8)."""
+        q = np.ascontiguousarray(queries, np.float32)
+        nq = q.shape[0]
+        s = np.zeros((nq, k), np.float32)
+        i = np.zeros((nq, k), np.int64)
+        self.ctx._check(lib().fr_gallery_search_fp8(self.h, q.ctypes.data, nq, k, FR_MEM_HOST, s.ctypes.data, i.ctypes.data))
+        return s, i
+
+    def search_fp8_dev(self, q_ptr: int, nq: int, k: int, out_s_ptr: int, out_i_ptr: int):
+        self.ctx._check(lib().fr_gallery_search_fp8(self.h, q_ptr, nq, k, FR_MEM_DEVICE, out_s_ptr, out_i_ptr))
+
+    def search_packed_fp8_dev(self, q_ptr: int, nq: int, k: int, out_rec_ptr: int):
+        self.ctx._check(lib().fr_gallery_search_packed_fp8(self.h, q_ptr, nq, k, FR_MEM_DEVICE, out_rec_ptr))
 
     def search_packed(self, queries: np.ndarray, k: int = 10) -> np.ndarray:
         """Local top-k as packed records (uint64: low word fp32 score bits, high word global index)."""

@@ -249,7 +249,7 @@ __global__ void rows_to_e4m3_kernel(const float* __restrict__ in_f32, const bf16
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   const size_t stride = (size_t)gridDim.x * blockDim.x;
   for (; i < n; i += stride) {
-    const float v = in_f32 ? in_f32[i] : __bfloat162float(in_bf16[i]);
+    const float v = in_f32 ? __bfloat162float(__float2bfloat16_rn(in_f32[i])) : __bfloat162float(in_bf16[i]);
     out[i] = (uint8_t)__nv_cvt_float_to_fp8(v * FP8_SCALE, __NV_SATFINITE, __NV_E4M3);
   }
 }
@@ -486,21 +486,50 @@ struct GGuard {
 
 extern "C" {
 
-int fr_gallery_create(fr_ctx* ctx, fr_gallery** out, int64_t capacity_rows, int64_t index_base) {
+int fr_gallery_create_ex(fr_ctx* ctx, fr_gallery** out, int64_t capacity_rows, int64_t index_base, int flags) {
   if (!ctx || !out || capacity_rows <= 0) return fr_fail(ctx, FR_ERR_INVALID_ARG, "bad gallery arguments");
+  if ((flags & ~(FR_GALLERY_FP8 | FR_GALLERY_BF16_ON_HOST)) || ((flags & FR_GALLERY_BF16_ON_HOST) && !(flags & FR_GALLERY_FP8)))
+    return fr_fail(ctx, FR_ERR_INVALID_ARG, "bad gallery flags (BF16_ON_HOST needs FP8)");
   GGuard g(ctx);
   std::unique_ptr<fr_gallery> G(new fr_gallery());
   G->ctx = ctx;
   G->cap = capacity_rows;
   G->base = index_base;
+  G->flags = flags;
   // round the allocation up to a whole tile so TMA boxes never leave the allocation
   const size_t alloc_rows = ((size_t)capacity_rows + GN - 1) / GN * GN;
-  if (cudaMalloc(&G->rows, alloc_rows * DIM * 2) != cudaSuccess || cudaMalloc(&G->err_flag, 4) != cudaSuccess)
+  bool ok = cudaMalloc(&G->err_flag, 4) == cudaSuccess;
+  if (flags & FR_GALLERY_BF16_ON_HOST) {
+    // capacity mode: only the e4m3 rows live in HBM (512 B / row); the bf16 rows the re-rank reads sit in
+    // mapped pinned host memory (unified addressing: the kernels dereference the same pointer)
+    ok = ok && cudaHostAlloc(&G->rows_host, alloc_rows * DIM * 2, cudaHostAllocMapped | cudaHostAllocPortable) == cudaSuccess;
+    if (ok) {
+      memset(G->rows_host, 0, alloc_rows * DIM * 2);
+      void* dp = nullptr;
+      ok = cudaHostGetDevicePointer(&dp, G->rows_host, 0) == cudaSuccess;
+      G->rows = reinterpret_cast<bf16*>(dp);
+    }
+  } else {
+    ok = ok && cudaMalloc(&G->rows, alloc_rows * DIM * 2) == cudaSuccess;
+    if (ok) cudaMemsetAsync(G->rows, 0, alloc_rows * DIM * 2, ctx->stream);
+  }
+  if (flags & FR_GALLERY_FP8) {
+    ok = ok && cudaMalloc(&G->rows8, alloc_rows * DIM) == cudaSuccess;
+    if (ok) cudaMemsetAsync(G->rows8, 0, alloc_rows * DIM, ctx->stream);
+  }
+  if (!ok) {
+    if (G->rows_host) cudaFreeHost(G->rows_host); else if (G->rows) cudaFree(G->rows);
+    if (G->rows8) cudaFree(G->rows8);
+    if (G->err_flag) cudaFree(G->err_flag);
     return fr_fail(ctx, FR_ERR_CUDA, "gallery allocation failed");
-  cudaMemsetAsync(G->rows, 0, alloc_rows * DIM * 2, ctx->stream);
+  }
   cudaMemsetAsync(G->err_flag, 0, 4, ctx->stream);
   *out = G.release();
   return FR_OK;
+}
+
+int fr_gallery_create(fr_ctx* ctx, fr_gallery** out, int64_t capacity_rows, int64_t index_base) {
+  return fr_gallery_create_ex(ctx, out, capacity_rows, index_base, FR_GALLERY_BF16);
 }
 
 void fr_gallery_destroy(fr_gallery* g) {
@@ -508,7 +537,9 @@ void fr_gallery_destroy(fr_gallery* g) {
   {
     GGuard gg(g->ctx);
     cudaStreamSynchronize(g->ctx->stream);
-    cudaFree(g->rows);
+    if (g->rows_host) cudaFreeHost(g->rows_host); else cudaFree(g->rows);
+    if (g->rows8) cudaFree(g->rows8);
+    g->q_e4m3.release(); g->grp_s.release(); g->grp_i.release();
     cudaFree(g->err_flag);
     g->q_bf16.release(); g->q_f32.release(); g->part_s.release(); g->part_i.release();
     g->out_s.release(); g->out_i.release(); g->rec_local.release(); g->rec_all.release();
@@ -532,6 +563,10 @@ int fr_gallery_add(fr_gallery* g, const float* rows, int64_t n, int memspace) {
   }
   rows_to_bf16_kernel<<<148 * 4, 256, 0, ctx->stream>>>(d_rows, g->rows + (size_t)g->size * DIM, elems);
   ctx->launches++;
+  if (g->rows8) {   // e4m3 mirror of the bf16-rounded values (what a save -> load round trip would quantise)
+    rows_to_e4m3_kernel<<<148 * 4, 256, 0, ctx->stream>>>(d_rows, nullptr, g->rows8 + (size_t)g->size * DIM, elems);
+    ctx->launches++;
+  }
   FR_CUDA_OK(ctx, cudaGetLastError());
   if (memspace != FR_MEM_DEVICE) FR_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
   g->size += n;
@@ -546,6 +581,11 @@ int fr_gallery_fill_synthetic(fr_gallery* g, int64_t n, uint64_t seed) {
   const unsigned blocks = (unsigned)((n + 7) / 8);
   fill_synthetic_kernel<<<blocks, 256, 0, ctx->stream>>>(g->rows, g->size, n, seed, g->base);
   ctx->launches++;
+  if (g->rows8) {
+    rows_to_e4m3_kernel<<<148 * 8, 256, 0, ctx->stream>>>(nullptr, g->rows + (size_t)g->size * DIM,
+                                                          g->rows8 + (size_t)g->size * DIM, (size_t)n * DIM);
+    ctx->launches++;
+  }
   FR_CUDA_OK(ctx, cudaGetLastError());
   g->size += n;
   return FR_OK;
@@ -595,7 +635,7 @@ int fr_gallery_save(fr_gallery* g, const char* path) {
   FR_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
   for (int64_t r = 0; ok && r < g->size; r += kIoChunkRows) {
     const size_t n = (size_t)std::min<int64_t>(kIoChunkRows, g->size - r);
-    if (cudaMemcpy(buf.data(), g->rows + (size_t)r * DIM, n * DIM * 2, cudaMemcpyDeviceToHost) != cudaSuccess) ok = false;
+    if (cudaMemcpy(buf.data(), g->rows + (size_t)r * DIM, n * DIM * 2, cudaMemcpyDefault) != cudaSuccess) ok = false;
     ok = ok && fwrite(buf.data(), 2, n * DIM, f) == n * DIM;
   }
   ok = (fclose(f) == 0) && ok;
@@ -626,12 +666,18 @@ int fr_gallery_load(fr_gallery* g, const char* path, int64_t* file_index_base) {
   for (int64_t r = 0; ok && r < h.rows; r += kIoChunkRows) {
     const size_t n = (size_t)std::min<int64_t>(kIoChunkRows, h.rows - r);
     ok = fread(buf.data(), 2, n * DIM, f) == n * DIM;
-    if (ok && cudaMemcpy(g->rows + (size_t)(g->size + r) * DIM, buf.data(), n * DIM * 2, cudaMemcpyHostToDevice) !=
+    if (ok && cudaMemcpy(g->rows + (size_t)(g->size + r) * DIM, buf.data(), n * DIM * 2, cudaMemcpyDefault) !=
                   cudaSuccess)
       ok = false;
   }
   fclose(f);
   if (!ok) return fr_fail(ctx, FR_ERR_IO, std::string("short read: ") + path);
+  if (g->rows8 && h.rows > 0) {
+    rows_to_e4m3_kernel<<<148 * 8, 256, 0, ctx->stream>>>(nullptr, g->rows + (size_t)g->size * DIM,
+                                                          g->rows8 + (size_t)g->size * DIM, (size_t)h.rows * DIM);
+    ctx->launches++;
+    FR_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+  }
   g->size += h.rows;
   if (file_index_base) *file_index_base = h.index_base;
   return FR_OK;
@@ -648,6 +694,12 @@ int fr_gallery_remove(fr_gallery* g, int64_t row) {
     FR_CUDA_OK(ctx, cudaMemcpyAsync(g->rows + (size_t)row * DIM, g->rows + (size_t)last * DIM, DIM * 2,
                                     cudaMemcpyDeviceToDevice, ctx->stream));
   FR_CUDA_OK(ctx, cudaMemsetAsync(g->rows + (size_t)last * DIM, 0, DIM * 2, ctx->stream));
+  if (g->rows8) {
+    if (row != last)
+      FR_CUDA_OK(ctx, cudaMemcpyAsync(g->rows8 + (size_t)row * DIM, g->rows8 + (size_t)last * DIM, DIM,
+                                      cudaMemcpyDeviceToDevice, ctx->stream));
+    FR_CUDA_OK(ctx, cudaMemsetAsync(g->rows8 + (size_t)last * DIM, 0, DIM, ctx->stream));
+  }
   g->size = last;
   return FR_OK;
 }
@@ -656,11 +708,18 @@ int fr_gallery_remove(fr_gallery* g, int64_t row) {
 
 // Local search of one shard, everything enqueued on ctx->stream (caller holds the ctx lock).
 // Results: (d_os, d_oi) device arrays, or packed records d_rec (then d_os / d_oi are ignored).
+// fp8 = true: coarse pass on the e4m3 rows (kind::f8f6f4, twice the MMA rate, half the bytes), then an exact
+// bf16 re-rank of the union of the per-split top-16 lists (up to 128 candidates per query).
 static int gallery_search_local(fr_gallery* g, const float* queries, int nq, int k, int memspace, float* d_os,
-                                long long* d_oi, unsigned long long* d_rec) {
+                                long long* d_oi, unsigned long long* d_rec, bool fp8 = false) {
   fr_ctx* ctx = g->ctx;
   const int num_sms = ctx->num_sms;
-  FR_CUDA_OK(ctx, fr_opt_in_smem(ctx, gallery_topk_kernel, G_SMEM));
+  constexpr int G_SMEM8 = KB8 * tc::A_TILE_BYTES + G_STAGES * G_B_BYTES + 256 + 1024;
+  if (fp8 && !g->rows8) return fr_fail(ctx, FR_ERR_UNSUPPORTED, "gallery was created without FR_GALLERY_FP8");
+  if (!fp8 && (g->flags & FR_GALLERY_BF16_ON_HOST))
+    return fr_fail(ctx, FR_ERR_UNSUPPORTED, "bf16 rows live in host memory (FR_GALLERY_BF16_ON_HOST): use fr_gallery_search_fp8");
+  FR_CUDA_OK(ctx, fr_opt_in_smem(ctx, gallery_topk_kernel<false>, G_SMEM));
+  FR_CUDA_OK(ctx, fr_opt_in_smem(ctx, gallery_topk_kernel<true>, G_SMEM8));
   const int num_m_tiles = ceil_div(nq, tc::BM);
   const int nq_pad = num_m_tiles * tc::BM;
   const int n_tiles = (int)((g->size + GN - 1) / GN);
@@ -683,11 +742,20 @@ static int gallery_search_local(fr_gallery* g, const float* queries, int nq, int
     FR_CUDA_OK(ctx, cudaMemsetAsync(g->q_bf16.as<bf16>() + (size_t)nq * DIM, 0, (size_t)(nq_pad - nq) * DIM * 2, ctx->stream));
   rows_to_bf16_kernel<<<148 * 2, 256, 0, ctx->stream>>>(d_q, g->q_bf16.as<bf16>(), (size_t)nq * DIM);
   ctx->launches++;
+  if (fp8) {
+    if (!g->q_e4m3.reserve(qelems)) return fr_fail(ctx, FR_ERR_CUDA, "search allocation failed");
+    if (nq_pad > nq) FR_CUDA_OK(ctx, cudaMemsetAsync(g->q_e4m3.as<uint8_t>() + (size_t)nq * DIM, 0, (size_t)(nq_pad - nq) * DIM, ctx->stream));
+    rows_to_e4m3_kernel<<<148 * 2, 256, 0, ctx->stream>>>(d_q, nullptr, g->q_e4m3.as<uint8_t>(), (size_t)nq * DIM);
+    ctx->launches++;
+  }
   if (n_tiles > 0) {
     CUtensorMap tmQ, tmG;
     const uint64_t g_rows = (uint64_t)((g->cap + GN - 1) / GN * GN);
-    if (!tc_make_map_2d(&tmQ, g->q_bf16.p, nq_pad, DIM, DIM, tc::BM) ||
-        !tc_make_map_2d(&tmG, g->rows, g_rows, DIM, DIM, GN))
+    const bool maps_ok = fp8 ? (tc_make_map_2d_u8(&tmQ, g->q_e4m3.p, nq_pad, DIM, DIM, tc::BM) &&
+                                tc_make_map_2d_u8(&tmG, g->rows8, g_rows, DIM, DIM, GN))
+                             : (tc_make_map_2d(&tmQ, g->q_bf16.p, nq_pad, DIM, DIM, tc::BM) &&
+                                tc_make_map_2d(&tmG, g->rows, g_rows, DIM, DIM, GN));
+    if (!maps_ok)
       return fr_fail(ctx, FR_ERR_CUDA, "gallery tensor map encode failed");
     GParams p;
     p.n_rows = (int)g->size;
@@ -699,9 +767,33 @@ static int gallery_search_local(fr_gallery* g, const float* queries, int nq, int
     p.out_s = g->part_s.as<float>();
     p.out_i = g->part_i.as<int>();
     p.err_flag = g->err_flag;
-    gallery_topk_kernel<<<num_m_tiles * splits, tc::NUM_THREADS, G_SMEM, ctx->stream>>>(tmQ, tmG, p);
+    if (fp8) gallery_topk_kernel<true><<<num_m_tiles * splits, tc::NUM_THREADS, G_SMEM8, ctx->stream>>>(tmQ, tmG, p);
+    else gallery_topk_kernel<false><<<num_m_tiles * splits, tc::NUM_THREADS, G_SMEM, ctx->stream>>>(tmQ, tmG, p);
     ctx->launches++;
     FR_CUDA_OK(ctx, cudaGetLastError());
+  }
+  if (fp8) {
+    // candidate set = union of at most RERANK_MAX_PARTS top-16 lists (split lists, group-merged when a small
+    // query batch was spread over more splits), re-scored exactly from the bf16 rows
+    int parts = n_tiles > 0 ? splits : 0;
+    const float* cs = g->part_s.as<float>();
+    const int* ci = g->part_i.as<int>();
+    if (parts > RERANK_MAX_PARTS) {
+      const int ppg = ceil_div(parts, RERANK_MAX_PARTS), groups = ceil_div(parts, ppg);
+      if (!g->grp_s.reserve((size_t)groups * nq_pad * TOPK * 4) || !g->grp_i.reserve((size_t)groups * nq_pad * TOPK * 4))
+        return fr_fail(ctx, FR_ERR_CUDA, "search allocation failed");
+      coarse_group_merge_kernel<<<dim3(ceil_div(nq, 128), groups), 128, 0, ctx->stream>>>(
+          cs, ci, parts, ppg, nq, nq_pad, g->grp_s.as<float>(), g->grp_i.as<int>());
+      ctx->launches++;
+      ci = g->grp_i.as<int>();
+      parts = groups;
+    }
+    rerank_kernel<<<ceil_div(nq, 8), 256, 0, ctx->stream>>>(g->q_bf16.as<bf16>(), g->rows, ci, parts, nq, nq_pad, k,
+                                                            (long long)g->base, d_os, d_oi, d_rec);
+    ctx->launches++;
+    FR_CUDA_OK(ctx, cudaGetLastError());
+    ctx->stage_end();
+    return FR_OK;
   }
   topk_merge_kernel<<<ceil_div(nq, 128), 128, 0, ctx->stream>>>(
       g->part_s.as<float>(), g->part_i.as<int>(), nullptr, n_tiles > 0 ? splits : 0, nq, nq_pad, TOPK, k,
@@ -749,6 +841,46 @@ int fr_gallery_search(fr_gallery* g, const float* queries, int nq, int k, int me
   if (memspace != FR_MEM_DEVICE) {
     FR_CUDA_OK(ctx, cudaMemcpyAsync(out_scores, d_os, (size_t)nq * k * 4, cudaMemcpyDeviceToHost, ctx->stream));
     FR_CUDA_OK(ctx, cudaMemcpyAsync(out_idx, d_oi, (size_t)nq * k * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    FR_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+  }
+  return FR_OK;
+}
+
+int fr_gallery_search_fp8(fr_gallery* g, const float* queries, int nq, int k, int memspace, float* out_scores,
+                          int64_t* out_idx) {
+  if (!g || !queries || !out_scores || !out_idx || nq <= 0 || k <= 0 || k > TOPK) return FR_ERR_INVALID_ARG;
+  fr_ctx* ctx = g->ctx;
+  GGuard gg(ctx);
+  float* d_os = out_scores;
+  long long* d_oi = reinterpret_cast<long long*>(out_idx);
+  if (memspace != FR_MEM_DEVICE) {
+    if (!g->out_s.reserve((size_t)nq * k * 4) || !g->out_i.reserve((size_t)nq * k * 8))
+      return fr_fail(ctx, FR_ERR_CUDA, "search allocation failed");
+    d_os = g->out_s.as<float>();
+    d_oi = g->out_i.as<long long>();
+  }
+  FR_CHECK(gallery_search_local(g, queries, nq, k, memspace, d_os, d_oi, nullptr, true));
+  if (memspace != FR_MEM_DEVICE) {
+    FR_CUDA_OK(ctx, cudaMemcpyAsync(out_scores, d_os, (size_t)nq * k * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    FR_CUDA_OK(ctx, cudaMemcpyAsync(out_idx, d_oi, (size_t)nq * k * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    FR_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+  }
+  return FR_OK;
+}
+
+int fr_gallery_search_packed_fp8(fr_gallery* g, const float* queries, int nq, int k, int memspace, uint64_t* out_records) {
+  if (!g || !queries || !out_records || nq <= 0 || k <= 0 || k > TOPK) return FR_ERR_INVALID_ARG;
+  fr_ctx* ctx = g->ctx;
+  GGuard gg(ctx);
+  if (g->base + g->size > 0xfffffffeLL) return fr_fail(ctx, FR_ERR_UNSUPPORTED, "packed records hold 32-bit row indices");
+  unsigned long long* d_rec = reinterpret_cast<unsigned long long*>(out_records);
+  if (memspace != FR_MEM_DEVICE) {
+    if (!g->rec_local.reserve((size_t)nq * k * 8)) return fr_fail(ctx, FR_ERR_CUDA, "search allocation failed");
+    d_rec = g->rec_local.as<unsigned long long>();
+  }
+  FR_CHECK(gallery_search_local(g, queries, nq, k, memspace, nullptr, nullptr, d_rec, true));
+  if (memspace != FR_MEM_DEVICE) {
+    FR_CUDA_OK(ctx, cudaMemcpyAsync(out_records, d_rec, (size_t)nq * k * 8, cudaMemcpyDeviceToHost, ctx->stream));
     FR_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
   }
   return FR_OK;

@@ -157,6 +157,15 @@ FR_API int fr_pipeline_wait(fr_ctx* ctx, int ticket);
  * returns, per query, the top-k raw cosine scores (descending; ties -> lower
  * index) and global row indices (index_base + local row). */
 FR_API int fr_gallery_create(fr_ctx* ctx, fr_gallery** out, int64_t capacity_rows, int64_t index_base);
+/* Storage options.  FR_GALLERY_FP8 keeps an e4m3 mirror of the rows (512 B / row) for
+ * fr_gallery_search_fp8: a coarse pass on the fp8 tensor cores (kind::f8f6f4, twice the bf16 rate,
+ * half the bytes) followed by an EXACT bf16 re-rank of the union of the per-split top-16 candidate
+ * lists (64 candidates per query at 4096 queries, up to 128).  With FR_GALLERY_BF16_ON_HOST the bf16
+ * rows that only the re-rank touches live in mapped pinned host memory, so a GPU holds twice the
+ * rows per GB of HBM; the plain bf16 search is then unavailable (FR_ERR_UNSUPPORTED). */
+enum { FR_GALLERY_BF16 = 0, FR_GALLERY_FP8 = 1, FR_GALLERY_BF16_ON_HOST = 2 };
+FR_API int fr_gallery_create_ex(fr_ctx* ctx, fr_gallery** out, int64_t capacity_rows,
+                                int64_t index_base, int flags);
 FR_API void fr_gallery_destroy(fr_gallery* g);
 FR_API int fr_gallery_add(fr_gallery* g, const float* rows, int64_t n, int memspace);
 /* Fill with n synthetic unit-norm rows generated on the device (Philox-style hash of seed,row). */
@@ -170,6 +179,11 @@ FR_API int fr_gallery_load(fr_gallery* g, const char* path, int64_t* file_index_
 FR_API int fr_gallery_remove(fr_gallery* g, int64_t row);
 FR_API int fr_gallery_search(fr_gallery* g, const float* queries, int nq, int k, int memspace,
                              float* out_scores, int64_t* out_idx);
+/* fp8 coarse pass + exact bf16 re-rank (needs FR_GALLERY_FP8).  Every returned score is the bf16
+ * search's score of the returned row; the returned set equals the bf16 search's wherever the true
+ * top-k members rank inside their split's top 16 by fp8 score (fp8 score error ~ 4e-3 rms). */
+FR_API int fr_gallery_search_fp8(fr_gallery* g, const float* queries, int nq, int k, int memspace,
+                                 float* out_scores, int64_t* out_idx);
 /* Merge `parts` per-shard top-k lists [parts][nq][k] (as gathered over NCCL) into [nq][k]. */
 FR_API int fr_topk_merge(fr_ctx* ctx, const float* scores, const int64_t* idx, int parts, int nq,
                          int k, int memspace, float* out_scores, int64_t* out_idx);
@@ -189,6 +203,8 @@ FR_API int fr_gallery_search_sharded(fr_gallery* g, void* nccl_comm, int world, 
  * gathered records [parts][nq][k]. */
 FR_API int fr_gallery_search_packed(fr_gallery* g, const float* queries, int nq, int k, int memspace,
                                     uint64_t* out_records);
+FR_API int fr_gallery_search_packed_fp8(fr_gallery* g, const float* queries, int nq, int k,
+                                        int memspace, uint64_t* out_records);
 FR_API int fr_topk_merge_packed(fr_ctx* ctx, const uint64_t* records, int parts, int nq, int k,
                                 int memspace, float* out_scores, int64_t* out_idx);
 

@@ -175,3 +175,97 @@ def test_remove_then_rebalance_across_shards_keeps_results(ctx, capi):
     assert all(idx.resolve(int(g)) not in removed for g in mi[:, 0]) and np.all(ms[:, 0] < 0.5)
     for s in shards:
         s.close()
+
+
+def _planted(rng, n_rows, n_planted_q, k):
+    """Random unit gallery; for the first n_planted_q queries, k rows planted at cosine 0.9, 0.85, ..."""
+    rows = rng.normal(size=(n_rows, 512)).astype(np.float32)
+    rows /= np.linalg.norm(rows, axis=1, keepdims=True)
+    q = rng.normal(size=(n_planted_q + 96, 512)).astype(np.float32)
+    q /= np.linalg.norm(q, axis=1, keepdims=True)
+    slots = rng.choice(n_rows, n_planted_q * k, replace=False).reshape(n_planted_q, k)
+    for qi in range(n_planted_q):
+        for j in range(k):
+            a = 0.9 - 0.05 * j
+            noise = rng.normal(size=512).astype(np.float32)
+            noise -= noise.dot(q[qi]) * q[qi]
+            noise /= np.linalg.norm(noise)
+            rows[slots[qi, j]] = a * q[qi] + np.sqrt(1 - a * a) * noise
+    return rows, q, slots
+
+
+def test_fp8_gallery_coarse_pass_plus_bf16_rerank(ctx, capi):
+    """SURVEY 8f-4: e4m3 gallery (kind::f8f6f4 coarse pass) with exact bf16 re-rank.
+    * every returned score is the bf16 search's score of that row (|d| <= 2e-6: summation order only);
+    * the re-ranked top-10 equals the bf16 search wherever the oracle's score gap between rank k and the
+      first candidate that could be lost (rank 17) exceeds twice the fp8 error bound;
+    * on random queries (gaps inside the fp8 noise) recall stays >= 0.9."""
+    from oracle import gallery as ogal
+    rng = np.random.default_rng(21)
+    n_rows, nq_p, k = 70_001, 64, 10
+    rows, q, slots = _planted(rng, n_rows, nq_p, k)
+    g = capi.Gallery(ctx, n_rows, index_base=500, flags=capi.Gallery.FP8)
+    for first in range(0, n_rows, 20_000):
+        g.add(rows[first:first + 20_000])
+    s_b, i_b = g.search(q, k)
+    s_f, i_f = g.search_fp8(q, k)
+    assert np.array_equal(i_f[:nq_p], i_b[:nq_p]) and np.array_equal(i_b[:nq_p] - 500, slots)   # planted: exact
+    # re-rank exactness: the score of every returned row, recomputed by the numpy oracle from bf16 values
+    qb, rb = ogal.to_bf16_f32(q), ogal.to_bf16_f32(rows)
+    exact = np.einsum("qd,qkd->qk", qb.astype(np.float64), rb[i_f - 500].astype(np.float64))
+    assert np.abs(s_f - exact).max() < 2e-6, float(np.abs(s_f - exact).max())
+    assert np.all(np.diff(s_f, axis=1) <= 0)
+    # gap rule on all queries, with the bf16 search's own top-16 as the oracle list
+    s16, _ = g.search(q, 16)
+    eps = 0.02                                   # 5 sigma of the e4m3 score error (sigma ~ 4e-3)
+    safe = (s16[:, k - 1] - s16[:, 15]) > 2 * eps
+    assert safe[:nq_p].all()
+    assert np.array_equal(i_f[safe], i_b[safe])
+    recall = np.mean([len(set(a) & set(b)) / k for a, b in zip(i_f[nq_p:], i_b[nq_p:])])
+    assert recall >= 0.9, recall
+    # small batches are spread over > 8 splits: the group-merge path must give the same answer
+    s1, i1 = g.search_fp8(q[:3], k)
+    assert np.array_equal(i1, i_f[:3]) and np.abs(s1 - s_f[:3]).max() < 2e-6
+    g.close()
+
+
+def test_fp8_gallery_host_resident_bf16_rows_and_persistence(ctx, capi, tmp_path):
+    """Capacity mode: only the e4m3 rows in HBM, bf16 rows in mapped pinned host memory.  Same results as
+    the all-HBM fp8 gallery; the plain bf16 search refuses; save / load / remove keep both copies in step."""
+    rng = np.random.default_rng(22)
+    n_rows, k = 20_000, 10
+    rows, q, _ = _planted(rng, n_rows, 16, k)
+    dev = capi.Gallery(ctx, n_rows, flags=capi.Gallery.FP8)
+    host = capi.Gallery(ctx, n_rows, flags=capi.Gallery.FP8 | capi.Gallery.BF16_ON_HOST)
+    dev.add(rows)
+    host.add(rows)
+    sd, idd = dev.search_fp8(q, k)
+    sh, ih = host.search_fp8(q, k)
+    assert np.array_equal(idd, ih) and np.array_equal(sd, sh)
+    with pytest.raises(capi.FrError) as e:
+        host.search(q, k)
+    assert e.value.code == capi.FR_ERR_UNSUPPORTED
+    with pytest.raises(capi.FrError):
+        capi.Gallery(ctx, 10, flags=capi.Gallery.BF16_ON_HOST)          # needs FP8
+    plain = capi.Gallery(ctx, 10)
+    with pytest.raises(capi.FrError):
+        plain.search_fp8(q[:1], 1)                                      # no e4m3 mirror
+    assert np.array_equal(host.get_rows(0, 50), dev.get_rows(0, 50))
+    # persistence: the file holds the bf16 rows; the e4m3 mirror is rebuilt on load
+    p = str(tmp_path / "shard.frg")
+    host.save(p)
+    again = capi.Gallery(ctx, n_rows, flags=capi.Gallery.FP8)
+    again.load(p)
+    s2, i2 = again.search_fp8(q, k)
+    assert np.array_equal(i2, idd) and np.array_equal(s2, sd)
+    # remove: the last row moves into the hole in both copies
+    victim = int(idd[0, 0])
+    for gal in (dev, host):
+        gal.remove(victim)
+    s3, i3 = dev.search_fp8(q[:1], k)
+    s4, i4 = host.search_fp8(q[:1], k)
+    assert np.array_equal(i3, i4) and np.array_equal(s3, s4) and victim not in i3[0][s3[0] > 0.8]
+    moved = dev.get_rows(victim, 1)[0]
+    assert np.array_equal(moved, __import__("oracle.gallery", fromlist=["x"]).to_bf16_f32(rows[n_rows - 1]))
+    for gal in (dev, host, again, plain):
+        gal.close()
