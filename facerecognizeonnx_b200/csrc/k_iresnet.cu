@@ -124,6 +124,10 @@ struct ConvLaunch {
   CUtensorMap a_halo;      // halo mode: box = (a_rows / a_boxes) x 64
   CUtensorMap b_small;     // halo mode: the weights with a 64-row box (N-split tail items)
   bool has_b_small = false;
+  // 2-CTA mode (halo_gemm2_kernel): the weights with BN/2-, BN/4- and BN/8-row boxes (each CTA of the pair
+  // loads half of an item's weight rows; the smaller boxes serve the N-split tail items)
+  CUtensorMap b_half, b_half2, b_half4;
+  bool two_cta = false;
   tc::Params p;
   int bn = 64;
   int rows_per_img = 1;  // Hp*Wp of the output geometry
@@ -174,6 +178,34 @@ int tc_launch(fr_ctx* ctx, ConvLaunch& L, int m_rows) {
   FR_CUDA_OK(ctx, fr_opt_in_smem(ctx, tc::shift_gemm_kernel<128>, tc::Cfg<128>::SMEM_BYTES));
   FR_CUDA_OK(ctx, fr_opt_in_smem(ctx, tc::shift_gemm_kernel<256>, tc::Cfg<256>::SMEM_BYTES));
   const int grid = std::min(total, num_sms);
+  if (L.halo && L.two_cta && env_flag("FR_TC_2CTA", 1)) {
+    // cta_group::2: work item = 256 rows x BN columns per CTA pair (see tc::halo_gemm2_kernel)
+    const int nclusters = num_sms / 2;
+    const int supers = ceil_div(L.p.num_m_tiles, 2) * L.p.n_tiles_n;
+    L.p.tail_split = 1;
+    L.p.tail_first = supers;
+    int items = supers;
+    if (env_flag("FR_TC_TAILSPLIT", 1)) {
+      const int tail = supers % nclusters;
+      int split = 1;
+      for (int s2 = 2; s2 <= 4 && L.bn / s2 >= 64; s2 *= 2)
+        if (tail > 0 && tail * s2 <= nclusters) split = s2;
+      if (split > 1) {
+        L.p.tail_split = split;
+        L.p.tail_first = supers - tail;
+        items = L.p.tail_first + tail * split;
+      }
+    }
+    const int cgrid = 2 * std::min(items, nclusters);
+    using C2 = tc::Halo2Cfg<256>;
+    L.p.a_stages = std::min(env_flag("FR_TC_ASTAGES2", 2), C2::pick_a_stages(L.p.a_rows));
+    const int smem2 = C2::smem_bytes(L.p.a_rows, L.p.a_stages);
+    FR_CUDA_OK(ctx, fr_opt_in_smem(ctx, tc::halo_gemm2_kernel<256>, 227 * 1024));
+    tc::halo_gemm2_kernel<256><<<cgrid, tc::CONV_THREADS, smem2, ctx->stream>>>(L.a_halo, L.b_half, L.b_half2, L.b_half4, L.p);
+    ctx->launches++;
+    FR_CUDA_OK(ctx, cudaGetLastError());
+    return FR_OK;
+  }
   if (L.halo) {
     const int supers = ceil_div(L.p.num_m_tiles, L.mt) * L.p.n_tiles_n;
     // N-split of the last, partial wave (see tc::Params::tail_split)
@@ -851,6 +883,10 @@ static int rec_build_plan(fr_ctx* ctx, int cap) {
     ok = ok && tc_make_map_2d(&c1.b0, bw.w1, (uint64_t)9 * bw.planes, bw.cin, bw.cin, c1.bn);
     c1.has_b_small = ok && c1.halo && c1.bn > 64 && tc_make_map_2d(&c1.b_small, bw.w1, (uint64_t)9 * bw.planes, bw.cin, bw.cin, 64);
     c1.b1 = c1.b0;
+    c1.two_cta = ok && c1.halo && c1.bn == 256 && c1.mt == 1 && !c1.resb && c1.p.a_boxes == 1 &&
+                 tc_make_map_2d(&c1.b_half, bw.w1, (uint64_t)9 * bw.planes, bw.cin, bw.cin, 128) &&
+                 tc_make_map_2d(&c1.b_half2, bw.w1, (uint64_t)9 * bw.planes, bw.cin, bw.cin, 64) &&
+                 tc_make_map_2d(&c1.b_half4, bw.w1, (uint64_t)9 * bw.planes, bw.cin, bw.cin, 32);
     // ---- conv2: 3x3 stride s (+ fused 1x1 shortcut conv) + residual -> out
     ConvLaunch& c2 = m->conv2[i];
     memset(&c2.p, 0, sizeof(c2.p));
@@ -884,6 +920,10 @@ static int rec_build_plan(fr_ctx* ctx, int cap) {
     }
     ok = ok && tc_make_map_2d(&c2.b0, bw.w2, (uint64_t)9 * bw.planes, bw.planes, bw.planes, c2.bn);
     c2.has_b_small = ok && c2.halo && c2.bn > 64 && tc_make_map_2d(&c2.b_small, bw.w2, (uint64_t)9 * bw.planes, bw.planes, bw.planes, 64);
+    c2.two_cta = ok && c2.halo && c2.bn == 256 && c2.mt == 1 && !c2.resb && c2.p.a_boxes == 1 &&
+                 tc_make_map_2d(&c2.b_half, bw.w2, (uint64_t)9 * bw.planes, bw.planes, bw.planes, 128) &&
+                 tc_make_map_2d(&c2.b_half2, bw.w2, (uint64_t)9 * bw.planes, bw.planes, bw.planes, 64) &&
+                 tc_make_map_2d(&c2.b_half4, bw.w2, (uint64_t)9 * bw.planes, bw.planes, bw.planes, 32);
     if (bw.stride != 2) c2.b1 = c2.b0;
     x = bb.out;
     xe = bb.out_even;
@@ -1172,6 +1212,10 @@ int rec_test_conv(fr_ctx* ctx, const float* x, int n, int cin, int h, int w, con
   L.b1 = L.b0;
   if (ok && ksize == 3) ok = tc_setup_halo(L, d_x, rows, cin, Wp);
   L.has_b_small = ok && L.halo && L.bn > 64 && tc_make_map_2d(&L.b_small, d_w, (uint64_t)ksize * ksize * cout, cin, cin, 64);
+  L.two_cta = ok && L.halo && L.bn == 256 && L.mt == 1 && !L.resb && L.p.a_boxes == 1 &&
+              tc_make_map_2d(&L.b_half, d_w, (uint64_t)9 * cout, cin, cin, 128) &&
+              tc_make_map_2d(&L.b_half2, d_w, (uint64_t)9 * cout, cin, cin, 64) &&
+              tc_make_map_2d(&L.b_half4, d_w, (uint64_t)9 * cout, cin, cin, 32);
   int status = FR_OK;
   if (!ok) status = fr_fail(ctx, FR_ERR_CUDA, "fr_test_conv: tensor map encode failed");
   if (status == FR_OK) status = tc_launch(ctx, L, (int)rows);

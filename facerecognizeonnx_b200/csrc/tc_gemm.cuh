@@ -793,4 +793,256 @@ halo_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   }
 }
 
+
+// ------------------------------------------------------- 2-CTA halo-mode kernel
+// The 256 / 512-channel 3x3 stride-1 convolutions (28 + 4 launches, half of the trunk's time) are not
+// bound by the tensor pipe but by the L2 -> shared-memory feed: with cta_group::1 every CTA streams the
+// whole 256 x 64 weight tile of every tap (9 x 32 KB per 20 KB of activations per K block, 67 B/clk/SM
+// at the MMA's own pace; measured tensor-pipe activity 73-75 %).  A CTA PAIR (cluster of 2, one TPC)
+// executes one tcgen05.mma.cta_group::2 of M = 256: each CTA holds its own 128-row activation block and
+// only HALF of the weight tile (its N/2 rows); the tensor cores of the two SMs exchange the halves.  Per
+// SM that is 9 x 16 KB of weights per K block (36 B/clk) and 8 KB of shared-memory operand reads per
+// 128-cycle MMA instead of 12 KB.
+//   * both CTAs run the same code on the same shared-memory layout; work item = 256 rows x BN columns;
+//   * producers: each CTA loads its A block and its half of B with cp.async.bulk.tensor...cta_group::2,
+//     completing on the LEADER's (cluster rank 0) full barriers, which the leader arms for both halves;
+//   * MMA: issued by the leader only; tcgen05.commit...multicast::cluster releases the stage / publishes
+//     the accumulator in BOTH CTAs (each waits on its own barrier copy);
+//   * epilogue: each CTA drains its own 128 TMEM lanes; the peer's warps arrive remotely on the leader's
+//     tempty barrier.
+// Tail items (last partial wave) are split along N like in halo_gemm_kernel: N = BN / tail_split, each
+// CTA loading N/2 weight rows through the map with the matching box height.
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// TMA load whose completion bytes are counted on the mbarrier of the pair's leader CTA (address with
+// the CTA-rank bit cleared, like CUTLASS's SM100_TMA_2SM_LOAD)
+__device__ __forceinline__ void tma_load_2d_2sm(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4}], [%2];"
+      :
+      : "r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar) & 0xFEFFFFFFu), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void mma_bf16_2sm(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                             uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      :
+      : "r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// commit of all prior MMAs of this thread: one arrival on the barrier at this offset in both CTAs
+__device__ __forceinline__ void tc_commit_2sm(uint64_t* bar) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+      :
+      : "r"(smem_u32(bar)), "h"((uint16_t)3)
+      : "memory");
+}
+// arrive on the barrier at the same offset in CTA `rank` of the cluster
+__device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, uint32_t rank) {
+  asm volatile(
+      "{\n\t.reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}"
+      :
+      : "r"(smem_u32(bar)), "r"(rank)
+      : "memory");
+}
+
+template <int BN> struct Halo2Cfg {
+  static constexpr int B_HALF_BYTES = (BN / 2) * BK * 2;   // this CTA's half of one weight tile
+  static constexpr int MAX_A_STAGES = 6;
+  static constexpr int B_STAGES = 6;
+  static constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;   // double-buffered accumulators
+  static int smem_bytes(int a_rows, int a_stages) { return a_stages * a_rows * 128 + B_STAGES * B_HALF_BYTES + 256 + 1024; }
+  static int pick_a_stages(int a_rows) {
+    int s = 2;
+    while (s < MAX_A_STAGES && smem_bytes(a_rows, s + 1) <= 200 * 1024) ++s;
+    return s;
+  }
+};
+
+template <int BN>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CONV_THREADS, 1)
+halo_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                  const __grid_constant__ CUtensorMap tmB2, const __grid_constant__ CUtensorMap tmB4,
+                  const __grid_constant__ Params p) {
+  using C = Halo2Cfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  const int a_bytes = p.a_rows * 128;
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + p.a_stages * a_bytes;
+  uint64_t* afull = reinterpret_cast<uint64_t*>(sB + C::B_STAGES * C::B_HALF_BYTES);
+  uint64_t* aempty = afull + C::MAX_A_STAGES;
+  uint64_t* bfull = aempty + C::MAX_A_STAGES;
+  uint64_t* bempty = bfull + C::B_STAGES;
+  uint64_t* tfull = bempty + C::B_STAGES;
+  uint64_t* tempty = tfull + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < C::MAX_A_STAGES; ++s) { mbar_init(&afull[s], 1); mbar_init(&aempty[s], 1); }
+    for (int s = 0; s < C::B_STAGES; ++s) { mbar_init(&bfull[s], 1); mbar_init(&bempty[s], 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 2 * EPI_WARPS); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    prefetch_tmap(&tmA);
+    prefetch_tmap(&tmB);
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"((uint32_t)C::TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();     // both CTAs' barriers are initialised before anyone signals across the pair
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int num_super = (p.num_m_tiles + 1) / 2;
+  const int tail_split = p.tail_split > 1 ? p.tail_split : 1;
+  const int tail_first = tail_split > 1 ? p.tail_first : num_super * p.n_tiles_n;
+  const int total_items = tail_first + (num_super * p.n_tiles_n - tail_first) * tail_split;
+  const int nkb = p.taps[0].nkb;
+  const int wp = p.Wp;
+  const int box_rows = p.a_rows / p.a_boxes;
+  const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
+  auto item_coords = [&](int item, int& m0, int& n0, int& nlen) {
+    int tile = item, sub = 0;
+    nlen = BN;
+    if (item >= tail_first) {
+      const int j = item - tail_first;
+      tile = tail_first + j / tail_split;
+      sub = j % tail_split;
+      nlen = BN / tail_split;
+    }
+    m0 = (tile / p.n_tiles_n) * (2 * BM) + (int)rank * BM;   // this CTA's 128 rows of the 256-row item
+    n0 = (tile % p.n_tiles_n) * BN + sub * nlen;
+  };
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int sa = 0, sb = 0;
+      uint32_t pa = 0, pb = 0;
+      for (int item = cluster_id; item < total_items; item += num_clusters) {
+        int m0, n0, nlen;
+        item_coords(item, m0, n0, nlen);
+        const int half = nlen / 2;                              // weight rows this CTA loads per tap
+        const CUtensorMap* mb = nlen == BN ? &tmB : (nlen == BN / 2 ? &tmB2 : &tmB4);
+        for (int kb = 0; kb < nkb; ++kb) {
+          mbar_wait(&aempty[sa], pa ^ 1u, p.err_flag);
+          if (leader) mbar_expect_tx(&afull[sa], 2u * (uint32_t)a_bytes);
+          for (int bx = 0; bx < p.a_boxes; ++bx)
+            tma_load_2d_2sm(sA + sa * a_bytes + bx * box_rows * 128, &tmA, &afull[sa], kb * BK,
+                            m0 - wp - 1 + bx * box_rows);
+          if (++sa == p.a_stages) { sa = 0; pa ^= 1u; }
+          for (int t = 0; t < 9; ++t) {
+            mbar_wait(&bempty[sb], pb ^ 1u, p.err_flag);
+            if (leader) mbar_expect_tx(&bfull[sb], 2u * (uint32_t)(half * BK * 2));
+            tma_load_2d_2sm(sB + sb * C::B_HALF_BYTES, mb, &bfull[sb], kb * BK, t * p.cout + n0 + (int)rank * half);
+            if (++sb == C::B_STAGES) { sb = 0; pb ^= 1u; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (leader) {
+      const uint64_t d0 = make_smem_desc(sA);
+      const uint32_t desc_hi = (uint32_t)(d0 >> 32);
+      const uint32_t a_lo0 = (uint32_t)d0;
+      const uint32_t b_lo0 = (uint32_t)make_smem_desc(sB);
+      auto desc = [&](uint32_t lo) { return ((uint64_t)desc_hi << 32) | (uint64_t)lo; };
+      const uint32_t a_step = (uint32_t)a_bytes >> 4;
+      int sa = 0, sb = 0;
+      uint32_t pa = 0, pb = 0, it = 0;
+      for (int item = cluster_id; item < total_items; item += num_clusters, ++it) {
+        const uint32_t acc = it & 1u, acc_phase = (it >> 1) & 1u;
+        mbar_wait(&tempty[acc], acc_phase ^ 1u, p.err_flag);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        const int nlen = item >= tail_first ? BN / tail_split : BN;
+        const uint32_t idesc = make_idesc(2 * BM, nlen);
+        for (int kb = 0; kb < nkb; ++kb) {
+          mbar_wait(&afull[sa], pa, p.err_flag);
+          tc_fence_after();
+          const uint32_t ablk = a_lo0 + (uint32_t)sa * a_step;
+#pragma unroll
+          for (int t = 0; t < 9; ++t) {
+            mbar_wait(&bfull[sb], pb, p.err_flag);
+            tc_fence_after();
+            const uint32_t btile = b_lo0 + (uint32_t)sb * (uint32_t)(C::B_HALF_BYTES >> 4);
+            const uint32_t adesc = ablk + (uint32_t)((t / 3) * wp + (t % 3)) * 8u;
+            const uint32_t accumulate = (kb | t) ? 1u : 0u;
+            if (elect_one()) {
+#pragma unroll
+              for (int k = 0; k < BK / 16; ++k)
+                mma_bf16_2sm(d_tmem, desc(adesc + k * 2), desc(btile + k * 2), idesc, (accumulate | (uint32_t)k) ? 1u : 0u);
+              tc_commit_2sm(&bempty[sb]);
+            }
+            __syncwarp();
+            if (++sb == C::B_STAGES) { sb = 0; pb ^= 1u; }
+          }
+          if (elect_one()) tc_commit_2sm(&aempty[sa]);
+          __syncwarp();
+          if (++sa == p.a_stages) { sa = 0; pa ^= 1u; }
+        }
+        if (elect_one()) tc_commit_2sm(&tfull[acc]);
+        __syncwarp();
+      }
+    }
+  } else {
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    constexpr int CPS = BN / 32 / (EPI_WARPS / 4);
+    const int c_begin = ((warp - 2) >> 2) * CPS;
+    uint32_t it = 0;
+    for (int item = cluster_id; item < total_items; item += num_clusters, ++it) {
+      int m0, n0, nlen;
+      item_coords(item, m0, n0, nlen);
+      const int cps = nlen == BN ? CPS : nlen / 32 / (EPI_WARPS / 4);
+      const int cb = nlen == BN ? c_begin : ((warp - 2) >> 2) * cps;
+      const uint32_t acc = it & 1u, acc_phase = (it >> 1) & 1u;
+      const EpiRow er = epi_row(p, m0 + row, n0, 0);
+      uint4 rv[4];
+      epi_load_res(er, cb, rv);
+      mbar_wait(&tfull[acc], acc_phase, p.err_flag);
+      tc_fence_after();
+      const uint32_t taddr0 = tmem_base + acc * BN + ((uint32_t)(q * 32) << 16);
+      if (cps > 0) epilogue_tile<BN>(p, er, taddr0, n0, 0, cb, cb + cps, rv);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        if (leader) mbar_arrive(&tempty[acc]);
+        else mbar_arrive_cluster(&tempty[acc], 0);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();     // the peer may still be signalling / reading this CTA's shared memory
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
+                 "r"((uint32_t)C::TMEM_COLS)
+                 : "memory");
+  }
+}
+
 }  // namespace tc

@@ -38,6 +38,28 @@ def test_tc_conv3x3_plain(ctx, n, cin, cout, h, w):
     assert _rel(y, ref) < 6e-3, _rel(y, ref)   # output itself is rounded to bf16 (2^-9 relative)
 
 
+@pytest.mark.parametrize("n,cin,cout,h,w", [(1, 256, 256, 14, 14), (3, 256, 256, 14, 14), (40, 256, 256, 14, 14),
+                                            (5, 512, 512, 7, 7), (2, 128, 256, 7, 7), (90, 256, 256, 7, 7)])
+def test_tc_conv3x3_two_cta_pair(ctx, n, cin, cout, h, w):
+    """halo_gemm2_kernel (tcgen05.mma.cta_group::2, M = 256 over a CTA pair, each CTA loading half of the
+    weight tile): all 256 / 512-output-channel 3x3 stride-1 layers.  Odd numbers of 128-row tiles (the peer
+    CTA's half of the last item is past the end), more items than clusters (ring wrap-around, both TMEM
+    buffers), and the N-split tail all appear in these shapes.  Bias + PReLU + residual epilogue."""
+    rng = np.random.default_rng(n + cin + h)
+    x = rng.normal(size=(n, cin, h, w)).astype(np.float32)
+    wt = (rng.normal(size=(cout, cin, 3, 3)) / np.sqrt(9 * cin)).astype(np.float32)
+    b = rng.normal(size=cout).astype(np.float32)
+    slope = rng.uniform(0.1, 0.4, cout).astype(np.float32)
+    res = rng.normal(size=(n, cout, h, w)).astype(np.float32)
+    y = ctx.test_conv(x, wt, bias=b, prelu=slope, residual=res)
+    ref = F.conv2d(_bf16(x), _bf16(wt), torch.from_numpy(b), padding=1)
+    ref = (F.prelu(ref, torch.from_numpy(slope)) + _bf16(res)).numpy()
+    assert _rel(y, ref) < 8e-3, _rel(y, ref)
+    # column halves must not be swapped between the two CTAs: check the two N halves separately
+    hn = cout // 2
+    assert _rel(y[:, :hn], ref[:, :hn]) < 8e-3 and _rel(y[:, hn:], ref[:, hn:]) < 8e-3
+
+
 def test_tc_conv3x3_full_epilogue(ctx):
     rng = np.random.default_rng(7)
     n, cin, cout, h, w = 2, 128, 128, 14, 14
