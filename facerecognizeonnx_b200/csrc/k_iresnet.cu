@@ -142,6 +142,13 @@ static int env_flag(const char* name, int dflt) {
 }
 
 // Configure halo mode for a 3x3 stride-1 conv whose A operand is `base` ([rows, cin], pitch cin).
+// which layer classes run on CTA pairs (tc::halo_gemm2_kernel): bit 0 = 256 / 512 channels, bit 1 = 128, bit 2 = 64
+static int two_cta_mask() { static const int v = env_flag("FR_TC_2CTA", 7); return v; }
+static bool two_cta_eligible(int bn, int cin) {
+  const int m = two_cta_mask();
+  return (bn == 256 && (m & 1)) || (bn == 128 && (m & 2)) || (bn == 64 && cin == 64 && (m & 4));
+}
+
 static bool tc_setup_halo(ConvLaunch& L, const void* base, uint64_t rows, int cin, int Wp) {
   if (!env_flag("FR_TC_HALO", 1)) return true;   // default on (FR_TC_HALO=0 selects the per-tap loader)
   // M tiles per CTA iteration (they share one A block and every streamed weight tile).  Measured
@@ -152,6 +159,7 @@ static bool tc_setup_halo(ConvLaunch& L, const void* base, uint64_t rows, int ci
   if (mt == 3) mt = L.bn <= 128 ? 2 : 1;
   L.mt = mt;
   L.resb = (cin == 64) && env_flag("FR_TC_RESB", 1);
+  if (two_cta_eligible(L.bn, cin)) mt = 1;   // a CTA pair covers 256 rows with one tile per CTA
   int a_rows = (mt * tc::BM + 2 * Wp + 2 + 7) / 8 * 8;
   int boxes = 1;
   if (a_rows > 256) { boxes = 2; a_rows = (a_rows + 15) / 16 * 16; }
@@ -178,7 +186,7 @@ int tc_launch(fr_ctx* ctx, ConvLaunch& L, int m_rows) {
   FR_CUDA_OK(ctx, fr_opt_in_smem(ctx, tc::shift_gemm_kernel<128>, tc::Cfg<128>::SMEM_BYTES));
   FR_CUDA_OK(ctx, fr_opt_in_smem(ctx, tc::shift_gemm_kernel<256>, tc::Cfg<256>::SMEM_BYTES));
   const int grid = std::min(total, num_sms);
-  if (L.halo && L.two_cta && env_flag("FR_TC_2CTA", 1)) {
+  if (L.halo && L.two_cta) {
     // cta_group::2: work item = 256 rows x BN columns per CTA pair (see tc::halo_gemm2_kernel)
     const int nclusters = num_sms / 2;
     const int supers = ceil_div(L.p.num_m_tiles, 2) * L.p.n_tiles_n;
@@ -197,11 +205,18 @@ int tc_launch(fr_ctx* ctx, ConvLaunch& L, int m_rows) {
       }
     }
     const int cgrid = 2 * std::min(items, nclusters);
-    using C2 = tc::Halo2Cfg<256>;
-    L.p.a_stages = std::min(env_flag("FR_TC_ASTAGES2", 2), C2::pick_a_stages(L.p.a_rows));
-    const int smem2 = C2::smem_bytes(L.p.a_rows, L.p.a_stages);
-    FR_CUDA_OK(ctx, fr_opt_in_smem(ctx, tc::halo_gemm2_kernel<256>, 227 * 1024));
-    tc::halo_gemm2_kernel<256><<<cgrid, tc::CONV_THREADS, smem2, ctx->stream>>>(L.a_halo, L.b_half, L.b_half2, L.b_half4, L.p);
+#define FR_HALO2_LAUNCH(BN_, RB_)                                                                            \
+  do {                                                                                                       \
+    using C2 = tc::Halo2Cfg<BN_, RB_>;                                                                       \
+    L.p.a_stages = std::min(env_flag("FR_TC_ASTAGES2", 2), C2::pick_a_stages(L.p.a_rows));                   \
+    FR_CUDA_OK(ctx, fr_opt_in_smem(ctx, tc::halo_gemm2_kernel<BN_, RB_>, 227 * 1024));                       \
+    tc::halo_gemm2_kernel<BN_, RB_><<<cgrid, tc::CONV_THREADS, C2::smem_bytes(L.p.a_rows, L.p.a_stages),     \
+                                     ctx->stream>>>(L.a_halo, L.b_half, L.b_half2, L.b_half4, L.p);          \
+  } while (0)
+    if (L.bn == 256) FR_HALO2_LAUNCH(256, false);
+    else if (L.bn == 128) FR_HALO2_LAUNCH(128, false);
+    else FR_HALO2_LAUNCH(64, true);
+#undef FR_HALO2_LAUNCH
     ctx->launches++;
     FR_CUDA_OK(ctx, cudaGetLastError());
     return FR_OK;
@@ -883,10 +898,10 @@ static int rec_build_plan(fr_ctx* ctx, int cap) {
     ok = ok && tc_make_map_2d(&c1.b0, bw.w1, (uint64_t)9 * bw.planes, bw.cin, bw.cin, c1.bn);
     c1.has_b_small = ok && c1.halo && c1.bn > 64 && tc_make_map_2d(&c1.b_small, bw.w1, (uint64_t)9 * bw.planes, bw.cin, bw.cin, 64);
     c1.b1 = c1.b0;
-    c1.two_cta = ok && c1.halo && c1.bn == 256 && c1.mt == 1 && !c1.resb && c1.p.a_boxes == 1 &&
-                 tc_make_map_2d(&c1.b_half, bw.w1, (uint64_t)9 * bw.planes, bw.cin, bw.cin, 128) &&
-                 tc_make_map_2d(&c1.b_half2, bw.w1, (uint64_t)9 * bw.planes, bw.cin, bw.cin, 64) &&
-                 tc_make_map_2d(&c1.b_half4, bw.w1, (uint64_t)9 * bw.planes, bw.cin, bw.cin, 32);
+    c1.two_cta = ok && c1.halo && c1.mt == 1 && two_cta_eligible(c1.bn, bw.cin) && (c1.bn != 64 || c1.resb) &&
+                 tc_make_map_2d(&c1.b_half, bw.w1, (uint64_t)9 * bw.planes, bw.cin, bw.cin, c1.bn / 2) &&
+                 tc_make_map_2d(&c1.b_half2, bw.w1, (uint64_t)9 * bw.planes, bw.cin, bw.cin, std::max(c1.bn / 4, 16)) &&
+                 tc_make_map_2d(&c1.b_half4, bw.w1, (uint64_t)9 * bw.planes, bw.cin, bw.cin, std::max(c1.bn / 8, 16));
     // ---- conv2: 3x3 stride s (+ fused 1x1 shortcut conv) + residual -> out
     ConvLaunch& c2 = m->conv2[i];
     memset(&c2.p, 0, sizeof(c2.p));
@@ -920,10 +935,10 @@ static int rec_build_plan(fr_ctx* ctx, int cap) {
     }
     ok = ok && tc_make_map_2d(&c2.b0, bw.w2, (uint64_t)9 * bw.planes, bw.planes, bw.planes, c2.bn);
     c2.has_b_small = ok && c2.halo && c2.bn > 64 && tc_make_map_2d(&c2.b_small, bw.w2, (uint64_t)9 * bw.planes, bw.planes, bw.planes, 64);
-    c2.two_cta = ok && c2.halo && c2.bn == 256 && c2.mt == 1 && !c2.resb && c2.p.a_boxes == 1 &&
-                 tc_make_map_2d(&c2.b_half, bw.w2, (uint64_t)9 * bw.planes, bw.planes, bw.planes, 128) &&
-                 tc_make_map_2d(&c2.b_half2, bw.w2, (uint64_t)9 * bw.planes, bw.planes, bw.planes, 64) &&
-                 tc_make_map_2d(&c2.b_half4, bw.w2, (uint64_t)9 * bw.planes, bw.planes, bw.planes, 32);
+    c2.two_cta = ok && c2.halo && c2.mt == 1 && two_cta_eligible(c2.bn, bw.planes) && (c2.bn != 64 || c2.resb) &&
+                 tc_make_map_2d(&c2.b_half, bw.w2, (uint64_t)9 * bw.planes, bw.planes, bw.planes, c2.bn / 2) &&
+                 tc_make_map_2d(&c2.b_half2, bw.w2, (uint64_t)9 * bw.planes, bw.planes, bw.planes, std::max(c2.bn / 4, 16)) &&
+                 tc_make_map_2d(&c2.b_half4, bw.w2, (uint64_t)9 * bw.planes, bw.planes, bw.planes, std::max(c2.bn / 8, 16));
     if (bw.stride != 2) c2.b1 = c2.b0;
     x = bb.out;
     xe = bb.out_even;
@@ -1212,10 +1227,10 @@ int rec_test_conv(fr_ctx* ctx, const float* x, int n, int cin, int h, int w, con
   L.b1 = L.b0;
   if (ok && ksize == 3) ok = tc_setup_halo(L, d_x, rows, cin, Wp);
   L.has_b_small = ok && L.halo && L.bn > 64 && tc_make_map_2d(&L.b_small, d_w, (uint64_t)ksize * ksize * cout, cin, cin, 64);
-  L.two_cta = ok && L.halo && L.bn == 256 && L.mt == 1 && !L.resb && L.p.a_boxes == 1 &&
-              tc_make_map_2d(&L.b_half, d_w, (uint64_t)9 * cout, cin, cin, 128) &&
-              tc_make_map_2d(&L.b_half2, d_w, (uint64_t)9 * cout, cin, cin, 64) &&
-              tc_make_map_2d(&L.b_half4, d_w, (uint64_t)9 * cout, cin, cin, 32);
+  L.two_cta = ok && L.halo && L.mt == 1 && two_cta_eligible(L.bn, cin) && (L.bn != 64 || L.resb) &&
+              tc_make_map_2d(&L.b_half, d_w, (uint64_t)9 * cout, cin, cin, L.bn / 2) &&
+              tc_make_map_2d(&L.b_half2, d_w, (uint64_t)9 * cout, cin, cin, std::max(L.bn / 4, 16)) &&
+              tc_make_map_2d(&L.b_half4, d_w, (uint64_t)9 * cout, cin, cin, std::max(L.bn / 8, 16));
   int status = FR_OK;
   if (!ok) status = fr_fail(ctx, FR_ERR_CUDA, "fr_test_conv: tensor map encode failed");
   if (status == FR_OK) status = tc_launch(ctx, L, (int)rows);

@@ -859,12 +859,13 @@ __device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, uint32_t rank
       : "memory");
 }
 
-template <int BN> struct Halo2Cfg {
+template <int BN, bool RESB> struct Halo2Cfg {
   static constexpr int B_HALF_BYTES = (BN / 2) * BK * 2;   // this CTA's half of one weight tile
   static constexpr int MAX_A_STAGES = 6;
   static constexpr int B_STAGES = 6;
+  static constexpr int B_BYTES = RESB ? 9 * B_HALF_BYTES : B_STAGES * B_HALF_BYTES;   // RESB: all nine taps resident
   static constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;   // double-buffered accumulators
-  static int smem_bytes(int a_rows, int a_stages) { return a_stages * a_rows * 128 + B_STAGES * B_HALF_BYTES + 256 + 1024; }
+  static int smem_bytes(int a_rows, int a_stages) { return a_stages * a_rows * 128 + B_BYTES + 256 + 1024; }
   static int pick_a_stages(int a_rows) {
     int s = 2;
     while (s < MAX_A_STAGES && smem_bytes(a_rows, s + 1) <= 200 * 1024) ++s;
@@ -872,25 +873,27 @@ template <int BN> struct Halo2Cfg {
   }
 };
 
-template <int BN>
+// RESB (Cin == 64, one K block): the CTA's halves of all nine weight tiles stay resident in shared memory.
+template <int BN, bool RESB>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CONV_THREADS, 1)
 halo_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                   const __grid_constant__ CUtensorMap tmB2, const __grid_constant__ CUtensorMap tmB4,
                   const __grid_constant__ Params p) {
-  using C = Halo2Cfg<BN>;
+  using C = Halo2Cfg<BN, RESB>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
   const int a_bytes = p.a_rows * 128;
   uint8_t* sA = smem;
   uint8_t* sB = smem + p.a_stages * a_bytes;
-  uint64_t* afull = reinterpret_cast<uint64_t*>(sB + C::B_STAGES * C::B_HALF_BYTES);
+  uint64_t* afull = reinterpret_cast<uint64_t*>(sB + C::B_BYTES);
   uint64_t* aempty = afull + C::MAX_A_STAGES;
   uint64_t* bfull = aempty + C::MAX_A_STAGES;
   uint64_t* bempty = bfull + C::B_STAGES;
   uint64_t* tfull = bempty + C::B_STAGES;
   uint64_t* tempty = tfull + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  uint64_t* resfull = tempty + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(resfull + 1);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -900,6 +903,7 @@ halo_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     for (int s = 0; s < C::MAX_A_STAGES; ++s) { mbar_init(&afull[s], 1); mbar_init(&aempty[s], 1); }
     for (int s = 0; s < C::B_STAGES; ++s) { mbar_init(&bfull[s], 1); mbar_init(&bempty[s], 1); }
     for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 2 * EPI_WARPS); }
+    mbar_init(resfull, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     prefetch_tmap(&tmA);
     prefetch_tmap(&tmB);
@@ -939,6 +943,11 @@ halo_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 
   if (warp == 0) {
     if (lane == 0) {
+      if (RESB) {   // n_tiles_n == 1, nkb == 1: this CTA's BN/2 rows of each of the nine weight tiles, once
+        if (leader) mbar_expect_tx(resfull, 2u * 9u * (uint32_t)C::B_HALF_BYTES);
+        for (int t = 0; t < 9; ++t)
+          tma_load_2d_2sm(sB + t * C::B_HALF_BYTES, &tmB, resfull, 0, t * p.cout + (int)rank * (BN / 2));
+      }
       int sa = 0, sb = 0;
       uint32_t pa = 0, pb = 0;
       for (int item = cluster_id; item < total_items; item += num_clusters) {
@@ -953,11 +962,13 @@ halo_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             tma_load_2d_2sm(sA + sa * a_bytes + bx * box_rows * 128, &tmA, &afull[sa], kb * BK,
                             m0 - wp - 1 + bx * box_rows);
           if (++sa == p.a_stages) { sa = 0; pa ^= 1u; }
-          for (int t = 0; t < 9; ++t) {
-            mbar_wait(&bempty[sb], pb ^ 1u, p.err_flag);
-            if (leader) mbar_expect_tx(&bfull[sb], 2u * (uint32_t)(half * BK * 2));
-            tma_load_2d_2sm(sB + sb * C::B_HALF_BYTES, mb, &bfull[sb], kb * BK, t * p.cout + n0 + (int)rank * half);
-            if (++sb == C::B_STAGES) { sb = 0; pb ^= 1u; }
+          if (!RESB) {
+            for (int t = 0; t < 9; ++t) {
+              mbar_wait(&bempty[sb], pb ^ 1u, p.err_flag);
+              if (leader) mbar_expect_tx(&bfull[sb], 2u * (uint32_t)(half * BK * 2));
+              tma_load_2d_2sm(sB + sb * C::B_HALF_BYTES, mb, &bfull[sb], kb * BK, t * p.cout + n0 + (int)rank * half);
+              if (++sb == C::B_STAGES) { sb = 0; pb ^= 1u; }
+            }
           }
         }
       }
@@ -972,6 +983,10 @@ halo_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       const uint32_t a_step = (uint32_t)a_bytes >> 4;
       int sa = 0, sb = 0;
       uint32_t pa = 0, pb = 0, it = 0;
+      if (RESB) {
+        mbar_wait(resfull, 0, p.err_flag);
+        tc_fence_after();
+      }
       for (int item = cluster_id; item < total_items; item += num_clusters, ++it) {
         const uint32_t acc = it & 1u, acc_phase = (it >> 1) & 1u;
         mbar_wait(&tempty[acc], acc_phase ^ 1u, p.err_flag);
@@ -985,19 +1000,26 @@ halo_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           const uint32_t ablk = a_lo0 + (uint32_t)sa * a_step;
 #pragma unroll
           for (int t = 0; t < 9; ++t) {
-            mbar_wait(&bfull[sb], pb, p.err_flag);
-            tc_fence_after();
-            const uint32_t btile = b_lo0 + (uint32_t)sb * (uint32_t)(C::B_HALF_BYTES >> 4);
+            uint32_t btile;
+            if (RESB) {
+              btile = b_lo0 + (uint32_t)t * (uint32_t)(C::B_HALF_BYTES >> 4);
+            } else {
+              mbar_wait(&bfull[sb], pb, p.err_flag);
+              tc_fence_after();
+              btile = b_lo0 + (uint32_t)sb * (uint32_t)(C::B_HALF_BYTES >> 4);
+            }
             const uint32_t adesc = ablk + (uint32_t)((t / 3) * wp + (t % 3)) * 8u;
             const uint32_t accumulate = (kb | t) ? 1u : 0u;
             if (elect_one()) {
 #pragma unroll
               for (int k = 0; k < BK / 16; ++k)
                 mma_bf16_2sm(d_tmem, desc(adesc + k * 2), desc(btile + k * 2), idesc, (accumulate | (uint32_t)k) ? 1u : 0u);
-              tc_commit_2sm(&bempty[sb]);
+              if (!RESB) tc_commit_2sm(&bempty[sb]);
             }
             __syncwarp();
-            if (++sb == C::B_STAGES) { sb = 0; pb ^= 1u; }
+            if (!RESB) {
+              if (++sb == C::B_STAGES) { sb = 0; pb ^= 1u; }
+            }
           }
           if (elect_one()) tc_commit_2sm(&aempty[sa]);
           __syncwarp();
