@@ -128,6 +128,9 @@ struct ConvLaunch {
   // loads half of an item's weight rows; the smaller boxes serve the N-split tail items)
   CUtensorMap b_half, b_half2, b_half4;
   bool two_cta = false;
+  // 2-CTA shift mode (shift_gemm2_kernel, the stride-2 convs): b0 / b1 with BN/2-row boxes
+  CUtensorMap b0_half, b1_half;
+  bool two_cta_shift = false;
   tc::Params p;
   int bn = 64;
   int rows_per_img = 1;  // Hp*Wp of the output geometry
@@ -143,7 +146,7 @@ static int env_flag(const char* name, int dflt) {
 
 // Configure halo mode for a 3x3 stride-1 conv whose A operand is `base` ([rows, cin], pitch cin).
 // which layer classes run on CTA pairs (tc::halo_gemm2_kernel): bit 0 = 256 / 512 channels, bit 1 = 128, bit 2 = 64
-static int two_cta_mask() { static const int v = env_flag("FR_TC_2CTA", 7); return v; }
+static int two_cta_mask() { static const int v = env_flag("FR_TC_2CTA", 7); return v; }   // bit 3: stride-2 convs (shift_gemm2)
 static bool two_cta_eligible(int bn, int cin) {
   const int m = two_cta_mask();
   return (bn == 256 && (m & 1)) || (bn == 128 && (m & 2)) || (bn == 64 && cin == 64 && (m & 4));
@@ -252,6 +255,23 @@ int tc_launch(fr_ctx* ctx, ConvLaunch& L, int m_rows) {
     else if (L.bn == 128) { if (L.mt == 2) FR_HALO_LAUNCH(128, 2, false); else FR_HALO_LAUNCH(128, 1, false); }
     else { if (L.mt == 2) FR_HALO_LAUNCH(256, 2, false); else FR_HALO_LAUNCH(256, 1, false); }
 #undef FR_HALO_LAUNCH
+    ctx->launches++;
+    FR_CUDA_OK(ctx, cudaGetLastError());
+    return FR_OK;
+  }
+  if (L.two_cta_shift && L.p.k_splits <= 1) {
+    const int items = ceil_div(L.p.num_m_tiles, 2) * L.p.n_tiles_n;
+    const int cgrid = 2 * std::min(items, num_sms / 2);
+#define FR_SHIFT2_LAUNCH(BN_)                                                                                 \
+  do {                                                                                                        \
+    FR_CUDA_OK(ctx, fr_opt_in_smem(ctx, tc::shift_gemm2_kernel<BN_>, tc::Cfg2<BN_>::SMEM_BYTES));              \
+    tc::shift_gemm2_kernel<BN_><<<cgrid, tc::CONV_THREADS, tc::Cfg2<BN_>::SMEM_BYTES, ctx->stream>>>(          \
+        L.a0, L.a1, L.b0_half, L.b1_half, L.p);                                                               \
+  } while (0)
+    if (L.bn == 256) FR_SHIFT2_LAUNCH(256);
+    else if (L.bn == 128) FR_SHIFT2_LAUNCH(128);
+    else FR_SHIFT2_LAUNCH(64);
+#undef FR_SHIFT2_LAUNCH
     ctx->launches++;
     FR_CUDA_OK(ctx, cudaGetLastError());
     return FR_OK;
@@ -926,6 +946,10 @@ static int rec_build_plan(fr_ctx* ctx, int cap) {
       ok = ok && tc_make_map_2d(&c2.a0, bb.h.p, bb.h.rows(cap), bb.h.C, bb.h.C, tc::BM);
       ok = ok && tc_make_map_2d(&c2.a1, xe.p, xe.rows(cap), xe.C, xe.C, tc::BM);
       ok = ok && tc_make_map_2d(&c2.b1, bw.wds, bw.planes, bw.cin, bw.cin, c2.bn);
+      // bit 3 of FR_TC_2CTA: the stride-2 convs on CTA pairs
+      c2.two_cta_shift = ok && (two_cta_mask() & 8) &&
+                         tc_make_map_2d(&c2.b0_half, bw.w2, (uint64_t)9 * bw.planes, bw.planes, bw.planes, c2.bn / 2) &&
+                         tc_make_map_2d(&c2.b1_half, bw.wds, bw.planes, bw.cin, bw.cin, c2.bn / 2);
     } else {
       fill_taps_s1(c2.p, bb.h.Wp, bw.planes, bw.planes);
       c2.p.residual = x.p;
