@@ -128,9 +128,6 @@ struct ConvLaunch {
   // loads half of an item's weight rows; the smaller boxes serve the N-split tail items)
   CUtensorMap b_half, b_half2, b_half4;
   bool two_cta = false;
-  // 2-CTA shift mode (shift_gemm2_kernel, the stride-2 convs): b0 / b1 with BN/2-row boxes
-  CUtensorMap b0_half, b1_half;
-  bool two_cta_shift = false;
   tc::Params p;
   int bn = 64;
   int rows_per_img = 1;  // Hp*Wp of the output geometry
@@ -145,11 +142,11 @@ static int env_flag(const char* name, int dflt) {
 }
 
 // Configure halo mode for a 3x3 stride-1 conv whose A operand is `base` ([rows, cin], pitch cin).
-// which layer classes run on CTA pairs (tc::halo_gemm2_kernel): bit 0 = 256 / 512 channels, bit 1 = 128, bit 2 = 64
-static int two_cta_mask() { static const int v = env_flag("FR_TC_2CTA", 7); return v; }   // bit 3: stride-2 convs (shift_gemm2)
+// the 256 / 512-channel 3x3 stride-1 layers run on CTA pairs (tc::halo_gemm2_kernel); FR_TC_2CTA=0 is the A/B switch
 static bool two_cta_eligible(int bn, int cin) {
-  const int m = two_cta_mask();
-  return (bn == 256 && (m & 1)) || (bn == 128 && (m & 2)) || (bn == 64 && cin == 64 && (m & 4));
+  (void)cin;
+  static const int on = env_flag("FR_TC_2CTA", 1);
+  return on && bn == 256;
 }
 
 static bool tc_setup_halo(ConvLaunch& L, const void* base, uint64_t rows, int cin, int Wp) {
@@ -208,17 +205,15 @@ int tc_launch(fr_ctx* ctx, ConvLaunch& L, int m_rows) {
       }
     }
     const int cgrid = 2 * std::min(items, nclusters);
-#define FR_HALO2_LAUNCH(BN_, RB_)                                                                            \
+#define FR_HALO2_LAUNCH(BN_)                                                                                 \
   do {                                                                                                       \
-    using C2 = tc::Halo2Cfg<BN_, RB_>;                                                                       \
+    using C2 = tc::Halo2Cfg<BN_>;                                                                            \
     L.p.a_stages = std::min(env_flag("FR_TC_ASTAGES2", 2), C2::pick_a_stages(L.p.a_rows));                   \
-    FR_CUDA_OK(ctx, fr_opt_in_smem(ctx, tc::halo_gemm2_kernel<BN_, RB_>, 227 * 1024));                       \
-    tc::halo_gemm2_kernel<BN_, RB_><<<cgrid, tc::CONV_THREADS, C2::smem_bytes(L.p.a_rows, L.p.a_stages),     \
-                                     ctx->stream>>>(L.a_halo, L.b_half, L.b_half2, L.b_half4, L.p);          \
+    FR_CUDA_OK(ctx, fr_opt_in_smem(ctx, tc::halo_gemm2_kernel<BN_>, 227 * 1024));                            \
+    tc::halo_gemm2_kernel<BN_><<<cgrid, tc::CONV_THREADS, C2::smem_bytes(L.p.a_rows, L.p.a_stages),          \
+                                ctx->stream>>>(L.a_halo, L.b_half, L.b_half2, L.b_half4, L.p);               \
   } while (0)
-    if (L.bn == 256) FR_HALO2_LAUNCH(256, false);
-    else if (L.bn == 128) FR_HALO2_LAUNCH(128, false);
-    else FR_HALO2_LAUNCH(64, true);
+    FR_HALO2_LAUNCH(256);
 #undef FR_HALO2_LAUNCH
     ctx->launches++;
     FR_CUDA_OK(ctx, cudaGetLastError());
@@ -255,23 +250,6 @@ int tc_launch(fr_ctx* ctx, ConvLaunch& L, int m_rows) {
     else if (L.bn == 128) { if (L.mt == 2) FR_HALO_LAUNCH(128, 2, false); else FR_HALO_LAUNCH(128, 1, false); }
     else { if (L.mt == 2) FR_HALO_LAUNCH(256, 2, false); else FR_HALO_LAUNCH(256, 1, false); }
 #undef FR_HALO_LAUNCH
-    ctx->launches++;
-    FR_CUDA_OK(ctx, cudaGetLastError());
-    return FR_OK;
-  }
-  if (L.two_cta_shift && L.p.k_splits <= 1) {
-    const int items = ceil_div(L.p.num_m_tiles, 2) * L.p.n_tiles_n;
-    const int cgrid = 2 * std::min(items, num_sms / 2);
-#define FR_SHIFT2_LAUNCH(BN_)                                                                                 \
-  do {                                                                                                        \
-    FR_CUDA_OK(ctx, fr_opt_in_smem(ctx, tc::shift_gemm2_kernel<BN_>, tc::Cfg2<BN_>::SMEM_BYTES));              \
-    tc::shift_gemm2_kernel<BN_><<<cgrid, tc::CONV_THREADS, tc::Cfg2<BN_>::SMEM_BYTES, ctx->stream>>>(          \
-        L.a0, L.a1, L.b0_half, L.b1_half, L.p);                                                               \
-  } while (0)
-    if (L.bn == 256) FR_SHIFT2_LAUNCH(256);
-    else if (L.bn == 128) FR_SHIFT2_LAUNCH(128);
-    else FR_SHIFT2_LAUNCH(64);
-#undef FR_SHIFT2_LAUNCH
     ctx->launches++;
     FR_CUDA_OK(ctx, cudaGetLastError());
     return FR_OK;
@@ -918,7 +896,7 @@ static int rec_build_plan(fr_ctx* ctx, int cap) {
     ok = ok && tc_make_map_2d(&c1.b0, bw.w1, (uint64_t)9 * bw.planes, bw.cin, bw.cin, c1.bn);
     c1.has_b_small = ok && c1.halo && c1.bn > 64 && tc_make_map_2d(&c1.b_small, bw.w1, (uint64_t)9 * bw.planes, bw.cin, bw.cin, 64);
     c1.b1 = c1.b0;
-    c1.two_cta = ok && c1.halo && c1.mt == 1 && two_cta_eligible(c1.bn, bw.cin) && (c1.bn != 64 || c1.resb) &&
+    c1.two_cta = ok && c1.halo && c1.mt == 1 && two_cta_eligible(c1.bn, bw.cin) &&
                  tc_make_map_2d(&c1.b_half, bw.w1, (uint64_t)9 * bw.planes, bw.cin, bw.cin, c1.bn / 2) &&
                  tc_make_map_2d(&c1.b_half2, bw.w1, (uint64_t)9 * bw.planes, bw.cin, bw.cin, std::max(c1.bn / 4, 16)) &&
                  tc_make_map_2d(&c1.b_half4, bw.w1, (uint64_t)9 * bw.planes, bw.cin, bw.cin, std::max(c1.bn / 8, 16));
@@ -946,10 +924,7 @@ static int rec_build_plan(fr_ctx* ctx, int cap) {
       ok = ok && tc_make_map_2d(&c2.a0, bb.h.p, bb.h.rows(cap), bb.h.C, bb.h.C, tc::BM);
       ok = ok && tc_make_map_2d(&c2.a1, xe.p, xe.rows(cap), xe.C, xe.C, tc::BM);
       ok = ok && tc_make_map_2d(&c2.b1, bw.wds, bw.planes, bw.cin, bw.cin, c2.bn);
-      // bit 3 of FR_TC_2CTA: the stride-2 convs on CTA pairs
-      c2.two_cta_shift = ok && (two_cta_mask() & 8) &&
-                         tc_make_map_2d(&c2.b0_half, bw.w2, (uint64_t)9 * bw.planes, bw.planes, bw.planes, c2.bn / 2) &&
-                         tc_make_map_2d(&c2.b1_half, bw.wds, bw.planes, bw.cin, bw.cin, c2.bn / 2);
+
     } else {
       fill_taps_s1(c2.p, bb.h.Wp, bw.planes, bw.planes);
       c2.p.residual = x.p;
@@ -959,7 +934,7 @@ static int rec_build_plan(fr_ctx* ctx, int cap) {
     }
     ok = ok && tc_make_map_2d(&c2.b0, bw.w2, (uint64_t)9 * bw.planes, bw.planes, bw.planes, c2.bn);
     c2.has_b_small = ok && c2.halo && c2.bn > 64 && tc_make_map_2d(&c2.b_small, bw.w2, (uint64_t)9 * bw.planes, bw.planes, bw.planes, 64);
-    c2.two_cta = ok && c2.halo && c2.mt == 1 && two_cta_eligible(c2.bn, bw.planes) && (c2.bn != 64 || c2.resb) &&
+    c2.two_cta = ok && c2.halo && c2.mt == 1 && two_cta_eligible(c2.bn, bw.planes) &&
                  tc_make_map_2d(&c2.b_half, bw.w2, (uint64_t)9 * bw.planes, bw.planes, bw.planes, c2.bn / 2) &&
                  tc_make_map_2d(&c2.b_half2, bw.w2, (uint64_t)9 * bw.planes, bw.planes, bw.planes, std::max(c2.bn / 4, 16)) &&
                  tc_make_map_2d(&c2.b_half4, bw.w2, (uint64_t)9 * bw.planes, bw.planes, bw.planes, std::max(c2.bn / 8, 16));
@@ -1251,7 +1226,7 @@ int rec_test_conv(fr_ctx* ctx, const float* x, int n, int cin, int h, int w, con
   L.b1 = L.b0;
   if (ok && ksize == 3) ok = tc_setup_halo(L, d_x, rows, cin, Wp);
   L.has_b_small = ok && L.halo && L.bn > 64 && tc_make_map_2d(&L.b_small, d_w, (uint64_t)ksize * ksize * cout, cin, cin, 64);
-  L.two_cta = ok && L.halo && L.mt == 1 && two_cta_eligible(L.bn, cin) && (L.bn != 64 || L.resb) &&
+  L.two_cta = ok && L.halo && L.mt == 1 && two_cta_eligible(L.bn, cin) &&
               tc_make_map_2d(&L.b_half, d_w, (uint64_t)9 * cout, cin, cin, L.bn / 2) &&
               tc_make_map_2d(&L.b_half2, d_w, (uint64_t)9 * cout, cin, cin, std::max(L.bn / 4, 16)) &&
               tc_make_map_2d(&L.b_half4, d_w, (uint64_t)9 * cout, cin, cin, std::max(L.bn / 8, 16));

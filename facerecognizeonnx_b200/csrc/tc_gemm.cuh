@@ -812,6 +812,10 @@ halo_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 //     tempty barrier.
 // Tail items (last partial wave) are split along N like in halo_gemm_kernel: N = BN / tail_split, each
 // CTA loading N/2 weight rows through the map with the matching box height.
+// Used for BN = 256 only.  Measured on B200 (profiles/r2_two_cta_mask_sweep.txt): the pair pays where the
+// MMA is long (N = 256: 128 clk per instruction): trunk 6.01 -> 5.76 ms; with N = 64 MMAs (32 clk) the
+// 64-channel layers got 40 % SLOWER (the pair's per-instruction hand-shake dominates), N = 128 gave nothing,
+// and the stride-2 convs on pairs (per-tap A tiles, half weight tiles) measured 5.835 vs 5.836 ms.
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
   asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
@@ -859,11 +863,11 @@ __device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, uint32_t rank
       : "memory");
 }
 
-template <int BN, bool RESB> struct Halo2Cfg {
+template <int BN> struct Halo2Cfg {
   static constexpr int B_HALF_BYTES = (BN / 2) * BK * 2;   // this CTA's half of one weight tile
   static constexpr int MAX_A_STAGES = 6;
   static constexpr int B_STAGES = 6;
-  static constexpr int B_BYTES = RESB ? 9 * B_HALF_BYTES : B_STAGES * B_HALF_BYTES;   // RESB: all nine taps resident
+  static constexpr int B_BYTES = B_STAGES * B_HALF_BYTES;
   static constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;   // double-buffered accumulators
   static int smem_bytes(int a_rows, int a_stages) { return a_stages * a_rows * 128 + B_BYTES + 256 + 1024; }
   static int pick_a_stages(int a_rows) {
@@ -873,13 +877,12 @@ template <int BN, bool RESB> struct Halo2Cfg {
   }
 };
 
-// RESB (Cin == 64, one K block): the CTA's halves of all nine weight tiles stay resident in shared memory.
-template <int BN, bool RESB>
+template <int BN>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CONV_THREADS, 1)
 halo_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                   const __grid_constant__ CUtensorMap tmB2, const __grid_constant__ CUtensorMap tmB4,
                   const __grid_constant__ Params p) {
-  using C = Halo2Cfg<BN, RESB>;
+  using C = Halo2Cfg<BN>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
@@ -892,8 +895,7 @@ halo_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   uint64_t* bempty = bfull + C::B_STAGES;
   uint64_t* tfull = bempty + C::B_STAGES;
   uint64_t* tempty = tfull + 2;
-  uint64_t* resfull = tempty + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(resfull + 1);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -903,7 +905,6 @@ halo_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     for (int s = 0; s < C::MAX_A_STAGES; ++s) { mbar_init(&afull[s], 1); mbar_init(&aempty[s], 1); }
     for (int s = 0; s < C::B_STAGES; ++s) { mbar_init(&bfull[s], 1); mbar_init(&bempty[s], 1); }
     for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 2 * EPI_WARPS); }
-    mbar_init(resfull, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     prefetch_tmap(&tmA);
     prefetch_tmap(&tmB);
@@ -943,11 +944,6 @@ halo_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 
   if (warp == 0) {
     if (lane == 0) {
-      if (RESB) {   // n_tiles_n == 1, nkb == 1: this CTA's BN/2 rows of each of the nine weight tiles, once
-        if (leader) mbar_expect_tx(resfull, 2u * 9u * (uint32_t)C::B_HALF_BYTES);
-        for (int t = 0; t < 9; ++t)
-          tma_load_2d_2sm(sB + t * C::B_HALF_BYTES, &tmB, resfull, 0, t * p.cout + (int)rank * (BN / 2));
-      }
       int sa = 0, sb = 0;
       uint32_t pa = 0, pb = 0;
       for (int item = cluster_id; item < total_items; item += num_clusters) {
@@ -962,13 +958,11 @@ halo_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             tma_load_2d_2sm(sA + sa * a_bytes + bx * box_rows * 128, &tmA, &afull[sa], kb * BK,
                             m0 - wp - 1 + bx * box_rows);
           if (++sa == p.a_stages) { sa = 0; pa ^= 1u; }
-          if (!RESB) {
-            for (int t = 0; t < 9; ++t) {
-              mbar_wait(&bempty[sb], pb ^ 1u, p.err_flag);
-              if (leader) mbar_expect_tx(&bfull[sb], 2u * (uint32_t)(half * BK * 2));
-              tma_load_2d_2sm(sB + sb * C::B_HALF_BYTES, mb, &bfull[sb], kb * BK, t * p.cout + n0 + (int)rank * half);
-              if (++sb == C::B_STAGES) { sb = 0; pb ^= 1u; }
-            }
+          for (int t = 0; t < 9; ++t) {
+            mbar_wait(&bempty[sb], pb ^ 1u, p.err_flag);
+            if (leader) mbar_expect_tx(&bfull[sb], 2u * (uint32_t)(half * BK * 2));
+            tma_load_2d_2sm(sB + sb * C::B_HALF_BYTES, mb, &bfull[sb], kb * BK, t * p.cout + n0 + (int)rank * half);
+            if (++sb == C::B_STAGES) { sb = 0; pb ^= 1u; }
           }
         }
       }
@@ -983,10 +977,6 @@ halo_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       const uint32_t a_step = (uint32_t)a_bytes >> 4;
       int sa = 0, sb = 0;
       uint32_t pa = 0, pb = 0, it = 0;
-      if (RESB) {
-        mbar_wait(resfull, 0, p.err_flag);
-        tc_fence_after();
-      }
       for (int item = cluster_id; item < total_items; item += num_clusters, ++it) {
         const uint32_t acc = it & 1u, acc_phase = (it >> 1) & 1u;
         mbar_wait(&tempty[acc], acc_phase ^ 1u, p.err_flag);
@@ -1000,26 +990,19 @@ halo_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           const uint32_t ablk = a_lo0 + (uint32_t)sa * a_step;
 #pragma unroll
           for (int t = 0; t < 9; ++t) {
-            uint32_t btile;
-            if (RESB) {
-              btile = b_lo0 + (uint32_t)t * (uint32_t)(C::B_HALF_BYTES >> 4);
-            } else {
-              mbar_wait(&bfull[sb], pb, p.err_flag);
-              tc_fence_after();
-              btile = b_lo0 + (uint32_t)sb * (uint32_t)(C::B_HALF_BYTES >> 4);
-            }
+            mbar_wait(&bfull[sb], pb, p.err_flag);
+            tc_fence_after();
+            const uint32_t btile = b_lo0 + (uint32_t)sb * (uint32_t)(C::B_HALF_BYTES >> 4);
             const uint32_t adesc = ablk + (uint32_t)((t / 3) * wp + (t % 3)) * 8u;
             const uint32_t accumulate = (kb | t) ? 1u : 0u;
             if (elect_one()) {
 #pragma unroll
               for (int k = 0; k < BK / 16; ++k)
                 mma_bf16_2sm(d_tmem, desc(adesc + k * 2), desc(btile + k * 2), idesc, (accumulate | (uint32_t)k) ? 1u : 0u);
-              if (!RESB) tc_commit_2sm(&bempty[sb]);
+              tc_commit_2sm(&bempty[sb]);
             }
             __syncwarp();
-            if (!RESB) {
-              if (++sb == C::B_STAGES) { sb = 0; pb ^= 1u; }
-            }
+            if (++sb == C::B_STAGES) { sb = 0; pb ^= 1u; }
           }
           if (elect_one()) tc_commit_2sm(&aempty[sa]);
           __syncwarp();
@@ -1067,158 +1050,5 @@ halo_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   }
 }
 
-
-// ------------------------------------------------------- 2-CTA shift-GEMM kernel
-// The stride-2 convolutions (+ fused 1x1 shortcut tap) on CTA pairs: same scheme as halo_gemm2_kernel
-// with per-tap A tiles.  Work item = 256 rows x BN columns; each CTA loads its own 128 x 64 A tile and
-// its half (BN/2 rows) of the weight tile per stage, the leader issues M = 256 MMAs.  These layers
-// re-stream a full weight tile per 16 KB of activations (two thirds of the L2 -> shared-memory traffic
-// at 256 channels, tensor pipe 60-67 %); the pair halves it.
-template <int BN> struct Cfg2 {
-  static constexpr int B_HALF_BYTES = (BN / 2) * BK * 2;
-  static constexpr int STAGE_BYTES = A_TILE_BYTES + B_HALF_BYTES;
-  static constexpr int STAGES = BN == 256 ? 6 : 8;
-  static constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 256 + 1024;
-};
-
-template <int BN>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CONV_THREADS, 1)
-shift_gemm2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
-                   const __grid_constant__ CUtensorMap tmB0, const __grid_constant__ CUtensorMap tmB1,
-                   const __grid_constant__ Params p) {
-  using C = Cfg2<BN>;
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
-                                             ~static_cast<uintptr_t>(1023));
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE_BYTES);
-  uint64_t* empty = full + C::STAGES;
-  uint64_t* tfull = empty + C::STAGES;
-  uint64_t* tempty = tfull + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
-
-  const int warp = threadIdx.x >> 5;
-  const int lane = threadIdx.x & 31;
-  const uint32_t rank = cluster_ctarank();
-  const bool leader = rank == 0;
-  if (warp == 0 && lane == 0) {
-    for (int s = 0; s < C::STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 2 * EPI_WARPS); }
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    prefetch_tmap(&tmA0);
-    prefetch_tmap(&tmA1);
-    prefetch_tmap(&tmB0);
-    prefetch_tmap(&tmB1);
-  }
-  if (warp == 2) {
-    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
-                 "r"((uint32_t)C::TMEM_COLS)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
-  }
-  tc_fence_before();
-  __syncthreads();
-  cluster_sync_all();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-
-  const int num_super = (p.num_m_tiles + 1) / 2;
-  const int total_items = num_super * p.n_tiles_n;
-  const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
-
-  if (warp == 0) {
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int item = cluster_id; item < total_items; item += num_clusters) {
-        const int m0 = (item / p.n_tiles_n) * (2 * BM) + (int)rank * BM;
-        const int n0 = (item % p.n_tiles_n) * BN + (int)rank * (BN / 2);
-        for (int t = 0; t < p.num_taps; ++t) {
-          const Tap tp = p.taps[t];
-          const CUtensorMap* ma = tp.a_src ? &tmA1 : &tmA0;
-          const CUtensorMap* mb = tp.b_src ? &tmB1 : &tmB0;
-          for (int kb = 0; kb < tp.nkb; ++kb) {
-            mbar_wait(&empty[stage], phase ^ 1u, p.err_flag);
-            if (leader) mbar_expect_tx(&full[stage], 2u * (uint32_t)C::STAGE_BYTES);
-            uint8_t* sa = smem + stage * C::STAGE_BYTES;
-            tma_load_2d_2sm(sa, ma, &full[stage], tp.a_col + kb * BK, m0 + tp.a_row_shift);
-            tma_load_2d_2sm(sa + A_TILE_BYTES, mb, &full[stage], kb * BK, tp.b_row + n0);
-            if (++stage == C::STAGES) { stage = 0; phase ^= 1u; }
-          }
-        }
-      }
-    }
-  } else if (warp == 1) {
-    if (leader) {
-      constexpr uint32_t idesc = make_idesc(2 * BM, BN);
-      const uint64_t d0 = make_smem_desc(smem);
-      const uint32_t desc_hi = (uint32_t)(d0 >> 32);
-      const uint32_t lo0 = (uint32_t)d0;
-      auto desc = [&](uint32_t lo) { return ((uint64_t)desc_hi << 32) | (uint64_t)lo; };
-      int stage = 0;
-      uint32_t phase = 0, it = 0;
-      for (int item = cluster_id; item < total_items; item += num_clusters, ++it) {
-        const uint32_t acc = it & 1u, acc_phase = (it >> 1) & 1u;
-        mbar_wait(&tempty[acc], acc_phase ^ 1u, p.err_flag);
-        tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * BN;
-        uint32_t accumulate = 0;
-        for (int t = 0; t < p.num_taps; ++t) {
-          const int nkb = p.taps[t].nkb;
-          for (int kb = 0; kb < nkb; ++kb) {
-            mbar_wait(&full[stage], phase, p.err_flag);
-            tc_fence_after();
-            const uint32_t alo = lo0 + (uint32_t)stage * (uint32_t)(C::STAGE_BYTES >> 4);
-            const uint32_t blo = alo + (uint32_t)(A_TILE_BYTES >> 4);
-            if (elect_one()) {
-#pragma unroll
-              for (int k = 0; k < BK / 16; ++k)
-                mma_bf16_2sm(d_tmem, desc(alo + k * 2), desc(blo + k * 2), idesc, (accumulate | (uint32_t)k) ? 1u : 0u);
-              tc_commit_2sm(&empty[stage]);
-            }
-            __syncwarp();
-            accumulate = 1;
-            if (++stage == C::STAGES) { stage = 0; phase ^= 1u; }
-          }
-        }
-        if (elect_one()) tc_commit_2sm(&tfull[acc]);
-        __syncwarp();
-      }
-    }
-  } else {
-    const int q = warp & 3;
-    const int row = q * 32 + lane;
-    constexpr int CPS = BN / 32 / (EPI_WARPS / 4);
-    const int c_begin = ((warp - 2) >> 2) * CPS;
-    uint32_t it = 0;
-    for (int item = cluster_id; item < total_items; item += num_clusters, ++it) {
-      const int m0 = (item / p.n_tiles_n) * (2 * BM) + (int)rank * BM;
-      const int n0 = (item % p.n_tiles_n) * BN;
-      const uint32_t acc = it & 1u, acc_phase = (it >> 1) & 1u;
-      const EpiRow er = epi_row(p, m0 + row, n0, 0);
-      uint4 rv[4];
-      epi_load_res(er, c_begin, rv);
-      mbar_wait(&tfull[acc], acc_phase, p.err_flag);
-      tc_fence_after();
-      const uint32_t taddr0 = tmem_base + acc * BN + ((uint32_t)(q * 32) << 16);
-      epilogue_tile<BN>(p, er, taddr0, n0, 0, c_begin, c_begin + CPS, rv);
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) {
-        if (leader) mbar_arrive(&tempty[acc]);
-        else mbar_arrive_cluster(&tempty[acc], 0);
-      }
-    }
-  }
-  tc_fence_before();
-  __syncthreads();
-  cluster_sync_all();
-  if (warp == 2) {
-    tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
-                 "r"((uint32_t)C::TMEM_COLS)
-                 : "memory");
-  }
-}
 
 }  // namespace tc
