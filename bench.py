@@ -370,11 +370,11 @@ def run_gpu(args, rank, world, local_rank):
     tc_flop = n_faces * args.steps * (GFLOP_PER_FACE_TOTAL - GFLOP_PER_FACE_STEM) * 1e9
     achieved = tc_flop / trunk_s / 1e12 if trunk_s > 0 else 0.0
     traffic, traffic_src = None, None
-    tp = os.path.join(ROOT, "profiles", "r1_tc_traffic.json")
+    tp = os.path.join(ROOT, "profiles", "r2_tc_traffic.json")
     if os.path.exists(tp):   # dram__bytes_read+write per launch from the committed ncu capture of this family
         tj = json.load(open(tp))
-        traffic, traffic_src = tj["traffic_bytes_per_launch"], "profiles/r1_tc_traffic.json (ncu, averaged over the 49 launches)"
-    roofline = {"bound": "tensor", "kernel": "tc::halo_gemm_kernel / tc::shift_gemm_kernel <64|128|256> (IResNet-50 convs + FC)",
+        traffic, traffic_src = tj["traffic_bytes_per_launch"], "profiles/r2_tc_traffic.json (ncu, averaged over the 49 launches)"
+    roofline = {"bound": "tensor", "kernel": "tc::halo_gemm2_kernel<256> (CTA pairs) / tc::halo_gemm_kernel / tc::shift_gemm_kernel <64|128|256> (IResNet-50 convs + FC)",
                 "achieved": achieved, "peak": peaks["tflops_sustained"], "unit": "TFLOP/s",
                 "frac": achieved / peaks["tflops_sustained"], "peak_source": peaks["source"] + " (sustained bf16)",
                 "traffic": traffic, "traffic_source": traffic_src,
