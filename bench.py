@@ -500,7 +500,7 @@ def bench_configs_1_to_3(ctx, capi, torch, dev, stream, frames_dev, pad_np, rank
 
 
 def bench_gallery(ctx, capi, torch, dist, dev, rank, world, stream, peaks, rows_per_gpu=1_250_000, nq=4096, k=10,
-                  iters=5):
+                  iters=20):
     """1:N search: each rank holds rows_per_gpu synthetic unit rows (bf16, generated on the
     device), searches the same nq queries, the per-rank top-k lists are all-gathered over NCCL and
     merged.  Returns queries/s over the whole job (max over ranks) and per-GPU GEMM TFLOP/s."""

@@ -128,6 +128,9 @@ struct ConvLaunch {
   // loads half of an item's weight rows; the smaller boxes serve the N-split tail items)
   CUtensorMap b_half, b_half2, b_half4;
   bool two_cta = false;
+  // TMA-store epilogue (halo mode, OUT_STD, one N tile): the output tensor as [rows, cout], box 128 rows x 64 columns
+  CUtensorMap out_map;
+  bool tma_store = false;
   tc::Params p;
   int bn = 64;
   int rows_per_img = 1;  // Hp*Wp of the output geometry
@@ -239,11 +242,15 @@ int tc_launch(fr_ctx* ctx, ConvLaunch& L, int m_rows) {
     const int hgrid = std::min(items, num_sms);
 #define FR_HALO_LAUNCH(BN_, MT_, RB_)                                                              \
   do {                                                                                             \
+    using HC = tc::HaloCfg<BN_, MT_, RB_>;                                                         \
     FR_CUDA_OK(ctx, fr_opt_in_smem(ctx, tc::halo_gemm_kernel<BN_, MT_, RB_>, 227 * 1024));         \
-    L.p.a_stages = std::min(env_flag("FR_TC_ASTAGES", 2), tc::HaloCfg<BN_, MT_, RB_>::pick_a_stages(L.p.a_rows)); \
+    /* staging tiles only where they fit beside two A blocks and the weights */                    \
+    const bool ts = L.tma_store && BN_ <= 128 && HC::smem_bytes(L.p.a_rows, 2, true) <= 227 * 1024; \
+    L.p.tma_store = ts ? 1 : 0;                                                                    \
+    L.p.a_stages = std::min(env_flag("FR_TC_ASTAGES", 2), HC::pick_a_stages(L.p.a_rows, ts));      \
     tc::halo_gemm_kernel<BN_, MT_, RB_><<<hgrid, tc::CONV_THREADS,                                  \
-        tc::HaloCfg<BN_, MT_, RB_>::smem_bytes(L.p.a_rows, L.p.a_stages), ctx->stream>>>(            \
-        L.a_halo, L.b0, L.has_b_small ? L.b_small : L.b0, L.p);                                     \
+        HC::smem_bytes(L.p.a_rows, L.p.a_stages, ts), ctx->stream>>>(                               \
+        L.a_halo, L.b0, L.has_b_small ? L.b_small : L.b0, ts ? L.out_map : L.a_halo, L.p);          \
   } while (0)
     if (L.bn == 64 && L.resb) { if (L.mt == 2) FR_HALO_LAUNCH(64, 2, true); else FR_HALO_LAUNCH(64, 1, true); }
     else if (L.bn == 64) { if (L.mt == 2) FR_HALO_LAUNCH(64, 2, false); else FR_HALO_LAUNCH(64, 1, false); }
@@ -896,6 +903,8 @@ static int rec_build_plan(fr_ctx* ctx, int cap) {
     ok = ok && tc_make_map_2d(&c1.b0, bw.w1, (uint64_t)9 * bw.planes, bw.cin, bw.cin, c1.bn);
     c1.has_b_small = ok && c1.halo && c1.bn > 64 && tc_make_map_2d(&c1.b_small, bw.w1, (uint64_t)9 * bw.planes, bw.cin, bw.cin, 64);
     c1.b1 = c1.b0;
+    c1.tma_store = ok && c1.halo && env_flag("FR_TC_TMASTORE", 1) && c1.p.out_mode == tc::OUT_STD && c1.p.n_tiles_n == 1 &&
+                   c1.bn <= 128 && tc_make_map_2d(&c1.out_map, bb.h.p, bb.h.rows(cap), bb.h.C, bb.h.C, tc::BM);
     c1.two_cta = ok && c1.halo && c1.mt == 1 && two_cta_eligible(c1.bn, bw.cin) &&
                  tc_make_map_2d(&c1.b_half, bw.w1, (uint64_t)9 * bw.planes, bw.cin, bw.cin, c1.bn / 2) &&
                  tc_make_map_2d(&c1.b_half2, bw.w1, (uint64_t)9 * bw.planes, bw.cin, bw.cin, std::max(c1.bn / 4, 16)) &&
@@ -934,6 +943,8 @@ static int rec_build_plan(fr_ctx* ctx, int cap) {
     }
     ok = ok && tc_make_map_2d(&c2.b0, bw.w2, (uint64_t)9 * bw.planes, bw.planes, bw.planes, c2.bn);
     c2.has_b_small = ok && c2.halo && c2.bn > 64 && tc_make_map_2d(&c2.b_small, bw.w2, (uint64_t)9 * bw.planes, bw.planes, bw.planes, 64);
+    c2.tma_store = ok && c2.halo && env_flag("FR_TC_TMASTORE", 1) && c2.p.out_mode == tc::OUT_STD && c2.p.n_tiles_n == 1 &&
+                   c2.bn <= 128 && tc_make_map_2d(&c2.out_map, bb.out.p, bb.out.rows(cap), bb.out.C, bb.out.C, tc::BM);
     c2.two_cta = ok && c2.halo && c2.mt == 1 && two_cta_eligible(c2.bn, bw.planes) &&
                  tc_make_map_2d(&c2.b_half, bw.w2, (uint64_t)9 * bw.planes, bw.planes, bw.planes, c2.bn / 2) &&
                  tc_make_map_2d(&c2.b_half2, bw.w2, (uint64_t)9 * bw.planes, bw.planes, bw.planes, std::max(c2.bn / 4, 16)) &&
@@ -1226,6 +1237,8 @@ int rec_test_conv(fr_ctx* ctx, const float* x, int n, int cin, int h, int w, con
   L.b1 = L.b0;
   if (ok && ksize == 3) ok = tc_setup_halo(L, d_x, rows, cin, Wp);
   L.has_b_small = ok && L.halo && L.bn > 64 && tc_make_map_2d(&L.b_small, d_w, (uint64_t)ksize * ksize * cout, cin, cin, 64);
+  L.tma_store = ok && L.halo && env_flag("FR_TC_TMASTORE", 1) && L.p.n_tiles_n == 1 && L.bn <= 128 &&
+                tc_make_map_2d(&L.out_map, d_y, rows, cout, cout, tc::BM);
   L.two_cta = ok && L.halo && L.mt == 1 && two_cta_eligible(L.bn, cin) &&
               tc_make_map_2d(&L.b_half, d_w, (uint64_t)9 * cout, cin, cin, L.bn / 2) &&
               tc_make_map_2d(&L.b_half2, d_w, (uint64_t)9 * cout, cin, cin, std::max(L.bn / 4, 16)) &&

@@ -89,6 +89,10 @@ struct Params {
   // PReLU slopes in the kernel-parameter (constant) bank: every lane of the epilogue reads the same 32
   // slopes per chunk, so they come through the constant cache instead of 8 L1 loads per thread and chunk
   int prelu_in_params;
+  // halo mode, OUT_STD, one N tile: the epilogue stages the bf16 tile in shared memory (SWIZZLE_128B) and the
+  // tile leaves through cp.async.bulk.tensor stores (whole 128-byte lines from the async proxy) instead of
+  // lane-per-row 16-byte st.global, which cap at ~1.5 TB/s (the 64-channel layers were bound by exactly that)
+  int tma_store;
   __align__(16) float prelu_c[512];
 };
 
@@ -191,6 +195,25 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, u
 }
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
+}
+// TMA store of one box shared -> global (bulk async-group completion); rows outside the tensor are clipped
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+               :
+               : "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(src)), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// wait until at most N of this thread's bulk groups still READ their shared-memory source
+template <int N> __device__ __forceinline__ void tma_store_wait_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void named_bar_sync(int id, int threads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
+}
+__device__ __forceinline__ void sts_u4(uint32_t addr, const uint4& v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
 __device__ __forceinline__ void tc_fence_before() {
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -310,9 +333,12 @@ __device__ __forceinline__ void epi_load_res(const EpiRow& r, int c, uint4 (&rv)
 // Epilogue of one output tile for one thread (= one accumulator row): TMEM -> registers ->
 // bias / PReLU / residual -> global.  All 32 lanes of the warp must call it (tcgen05.ld).
 // rv holds the residual of chunk c_begin (epi_load_res, issued by the caller before its wait).
+// stage != 0: shared address of this 128-row sub-tile's staging buffer ([BN/64 boxes][128 rows][128 B],
+// SWIZZLE_128B); the OUT_STD tile goes there (zeros for halo / out-of-range rows) instead of to global memory.
 template <int BN>
 __device__ __forceinline__ void epilogue_tile(const Params& p, const EpiRow& er, uint32_t taddr0, int n0, int split,
-                                              int c_begin, int c_end, uint4 (&rv)[4]) {
+                                              int c_begin, int c_end, uint4 (&rv)[4], uint32_t stage = 0,
+                                              int tile_row = 0) {
   const bool valid = er.valid;
   const float* bias = p.bias + (size_t)er.cls * p.cout + n0;
   const float bias_on = split == 0 ? 1.f : 0.f;
@@ -384,15 +410,29 @@ __device__ __forceinline__ void epilogue_tile(const Params& p, const EpiRow& er,
           pk[i].z = pack_bf16(f[i * 8 + 4], f[i * 8 + 5]);
           pk[i].w = pack_bf16(f[i * 8 + 6], f[i * 8 + 7]);
         }
-        uint4* o = reinterpret_cast<uint4*>(p.out + out_off + c * 32);
+        if (stage) {
+          // 32 columns = 64 bytes = chunks [4 * (c & 1), +4) of the 128-byte row of box c / 2
+          const uint32_t base = stage + (uint32_t)(c >> 1) * (128u * 128u) + (uint32_t)tile_row * 128u;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) __stcs(o + i, pk[i]);
+          for (int i = 0; i < 4; ++i)
+            sts_u4(base + (uint32_t)((((c & 1) * 4 + i) ^ (tile_row & 7)) << 4), pk[i]);
+        } else {
+          uint4* o = reinterpret_cast<uint4*>(p.out + out_off + c * 32);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) __stcs(o + i, pk[i]);
+        }
         if (write_even) {
           uint4* oe = reinterpret_cast<uint4*>(p.out_even + even_off + c * 32);
 #pragma unroll
           for (int i = 0; i < 4; ++i) __stcs(oe + i, pk[i]);
         }
       }
+    }
+    if (stage && !valid) {
+      const uint32_t base = stage + (uint32_t)(c >> 1) * (128u * 128u) + (uint32_t)tile_row * 128u;
+      const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) sts_u4(base + (uint32_t)((((c & 1) * 4 + i) ^ (tile_row & 7)) << 4), z);
     }
     if (c + 1 < c_end && has_res) {
 #pragma unroll
@@ -575,10 +615,14 @@ template <int BN, int MT, bool RESB> struct HaloCfg {
   static constexpr int ACC_STAGES = (2 * MT * BN <= 512) ? 2 : 1;
   static constexpr int TMEM_COLS = ACC_STAGES * MT * BN < 32 ? 32 : ACC_STAGES * MT * BN;
   static constexpr int B_BYTES = RESB ? 9 * B_TILE_BYTES : B_STAGES * B_TILE_BYTES;
-  static int smem_bytes(int a_rows, int a_stages) { return a_stages * a_rows * 128 + B_BYTES + 256 + 1024; }
-  static int pick_a_stages(int a_rows) {
+  // TMA-store staging: two buffers (the store of sub-tile i drains while sub-tile i + 1 is written) of BN/64 boxes
+  static constexpr int STAGE_OUT_BYTES = (BN / 64) * 128 * 128;
+  static int smem_bytes(int a_rows, int a_stages, bool tma_store = false) {
+    return a_stages * a_rows * 128 + B_BYTES + 256 + 1024 + (tma_store ? 2 * STAGE_OUT_BYTES + 1024 : 0);
+  }
+  static int pick_a_stages(int a_rows, bool tma_store = false) {
     int s = 2;
-    while (s < MAX_A_STAGES && smem_bytes(a_rows, s + 1) <= 227 * 1024) ++s;
+    while (s < MAX_A_STAGES && smem_bytes(a_rows, s + 1, tma_store) <= 227 * 1024) ++s;
     return s;
   }
 };
@@ -589,7 +633,8 @@ template <int BN, int MT, bool RESB> struct HaloCfg {
 template <int BN, int MT, bool RESB>
 __global__ void __launch_bounds__(CONV_THREADS, 1)
 halo_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                 const __grid_constant__ CUtensorMap tmBs, const __grid_constant__ Params p) {
+                 const __grid_constant__ CUtensorMap tmBs, const __grid_constant__ CUtensorMap tmOut,
+                 const __grid_constant__ Params p) {
   using C = HaloCfg<BN, MT, RESB>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
@@ -605,10 +650,14 @@ halo_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   uint64_t* tempty = tfull + 2;
   uint64_t* resfull = tempty + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(resfull + 1);
+  // TMA-store staging (1024-byte aligned for SWIZZLE_128B), after the 256-byte barrier block
+  uint8_t* sOut = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(sB + C::B_BYTES + 256) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   if (warp == 0 && lane == 0) {
+    if (p.tma_store) prefetch_tmap(&tmOut);
     for (int s = 0; s < C::MAX_A_STAGES; ++s) { mbar_init(&afull[s], 1); mbar_init(&aempty[s], 1); }
     for (int s = 0; s < C::B_STAGES; ++s) { mbar_init(&bfull[s], 1); mbar_init(&bempty[s], 1); }
     for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], EPI_WARPS); }
@@ -755,7 +804,7 @@ halo_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int row = q * 32 + lane;
     constexpr int CPS = BN / 32 / (EPI_WARPS / 4);   // 32-column chunks per warp
     const int c_begin = ((warp - 2) >> 2) * CPS;
-    uint32_t it = 0;
+    uint32_t it = 0, st_count = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
       int m0, n0, nlen;
       item_coords(tile, m0, n0, nlen);
@@ -769,10 +818,28 @@ halo_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       epi_load_res(er, cb, rv);
       mbar_wait(&tfull[acc], acc_phase, p.err_flag);
       tc_fence_after();
+      const bool staged = p.tma_store && nlen == BN;
 #pragma unroll 1
       for (int mt = 0; mt < MT; ++mt) {
         const uint32_t taddr0 = tmem_base + acc * (MT * BN) + mt * BN + ((uint32_t)(q * 32) << 16);
-        epilogue_tile<BN>(p, er, taddr0, n0, 0, cb, cb + cps, rv);
+        // staged: sub-tile st uses staging buffer st & 1.  The issuing thread (warp 2, lane 0) has waited until
+        // the store that last read this buffer (two sub-tiles ago) is done with it; barrier 1 tells everyone.
+        if (staged) named_bar_sync(1, EPI_WARPS * 32);
+        const uint32_t stage = staged ? smem_u32(sOut) + (st_count & 1u) * (uint32_t)C::STAGE_OUT_BYTES : 0u;
+        epilogue_tile<BN>(p, er, taddr0, n0, 0, cb, cb + cps, rv, stage, row);
+        if (staged) {
+          fence_proxy_async_smem();                 // generic-proxy writes -> visible to the TMA engine
+          named_bar_sync(2, EPI_WARPS * 32);
+          if (warp == 2 && lane == 0) {
+#pragma unroll
+            for (int bx = 0; bx < BN / 64; ++bx)
+              tma_store_2d(&tmOut, sOut + (st_count & 1u) * C::STAGE_OUT_BYTES + bx * (128 * 128), n0 + bx * 64,
+                           m0 + mt * BM);
+            tma_store_commit();
+            tma_store_wait_read<1>();               // the OTHER buffer (previous sub-tile's store) is free again
+          }
+          ++st_count;
+        }
         if (mt + 1 < MT) {
           er = epi_row(p, m0 + (mt + 1) * BM + row, n0, 0);
           epi_load_res(er, cb, rv);
@@ -782,6 +849,8 @@ halo_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty[acc]);
     }
+    // the bulk stores must have finished reading shared memory before the CTA exits
+    if (p.tma_store && warp == 2 && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   }
   tc_fence_before();
   __syncthreads();

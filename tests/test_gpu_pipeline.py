@@ -167,3 +167,36 @@ def test_pipeline_submit_wait_matches_sync(ctx, capi):
         assert np.array_equal(got[1], exp[1])
         assert np.array_equal(got[2], exp[2])
         assert np.array_equal(got[3], exp[3])
+
+
+def test_detect_edge_cases_vs_oracle(ctx, capi, det_wdict):
+    """The reference's guard rails and awkward inputs (src/face_detector.cpp:139-222): tiny and huge frames,
+    extreme aspect ratios, ragged batches, no detection above the threshold, thresholds at their limits."""
+    rng = np.random.default_rng(47)
+    det = odet.FaceDetector(det_wdict)
+    shapes = [(1, 1), (2, 3), (7, 640), (640, 7), (1080, 1920), (1920, 1080), (641, 639), (333, 517)]
+    ims = [rng.integers(0, 256, (h, w, 3), dtype=np.uint8) for h, w in shapes]
+    batch = ctx.detect_batch(ims, 0.02, 0.4, cap=4096)          # ragged batch: every image its own geometry
+    for im, got in zip(ims, batch):
+        chw, scale = odet.preprocess(im)
+        assert chw is not None
+        heads = det.run_network(chw)
+        parity.assert_detections_explained(got, heads, scale, 0.02, 0.4)
+        assert np.array_equal(ctx.detect(im, 0.02, 0.4, cap=4096).view(np.uint8), got.view(np.uint8))
+    # a frame whose letterboxed size truncates to zero is refused like preprocess() does (:109-113) -> empty result
+    flat = rng.integers(0, 256, (3, 2000, 3), dtype=np.uint8)
+    assert odet.preprocess(flat)[0] is None
+    with pytest.raises(capi.FrError) as e:
+        ctx.detect(flat)
+    assert e.value.code == capi.FR_ERR_INVALID_ARG
+    # nothing above the threshold: zero detections, not an error; strict '>' at score_thr = 1.0
+    assert len(ctx.detect(ims[4], 0.9999, 0.4)) == 0
+    assert len(ctx.detect(ims[4], 1.0, 0.4)) == 0
+    # nms_thr = 0: any overlap suppresses (strict '>' on an IoU of 0 keeps disjoint boxes); nms_thr >= 1: nothing is suppressed
+    for nms_thr in (0.0, 1.0):
+        got = ctx.detect(ims[4], 0.02, nms_thr, cap=8192)
+        chw, scale = odet.preprocess(ims[4])
+        parity.assert_detections_explained(got, det.run_network(chw), scale, 0.02, nms_thr)
+    # the fused pipeline with no detection and no padding faces marks every slot invalid and returns zeros
+    faces, n_det, emb, valid = ctx.pipeline([ims[4]], 4, None, score_thr=0.9999)
+    assert n_det[0] == 0 and not valid.any() and not emb.any()
