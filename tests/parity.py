@@ -57,6 +57,10 @@ def assert_detections_explained(got, heads, scale, score_thr=0.5, nms_thr=0.4, e
                                 eps_px=2e-3, lm_tol=1e-3):
     """got: fr_face records (numpy structured) of one image, in the order the C ABI returned them.
     heads: the ORACLE engine's nine head tensors for that image.  Returns a dict of counters."""
+    # the 1e-3 px bar is in NETWORK-INPUT (640-space) pixels: postprocess divides by the letterbox scale
+    # (src/face_detector.cpp:255-273), so on a frame larger than 640 the same head error is 1/scale times larger
+    mag = max(1.0, 1.0 / float(scale))
+    eps_px, lm_tol = eps_px * mag, lm_tol * mag
     cands = oracle_candidates(heads, scale, score_thr - eps_s, eps_px)
     by_anchor = {c.anchor: c for c in cands}
     exp = odet.postprocess(odet.scrfd_decode(heads), scale, score_thr, nms_thr)
