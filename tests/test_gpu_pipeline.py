@@ -176,13 +176,14 @@ def test_detect_edge_cases_vs_oracle(ctx, capi, det_wdict):
     det = odet.FaceDetector(det_wdict)
     shapes = [(1, 1), (2, 3), (7, 640), (640, 7), (1080, 1920), (1920, 1080), (641, 639), (333, 517)]
     ims = [rng.integers(0, 256, (h, w, 3), dtype=np.uint8) for h, w in shapes]
-    batch = ctx.detect_batch(ims, 0.02, 0.4, cap=4096)          # ragged batch: every image its own geometry
+    CAP = 16800                                                 # every anchor: the cap must never truncate here (8225 candidates on the 1080p frame)
+    batch = ctx.detect_batch(ims, 0.02, 0.4, cap=CAP)           # ragged batch: every image its own geometry
     for im, got in zip(ims, batch):
         chw, scale = odet.preprocess(im)
         assert chw is not None
         heads = det.run_network(chw)
         parity.assert_detections_explained(got, heads, scale, 0.02, 0.4)
-        assert np.array_equal(ctx.detect(im, 0.02, 0.4, cap=4096).view(np.uint8), got.view(np.uint8))
+        assert len(got) < CAP and np.array_equal(ctx.detect(im, 0.02, 0.4, cap=CAP).view(np.uint8), got.view(np.uint8))
     # a frame whose letterboxed size truncates to zero is refused like preprocess() does (:109-113) -> empty result
     flat = rng.integers(0, 256, (3, 2000, 3), dtype=np.uint8)
     assert odet.preprocess(flat)[0] is None
@@ -194,7 +195,7 @@ def test_detect_edge_cases_vs_oracle(ctx, capi, det_wdict):
     assert len(ctx.detect(ims[4], 1.0, 0.4)) == 0
     # nms_thr = 0: any overlap suppresses (strict '>' on an IoU of 0 keeps disjoint boxes); nms_thr >= 1: nothing is suppressed
     for nms_thr in (0.0, 1.0):
-        got = ctx.detect(ims[4], 0.02, nms_thr, cap=8192)
+        got = ctx.detect(ims[4], 0.02, nms_thr, cap=CAP)
         chw, scale = odet.preprocess(ims[4])
         parity.assert_detections_explained(got, det.run_network(chw), scale, 0.02, nms_thr)
     # the fused pipeline with no detection and no padding faces marks every slot invalid and returns zeros
