@@ -145,9 +145,6 @@ static int env_flag(const char* name, int dflt) {
 }
 
 // Configure halo mode for a 3x3 stride-1 conv whose A operand is `base` ([rows, cin], pitch cin).
-// alternating-tile epilogue (tc::Params::epi_alt) for output tiles up to this many columns (0 = off)
-static int epi_alt_max_bn() { static const int v = env_flag("FR_TC_EPIALT", 128); return v; }
-
 // the 256 / 512-channel 3x3 stride-1 layers run on CTA pairs (tc::halo_gemm2_kernel); FR_TC_2CTA=0 is the A/B switch
 static bool two_cta_eligible(int bn, int cin) {
   (void)cin;
@@ -250,7 +247,6 @@ int tc_launch(fr_ctx* ctx, ConvLaunch& L, int m_rows) {
     /* staging tiles only where they fit beside two A blocks and the weights */                    \
     const bool ts = L.tma_store && BN_ <= 128 && HC::smem_bytes(L.p.a_rows, 2, true) <= 227 * 1024; \
     L.p.tma_store = ts ? 1 : 0;                                                                    \
-    L.p.epi_alt = (HC::ACC_STAGES == 2 && BN_ <= epi_alt_max_bn()) ? 1 : 0;                        \
     L.p.a_stages = std::min(env_flag("FR_TC_ASTAGES", 2), HC::pick_a_stages(L.p.a_rows, ts));      \
     tc::halo_gemm_kernel<BN_, MT_, RB_><<<hgrid, tc::CONV_THREADS,                                  \
         HC::smem_bytes(L.p.a_rows, L.p.a_stages, ts), ctx->stream>>>(                               \

@@ -93,12 +93,6 @@ struct Params {
   // tile leaves through cp.async.bulk.tensor stores (whole 128-byte lines from the async proxy) instead of
   // lane-per-row 16-byte st.global, which cap at ~1.5 TB/s (the 64-channel layers were bound by exactly that)
   int tma_store;
-  // halo mode with double-buffered accumulators: the two epilogue warp groups (warps 2-5 / 6-9) take ALTERNATE
-  // tiles (group g always drains TMEM buffer g, all columns) instead of splitting every tile's columns.  ncu on the
-  // 64-channel layers: the tensor pipe was 49.5 % active because the MMA warp waited for TMEM: each epilogue warp
-  // spent ~2800 cycles per tile (row geometry, barrier waits, 32 columns of math), more than the tile's 1150-1700
-  // cycles of MMAs.  Alternating halves the per-tile fixed cost per column and gives each group two tile periods.
-  int epi_alt;
   __align__(16) float prelu_c[512];
 };
 
@@ -681,7 +675,7 @@ halo_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     if (p.tma_store) prefetch_tmap(&tmOut);
     for (int s = 0; s < C::MAX_A_STAGES; ++s) { mbar_init(&afull[s], 1); mbar_init(&aempty[s], 1); }
     for (int s = 0; s < C::B_STAGES; ++s) { mbar_init(&bfull[s], 1); mbar_init(&bempty[s], 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], p.epi_alt ? EPI_WARPS / 2 : EPI_WARPS); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], EPI_WARPS); }
     mbar_init(resfull, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     prefetch_tmap(&tmA);
@@ -853,54 +847,6 @@ halo_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     constexpr int CPS = BN / 32 / (EPI_WARPS / 4);   // 32-column chunks per warp
     const int c_begin = ((warp - 2) >> 2) * CPS;
     uint32_t it = 0, st_count = 0;
-    if (C::ACC_STAGES == 2 && p.epi_alt) {
-      // ---- alternating groups: group g = warps 2+4g .. 5+4g handles tiles it = g, g+2, ... (TMEM buffer g),
-      // every column of its tile; staging buffer g, named barriers 1+g / 3+g (128 threads), issuer = the group's
-      // first warp, lane 0
-      const int grp = (warp - 2) >> 2;
-      const bool issuer = warp == 2 + 4 * grp && lane == 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
-        if ((int)(it & 1u) != grp) continue;
-        int m0, n0, nlen;
-        item_coords(tile, m0, n0, nlen);
-        const int cps = nlen / 32;
-        const uint32_t acc = (uint32_t)grp, acc_phase = (it >> 1) & 1u;
-        EpiRow er = epi_row(p, m0 + row, n0, 0);
-        uint4 rv[4];
-        epi_load_res(er, 0, rv);
-        mbar_wait(&tfull[acc], acc_phase, p.err_flag);
-        tc_fence_after();
-        const bool staged = p.tma_store && nlen == BN;
-#pragma unroll 1
-        for (int mt = 0; mt < MT; ++mt) {
-          const uint32_t taddr0 = tmem_base + acc * (MT * BN) + mt * BN + ((uint32_t)(q * 32) << 16);
-          if (staged) {
-            if (issuer) tma_store_wait_read<0>();     // this group's previous store has drained the staging buffer
-            named_bar_sync(1 + grp, (EPI_WARPS / 2) * 32);
-          }
-          const uint32_t stage = staged ? smem_u32(sOut) + (uint32_t)grp * (uint32_t)C::STAGE_OUT_BYTES : 0u;
-          epilogue_tile<BN>(p, er, taddr0, n0, 0, 0, cps, rv, stage, row);
-          if (staged) {
-            fence_proxy_async_smem();
-            named_bar_sync(3 + grp, (EPI_WARPS / 2) * 32);
-            if (issuer) {
-#pragma unroll
-              for (int bx = 0; bx < BN / 64; ++bx)
-                tma_store_2d(&tmOut, sOut + grp * C::STAGE_OUT_BYTES + bx * (128 * 128), n0 + bx * 64, m0 + mt * BM);
-              tma_store_commit();
-            }
-          }
-          if (mt + 1 < MT) {
-            er = epi_row(p, m0 + (mt + 1) * BM + row, n0, 0);
-            epi_load_res(er, 0, rv);
-          }
-        }
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&tempty[acc]);
-      }
-      if (p.tma_store && issuer) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
-    } else {
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
       int m0, n0, nlen;
       item_coords(tile, m0, n0, nlen);
@@ -944,7 +890,6 @@ halo_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty[acc]);
-    }
     }
     // the bulk stores must have finished reading shared memory before the CTA exits
     if (p.tma_store && warp == 2 && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
