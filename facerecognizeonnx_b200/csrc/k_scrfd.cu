@@ -1319,6 +1319,396 @@ b0_dwpw_mma_kernel(const float* __restrict__ in, float* __restrict__ out, const 
   }
 }
 
+// ---------------------------------------------------------------------------------------
+// Front of the backbone in ONE kernel: stem (3x3 s2, 3 -> 16) -> b0 (dw 3x3 + 1x1 16 -> 16) -> s0.0
+// (dw 3x3 s2 + 1x1 16 -> 40).  As three launches these layers stream the 320 x 320 x 16 fp32 maps
+// through HBM four times (2.06 GB per 64 frames, 522 us); fused, a block walks down a strip of the
+// frame and keeps the stem / b0 rows it still needs in two shared-memory rings, so the only HBM
+// traffic is the bf16 input (157 MB) and the 160 x 160 x 40 output (262 MB).
+//   unit   = (frame, strip of OW = 40 s0.0 output columns, segment of G groups); group = 4 b0 rows;
+//   per group (base b0 row y): [stem rows y+1..y+4] sync [b0 rows y..y+3] sync [s0.0 rows y/2, y/2+1 ->
+//              global]; a unit's prologue is a group that computes stem rows y0-3..y0 and b0 rows
+//              y0-2, y0-1 only; positions outside the frame are stored as zeros (the next conv's padding);
+//   tiles  : an MMA tile is 2 rows x 8 columns (fragment row g = upper pixel, g + 8 = the pixel below),
+//              so a thread owns ONE column: the b0 stencil of a 4-row block reads 6 rows x 3 columns
+//              (18 float4 loads for 4 pixels instead of 36), and ring rows are warp-uniform, so a stencil
+//              address is uniform row base + per-thread column offset;
+//   arithmetic: exactly the stem / b0 kernels' (same fragments, same accumulation order), and for
+//              s0.0 the b0 scheme with 5 n tiles (three-term tf32 split, separate small / big sums).
+// Pixels are 64-byte records (16 channels).  Stem ring: bit 1 of the 16-byte chunk index is XORed with
+// bit 1 of the column, which keeps a quarter warp's float4 loads (two adjacent records) conflict-free and
+// spreads a half warp's C-fragment stores (4 columns x 4 x 8 bytes) over all banks.  b0 ring: even and odd columns in
+// two planes (offset = 32 mod 128 bytes), so the stride-2 stencil of s0.0 also reads adjacent records.
+namespace ff {
+constexpr int HS = DET / 2, HO = DET / 4;
+constexpr int OW = 40;                 // s0.0 output columns per strip
+constexpr int NB = 2 * OW + 1;         // b0 columns a strip needs   (2*X0 - 1 .. 2*X0 + 79)
+constexpr int NS = 2 * OW + 3;         // stem columns               (2*X0 - 2 .. 2*X0 + 80)
+constexpr int CBS = (NS + 7) / 8;      // 8-column blocks of a stem row (11)
+constexpr int CBB = (NB + 7) / 8;      // of a b0 row (11)
+constexpr int IW = 176;                // input columns staged per strip row: 4*X0 - 8 .. 4*X0 + 167
+constexpr int IP = 208;                // strip row pitch (bf16): 104 words = 8 mod 32, so the rows of a filter window
+constexpr int IROWS = 9;               // (input rows 2y+1 .. 2y+9 of a group) start 8 banks apart ...
+constexpr int IPLANE = IROWS * IP + 32;   // ... and so do the planes (9 * 8 + 16 = 24 mod 32 = row index 3 * 8)
+constexpr int STRIP_ELEMS = 3 * IPLANE;
+constexpr int SROWS = 6, BROWS = 5;
+constexpr int S_ROWB = (NS + 1) * 64;
+constexpr int B_PLANE = (OW + 1) * 64 + 32;          // even columns first, then the odd ones
+constexpr int B_ROWB = B_PLANE + OW * 64;
+constexpr int WARPS = 6, FTHREADS = WARPS * 32;
+constexpr int OFF_SRING = 2 * STRIP_ELEMS * 2;
+constexpr int OFF_BRING = OFF_SRING + SROWS * S_ROWB;
+constexpr int OFF_STEM_BF = OFF_BRING + BROWS * B_ROWB;          // uint2 [2][2][3][32]
+constexpr int OFF_B0_BF = OFF_STEM_BF + 2 * 2 * 3 * 32 * 8;      // float2 [2][2][2][32]
+constexpr int OFF_S0_BF = OFF_B0_BF + 2 * 2 * 2 * 32 * 8;        // float2 [2][5][2][32]
+constexpr int OFF_PB0 = OFF_S0_BF + 2 * 5 * 2 * 32 * 8;          // float [16]
+constexpr int OFF_PB1 = OFF_PB0 + 16 * 4;                        // float [40]
+constexpr int SMEM_BYTES = OFF_PB1 + 40 * 4;
+static_assert(SMEM_BYTES * 2 + 2048 <= 227 * 1024, "two blocks per SM");
+static_assert(WARPS >= OW / 8, "one s0.0 tile per warp");
+static_assert(OFF_SRING % 16 == 0 && OFF_BRING % 16 == 0 && B_ROWB % 16 == 0 && OFF_STEM_BF % 16 == 0, "alignment");
+
+struct Params {
+  const __nv_bfloat16* in;   // [n][3][640][640]
+  float* out;                // s0.0 output, fp32 NHWC [n][160][160][40]
+  const uint2* stem_bf;
+  const float2* b0_bf;
+  const float2* s0_bf;
+  const float *pb0, *pb1;    // 1x1 biases: b0 [16], s0.0 [40]
+  float dw0[10 * 16];        // b0 depthwise taps [9][16] + bias [16]: read through the constant bank (4 distinct
+  float dw1[10 * 16];        // addresses per warp), which keeps 20 float4 loads per phase off the shared-memory pipe
+  float* tap_stem;           // TAPS: [n][320][320][16] copies of the intermediates (test hook)
+  float* tap_b0;
+  int groups;                // G: groups per unit (divides 80)
+};
+
+__device__ __forceinline__ void sts2(uint32_t a, float x, float y) {
+  asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(a), "f"(x), "f"(y) : "memory");
+}
+// byte offset of 16-byte chunk `chunk` of stem-ring column js inside a ring row
+__device__ __forceinline__ uint32_t s_off(int js, int chunk) {
+  return (uint32_t)(js * 64 + ((chunk ^ (js & 2)) << 4));
+}
+__device__ __forceinline__ float4 relu4(const float4& a) {
+  return make_float4(fmaxf(a.x, 0.f), fmaxf(a.y, 0.f), fmaxf(a.z, 0.f), fmaxf(a.w, 0.f));
+}
+// the 1x1 of 16 pixels (fragment rows g: xa, g + 8: xb; this thread's channels 4t .. 4t+3) against NT n tiles:
+// three-term tf32 split, cross terms in accS, hi*hi in accB (k slot t <-> channel 4t + 2ks, t + 4 <-> 4t + 2ks + 1)
+template <int NT, typename LoadB>
+__device__ __forceinline__ void pw_mma(const float4& xa, const float4& xb, float (&accS)[NT][4], float (&accB)[NT][4],
+                                       LoadB load_b) {
+  const float xs[2][4] = {{xa.x, xa.y, xa.z, xa.w}, {xb.x, xb.y, xb.z, xb.w}};
+#pragma unroll
+  for (int j = 0; j < NT; ++j)
+#pragma unroll
+    for (int q = 0; q < 4; ++q) { accS[j][q] = 0.f; accB[j][q] = 0.f; }
+#pragma unroll
+  for (int ks = 0; ks < 2; ++ks) {
+    uint32_t ahi[4], alo[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const float v = xs[q & 1][2 * ks + (q >> 1)];
+      const float hh = tf32_rna(v);
+      ahi[q] = __float_as_uint(hh);
+      alo[q] = __float_as_uint(tf32_rna(v - hh));
+    }
+#pragma unroll
+    for (int j = 0; j < NT; ++j) {
+      const float2 bhi = load_b(ks, j, 0), blo = load_b(ks, j, 1);
+      mma_tf32_1688(accS[j], alo, bhi);
+      mma_tf32_1688(accS[j], ahi, blo);
+      mma_tf32_1688(accB[j], ahi, bhi);
+    }
+  }
+}
+}  // namespace ff
+
+template <bool TAPS>
+__global__ void __launch_bounds__(ff::FTHREADS, 2)
+front_fused_kernel(const ff::Params P) {
+  using namespace ff;
+  extern __shared__ __align__(128) uint8_t sm_raw[];
+  uint16_t* strips = reinterpret_cast<uint16_t*>(sm_raw);
+  const uint32_t sm0 = smem_u32(sm_raw);
+  const uint32_t sring = sm0 + OFF_SRING, bring = sm0 + OFF_BRING;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int g = lane >> 2, t = lane & 3;
+  const int segs = (HS / 4) / P.groups;
+  int b = blockIdx.x;
+  const int seg = b % segs;
+  b /= segs;
+  const int strip_i = b & 3, n = b >> 2;
+  const int X0 = strip_i * OW;
+  const int y0 = seg * 4 * P.groups;
+  const __nv_bfloat16* ip = P.in + (size_t)n * 3 * DET * DET;
+
+  // input strip of the group with base row y: strip[c][ir][li] = input (c, 2y + 1 + ir, 4*X0 - 8 + li)
+  auto fill = [&](int buf, int y) {
+    uint16_t* sp = strips + buf * STRIP_ELEMS;
+    for (int i = tid; i < 3 * IROWS * (IW / 8); i += FTHREADS) {
+      const int cr = i / (IW / 8), q = i - cr * (IW / 8);
+      const int c = cr / IROWS, ir = cr - c * IROWS;
+      const int iy = 2 * y + 1 + ir, ic = 4 * X0 - 8 + 8 * q;
+      uint16_t* dst = sp + c * IPLANE + ir * IP + 8 * q;
+      if (iy >= 0 && iy < DET && ic >= 0 && ic < DET) {
+        const void* src = ip + ((size_t)c * DET + iy) * DET + ic;
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+      } else {
+        *reinterpret_cast<uint4*>(dst) = make_uint4(0, 0, 0, 0);
+      }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  fill(0, y0 - 4);
+  // constants -> shared memory
+  {
+    uint32_t* d = reinterpret_cast<uint32_t*>(sm_raw + OFF_STEM_BF);
+    const uint32_t* s = reinterpret_cast<const uint32_t*>(P.stem_bf);
+    for (int i = tid; i < 2 * 2 * 3 * 32 * 2; i += FTHREADS) d[i] = __ldg(s + i);
+    d = reinterpret_cast<uint32_t*>(sm_raw + OFF_B0_BF);
+    s = reinterpret_cast<const uint32_t*>(P.b0_bf);
+    for (int i = tid; i < 2 * 2 * 2 * 32 * 2; i += FTHREADS) d[i] = __ldg(s + i);
+    d = reinterpret_cast<uint32_t*>(sm_raw + OFF_S0_BF);
+    s = reinterpret_cast<const uint32_t*>(P.s0_bf);
+    for (int i = tid; i < 2 * 5 * 2 * 32 * 2; i += FTHREADS) d[i] = __ldg(s + i);
+    float* f = reinterpret_cast<float*>(sm_raw + OFF_PB0);
+    if (tid < 16) f[tid] = __ldg(P.pb0 + tid);
+    f = reinterpret_cast<float*>(sm_raw + OFF_PB1);
+    if (tid < 40) f[tid] = __ldg(P.pb1 + tid);
+  }
+  // stem: strip offsets of this thread's 8 k indices (k = (c*3 + r)*3 + s; k = 27 is the bias row)
+  int koff[8];
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    const int k = (q >> 2) * 16 + ((q >> 1) & 1) * 8 + 2 * t + (q & 1);
+    const int c = k / 9, r = (k - c * 9) / 3, sx = k - c * 9 - r * 3;
+    koff[q] = k < 27 ? c * IPLANE + r * IP + 3 + sx : 0;
+  }
+
+  // Ring positions: stem position k (0..5) = stem row y - 1 + k, b0 position m (0..4) = b0 row y - 1 + m.
+  // Physical ring rows advance by 4 per group: sb / bb = ring row of position 0.
+  int sb = 0, bb = 0;
+
+  // ---- stem rows at positions 2 .. 5: tile = (row pair rp, column block cb); fragment row g = position
+  //      2 + 2rp, column 8cb + g; row g + 8 = the position below
+  auto stem_phase = [&](const uint16_t* strip, int y) {
+    uint2 bf[2][2][3];
+    {
+      const uint2* s = reinterpret_cast<const uint2*>(sm_raw + OFF_STEM_BF);
+#pragma unroll
+      for (int ks = 0; ks < 2; ++ks)
+#pragma unroll
+        for (int j = 0; j < 2; ++j)
+#pragma unroll
+          for (int h = 0; h < 3; ++h) bf[ks][j][h] = s[((ks * 2 + j) * 3 + h) * 32 + lane];
+    }
+#pragma unroll 1
+    for (int cb = warp; cb < CBS; cb += WARPS) {       // both row pairs of the column block: 4 independent MMA chains
+      const int js = min(8 * cb + g, NS - 1);
+      const bool colv = 8 * cb + g < NS;
+      const uint16_t* sbase = strip + 2 * js;
+      float acc[2][2][4];
+#pragma unroll
+      for (int rp = 0; rp < 2; ++rp)
+#pragma unroll
+        for (int j = 0; j < 2; ++j) { acc[rp][j][0] = 0.f; acc[rp][j][1] = 0.f; acc[rp][j][2] = 0.f; acc[rp][j][3] = 0.f; }
+#pragma unroll
+      for (int ks = 0; ks < 2; ++ks) {
+        uint32_t a[2][4];
+#pragma unroll
+        for (int rp = 0; rp < 2; ++rp)
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {                   // a0:(g,k lo) a1:(g+8,k lo) a2:(g,k hi) a3:(g+8,k hi)
+            // input row of tap rr for position k = 2 + 2rp + (q & 1): 2*(k - 2) + rr inside the strip
+            const uint16_t* sp = sbase + (4 * rp + 2 * (q & 1)) * IP;
+            const int ko = ks * 4 + (q >> 1) * 2;
+            a[rp][q] = (uint32_t)sp[koff[ko]] | ((uint32_t)sp[koff[ko + 1]] << 16);
+          }
+        if (ks == 1 && t == 1) {                          // k = 27 carries the bias: A = 1.0
+#pragma unroll
+          for (int rp = 0; rp < 2; ++rp) {
+            a[rp][2] = (a[rp][2] & 0xffffu) | 0x3f800000u;
+            a[rp][3] = (a[rp][3] & 0xffffu) | 0x3f800000u;
+          }
+        }
+#pragma unroll
+        for (int h = 2; h >= 0; --h)                      // small pieces first
+#pragma unroll
+          for (int j = 0; j < 2; ++j)
+#pragma unroll
+            for (int rp = 0; rp < 2; ++rp) mma_bf16_16816(acc[rp][j], a[rp], bf[ks][j][h]);
+      }
+      if (colv) {
+        const int scol = 2 * X0 - 2 + js;
+        const bool col_in = scol >= 0 && scol < HS;
+#pragma unroll
+        for (int rp = 0; rp < 2; ++rp)
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const int k = 2 + 2 * rp + h;
+            const int srow = y - 1 + k;
+            const bool inside = col_in && srow >= 0 && srow < HS;
+            int slot = sb + k;
+            if (slot >= SROWS) slot -= SROWS;
+            const uint32_t rowb = sring + (uint32_t)(slot * S_ROWB) + 8 * (t & 1);
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+              const float v0 = inside ? fmaxf(acc[rp][j][2 * h], 0.f) : 0.f;
+              const float v1 = inside ? fmaxf(acc[rp][j][2 * h + 1], 0.f) : 0.f;
+              sts2(rowb + s_off(js, 2 * j + (t >> 1)), v0, v1);
+              if (TAPS && inside)
+                *reinterpret_cast<float2*>(P.tap_stem + (((size_t)n * HS + srow) * HS + scol) * 16 + 8 * j + 2 * t) =
+                    make_float2(v0, v1);
+            }
+          }
+      }
+    }
+  };
+
+  // ---- b0 rows at positions 1 .. 4 (first = 1: positions 3, 4 only): block = 8 columns x 4 rows, a thread
+  //      owns column 8cb + g and channels 4t .. 4t+3 of all four rows
+  auto b0_phase = [&](int y, int first) {
+    float4 wd[9];
+#pragma unroll
+    for (int q = 0; q < 9; ++q) wd[q] = *reinterpret_cast<const float4*>(&P.dw0[q * 16 + 4 * t]);
+    const float4 bd = *reinterpret_cast<const float4*>(&P.dw0[144 + 4 * t]);
+    float2 bw[2][2][2];
+    {
+      const float2* s = reinterpret_cast<const float2*>(sm_raw + OFF_B0_BF);
+#pragma unroll
+      for (int ks = 0; ks < 2; ++ks)
+#pragma unroll
+        for (int j = 0; j < 2; ++j)
+#pragma unroll
+          for (int h = 0; h < 2; ++h) bw[ks][j][h] = s[((ks * 2 + j) * 2 + h) * 32 + lane];
+    }
+    float2 pb[2];
+#pragma unroll
+    for (int j = 0; j < 2; ++j) pb[j] = *reinterpret_cast<const float2*>(sm_raw + OFF_PB0 + (8 * j + 2 * t) * 4);
+    uint32_t srow_b[6];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+      int slot = sb + k;
+      if (slot >= SROWS) slot -= SROWS;
+      srow_b[k] = sring + (uint32_t)(slot * S_ROWB);
+    }
+#pragma unroll 1
+    for (int cb = warp; cb < CBB; cb += WARPS) {
+      const int jb = min(8 * cb + g, NB - 1);
+      const bool colv = 8 * cb + g < NB;
+      uint32_t coff[3];
+#pragma unroll
+      for (int dx = 0; dx < 3; ++dx) coff[dx] = s_off(jb + dx, t);
+      float4 o[4] = {bd, bd, bd, bd};                      // positions 1 .. 4
+#pragma unroll
+      for (int k = 0; k < 6; ++k) {
+        if (first && k < 2) continue;
+        float4 v[3];
+#pragma unroll
+        for (int dx = 0; dx < 3; ++dx) v[dx] = lds4(srow_b[k] + coff[dx]);
+#pragma unroll
+        for (int m = 1; m <= 4; ++m) {
+          const int r = k - (m - 1);
+          if (r < 0 || r > 2) continue;
+#pragma unroll
+          for (int dx = 0; dx < 3; ++dx) fma4(o[m - 1], v[dx], wd[r * 3 + dx]);
+        }
+      }
+      const int bcol = 2 * X0 - 1 + jb;
+      const bool col_in = colv && bcol >= 0 && bcol < HS;
+      const uint32_t cdst = (uint32_t)((jb & 1) * B_PLANE + (jb >> 1) * 64 + 8 * t);
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        if (first && half == 0) continue;
+        float accS[2][4], accB[2][4];
+        pw_mma<2>(relu4(o[2 * half]), relu4(o[2 * half + 1]), accS, accB,
+                  [&](int ks, int j, int h) { return bw[ks][j][h]; });
+        if (colv) {
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const int m = 1 + 2 * half + h;
+            const int brow = y - 1 + m;
+            const bool inside = col_in && brow >= 0 && brow < HS;
+            int slot = bb + m;
+            if (slot >= BROWS) slot -= BROWS;
+            const uint32_t dst = bring + (uint32_t)(slot * B_ROWB) + cdst;
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+              const float v0 = inside ? fmaxf(accB[j][2 * h] + accS[j][2 * h] + pb[j].x, 0.f) : 0.f;
+              const float v1 = inside ? fmaxf(accB[j][2 * h + 1] + accS[j][2 * h + 1] + pb[j].y, 0.f) : 0.f;
+              sts2(dst + 32 * j, v0, v1);
+              if (TAPS && inside)
+                *reinterpret_cast<float2*>(P.tap_b0 + (((size_t)n * HS + brow) * HS + bcol) * 16 + 8 * j + 2 * t) =
+                    make_float2(v0, v1);
+            }
+          }
+        }
+      }
+    }
+  };
+
+  // ---- s0.0 output rows y/2 (fragment row g), y/2 + 1 (row g + 8), columns X0 + 8cb + g, from b0 positions 0 .. 4
+  auto s0_tile = [&](int y, int bbp, int cb) {
+    float4 wd[9];
+#pragma unroll
+    for (int q = 0; q < 9; ++q) wd[q] = *reinterpret_cast<const float4*>(&P.dw1[q * 16 + 4 * t]);
+    const float4 bd = *reinterpret_cast<const float4*>(&P.dw1[144 + 4 * t]);
+    const float2* sbf = reinterpret_cast<const float2*>(sm_raw + OFF_S0_BF);
+    const float* spb = reinterpret_cast<const float*>(sm_raw + OFF_PB1);
+    const int pc = 8 * cb + g;
+    // column 2*pc + s: s = 0 even plane [pc], 1 odd plane [pc], 2 even plane [pc + 1]
+    const uint32_t coff = (uint32_t)(pc * 64 + 16 * t);
+    float4 o[2] = {bd, bd};
+#pragma unroll
+    for (int m = 0; m < 5; ++m) {
+      int slot = bbp + m;
+      if (slot >= BROWS) slot -= BROWS;
+      const uint32_t rowb = bring + (uint32_t)(slot * B_ROWB) + coff;
+      const float4 v0 = lds4(rowb), v1 = lds4(rowb + B_PLANE), v2 = lds4(rowb + 64);
+#pragma unroll
+      for (int yl = 0; yl < 2; ++yl) {
+        const int r = m - 2 * yl;
+        if (r < 0 || r > 2) continue;
+        fma4(o[yl], v0, wd[r * 3 + 0]);
+        fma4(o[yl], v1, wd[r * 3 + 1]);
+        fma4(o[yl], v2, wd[r * 3 + 2]);
+      }
+    }
+    float accS[5][4], accB[5][4];
+    pw_mma<5>(relu4(o[0]), relu4(o[1]), accS, accB,
+              [&](int ks, int j, int h) { return sbf[((ks * 5 + j) * 2 + h) * 32 + lane]; });
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      float* op = P.out + (((size_t)n * HO + (y >> 1) + h) * HO + X0 + pc) * 40 + 2 * t;
+#pragma unroll
+      for (int j = 0; j < 5; ++j) {
+        const float2 pbv = *reinterpret_cast<const float2*>(spb + 8 * j + 2 * t);
+        *reinterpret_cast<float2*>(op + 8 * j) =
+            make_float2(fmaxf(accB[j][2 * h] + accS[j][2 * h] + pbv.x, 0.f),
+                        fmaxf(accB[j][2 * h + 1] + accS[j][2 * h + 1] + pbv.y, 0.f));
+      }
+    }
+  };
+
+#pragma unroll 1
+  for (int gi = -1; gi < P.groups; ++gi) {        // gi = -1: the unit's prologue
+    const int y = y0 + 4 * gi;
+    const int buf = (gi + 1) & 1;
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();                      // strip(gi) landed; every reader of the previous group is done
+    if (gi + 1 < P.groups) fill(buf ^ 1, y + 4);
+    stem_phase(strips + buf * STRIP_ELEMS, y);
+    __syncthreads();
+    b0_phase(y, gi < 0 ? 1 : 0);
+    __syncthreads();
+    if (gi >= 0 && warp < OW / 8) s0_tile(y, bb, warp);
+    sb += 4;
+    if (sb >= SROWS) sb -= SROWS;
+    bb += 4;
+    if (bb >= BROWS) bb -= BROWS;
+  }
+}
+
 }  // namespace
 
 struct PackedConv {        // device-side packed parameters of one (fused) layer
@@ -1341,6 +1731,10 @@ struct DetModel {
   float* stem_w = nullptr;
   float* stem_b = nullptr;
   float2* b0_bfrag = nullptr;    // b0's 1x1 weights as m16n8k8 tf32 B fragments [kstep][ntile][hi/lo][lane]
+  float2* s00_bfrag = nullptr;   // s0.0's 1x1 weights (16 -> 40), same fragment layout with 5 n tiles
+  float front_dw[2][160];        // host copies of the b0 / s0.0 depthwise taps [9][16] + bias [16] (kernel parameters)
+  const __nv_bfloat16* last_in = nullptr;   // input of the last forward that ran the fused front (det_tap re-runs it)
+  int last_n = 0;
   uint2* stem_bfrag = nullptr;   // stem weights + bias row as m16n8k16 B fragments [kstep][ntile][piece][lane]
   std::vector<void*> allocs;
   int cap = 0;
@@ -1695,6 +2089,11 @@ int det_model_create(fr_ctx* ctx, const fr_weights* w) {
     pc.dw_w = upload(m.get(), dwt);
     pc.dw_b = upload(m.get(), w->at(name + ".dw.b").data);
     ok = ok && pc.dw_w && pc.dw_b;
+    if ((name == "b0" || name == "s0.0") && cin == 16) {   // kernel-parameter copies for front_fused_kernel
+      float* dst = m->front_dw[name == "b0" ? 0 : 1];
+      memcpy(dst, dwt.data(), 144 * sizeof(float));
+      memcpy(dst + 144, w->at(name + ".dw.b").data.data(), 16 * sizeof(float));
+    }
   };
   {
     const fr_tensor& tw = w->at("stem.w");   // [16][3][3][3] -> [27][16]
@@ -1763,6 +2162,31 @@ int det_model_create(fr_ctx* ctx, const fr_weights* w) {
   }
   for (int s = 0; s < 4; ++s)
     for (int b = 0; b < kStages[s][0]; ++b) dwsep("s" + std::to_string(s) + "." + std::to_string(b), b == 0 ? 2 : 1);
+  {
+    // s0.0's 1x1 for front_fused_kernel: B fragment of lane 4g + t = W[n = 8j + g][channel 4t + 2ks (+1)], hi / lo tf32
+    const fr_tensor& pw = w->at("s0.0.pw.w");
+    ok = ok && pw.dims[0] == 40 && pw.dims[1] == 16;
+    std::vector<float2> frag(2 * 5 * 2 * 32);
+    for (int ks = 0; ok && ks < 2; ++ks)
+      for (int j = 0; j < 5; ++j)
+        for (int h = 0; h < 2; ++h)
+          for (int lane = 0; lane < 32; ++lane) {
+            const int g = lane >> 2, t = lane & 3, nn = 8 * j + g;
+            float v[2];
+            for (int i = 0; i < 2; ++i) {
+              const float wv = pw.data[(size_t)nn * 16 + 4 * t + 2 * ks + i];
+              const float hi = tf32_rna_host(wv);
+              v[i] = h == 0 ? hi : tf32_rna_host(wv - hi);
+            }
+            frag[((ks * 5 + j) * 2 + h) * 32 + lane] = make_float2(v[0], v[1]);
+          }
+    if (ok && cudaMalloc(&m->s00_bfrag, frag.size() * sizeof(float2)) == cudaSuccess) {
+      cudaMemcpy(m->s00_bfrag, frag.data(), frag.size() * sizeof(float2), cudaMemcpyHostToDevice);
+      m->allocs.push_back(m->s00_bfrag);
+    } else {
+      ok = false;
+    }
+  }
   for (int i = 0; i < 3; ++i) dense("lat" + std::to_string(i), 1);
   for (int i = 0; i < 3; ++i) dense("fpn" + std::to_string(i), 1);
   for (int i = 0; i < 2; ++i) dense("down" + std::to_string(i), 2);
@@ -1822,8 +2246,65 @@ static int env_int(const char* name, int dflt) {
 // each chunk uses frames [0, chunk) of the activation buffers and the last chunked layer writes its
 // output at the chunk's offset of the full-batch tensor.  Per-frame results do not depend on the
 // batch around a frame, so this is bit-identical to the unchunked run.
+// stem -> b0 -> s0.0 in one launch (front_fused_kernel); taps: also write the stem / b0 activations
+static int launch_front_fused(fr_ctx* ctx, const __nv_bfloat16* d_in_chw, int n, bool taps) {
+  DetModel* m = ctx->det;
+  const PackedConv& b0 = m->conv.at("b0");
+  const PackedConv& s00 = m->conv.at("s0.0");
+  ff::Params P;
+  P.in = d_in_chw;
+  P.out = m->a_stage[0];
+  P.stem_bf = m->stem_bfrag;
+  P.b0_bf = m->b0_bfrag;
+  P.s0_bf = m->s00_bfrag;
+  P.pb0 = b0.bias;
+  P.pb1 = s00.bias;
+  memcpy(P.dw0, m->front_dw[0], sizeof(P.dw0));
+  memcpy(P.dw1, m->front_dw[1], sizeof(P.dw1));
+  P.tap_stem = taps ? m->a_stem : nullptr;
+  P.tap_b0 = taps ? m->a_b0 : nullptr;
+  // groups per unit: long units amortise the prologue (3 stem rows + 1 b0 row per unit); small batches
+  // get short units so that one frame still spreads over the whole GPU
+  P.groups = n >= 8 ? 10 : 2;
+  const int units = n * 4 * ((ff::HS / 4) / P.groups);
+  if (taps) {
+    FR_CUDA_OK(ctx, fr_opt_in_smem(ctx, front_fused_kernel<true>, ff::SMEM_BYTES));
+    front_fused_kernel<true><<<(unsigned)units, ff::FTHREADS, ff::SMEM_BYTES, ctx->stream>>>(P);
+  } else {
+    FR_CUDA_OK(ctx, fr_opt_in_smem(ctx, front_fused_kernel<false>, ff::SMEM_BYTES));
+    front_fused_kernel<false><<<(unsigned)units, ff::FTHREADS, ff::SMEM_BYTES, ctx->stream>>>(P);
+  }
+  ctx->launches++;
+  FR_CUDA_OK(ctx, cudaGetLastError());
+  return FR_OK;
+}
+
+static bool front_fused_enabled() {
+  const char* v = getenv("FR_SCRFD_FRONT_FUSED");   // A/B switch: 0 = the three separate kernels
+  return !(v && atoi(v) == 0);
+}
+
 static int det_front(fr_ctx* ctx, const __nv_bfloat16* d_in_chw, int n, int n_layers, size_t out_frame_off) {
   DetModel* m = ctx->det;
+  m->last_in = nullptr;
+  if (n_layers >= 15 && out_frame_off == 0 && front_fused_enabled()) {
+    FR_CHECK(launch_front_fused(ctx, d_in_chw, n, false));
+    m->last_in = d_in_chw;
+    m->last_n = n;
+    const float* cur = m->a_stage[0];
+    int hw = 160, bi = 1;
+    for (int s = 0; s < 4; ++s)
+      for (int b = (s == 0 ? 1 : 0); b < kStages[s][0]; ++b, ++bi) {
+        const int stride = b == 0 ? 2 : 1;
+        const int ho = hw / stride;
+        LayerIO io;
+        io.in = cur; io.out = m->a_stage[bi]; io.hin = hw; io.stride = stride; io.relu = 1;
+        FR_CHECK(launch_layer(ctx, m->conv.at("s" + std::to_string(s) + "." + std::to_string(b)), io, n));
+        hw = ho;
+        cur = m->a_stage[bi];
+      }
+    return FR_OK;
+  }
   // last front layer writes at frame offset `out_frame_off` of its (full-batch) output tensor
   auto dst = [&](int layer, float* base, size_t per_frame) {
     return layer == n_layers - 1 ? base + out_frame_off * per_frame : base;
@@ -1963,6 +2444,8 @@ int det_tap(fr_ctx* ctx, int tap, int n, float* h_out, size_t out_elems) {
   DetModel* m = ctx->det;
   if (!m || m->cap < n) return fr_fail(ctx, FR_ERR_NOT_LOADED, "no detector activations");
   const float* src = nullptr;
+  // the fused front keeps the stem / b0 activations in shared memory: re-run it with the tap copies on
+  if (tap <= 1 && m->last_in && m->last_n >= n) FR_CHECK(launch_front_fused(ctx, m->last_in, m->last_n, true));
   if (tap == 0) src = m->a_stem;
   else if (tap == 1) src = m->a_b0;
   else if (tap >= 2 && tap < 15) src = m->a_stage[tap - 2];

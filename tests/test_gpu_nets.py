@@ -193,6 +193,32 @@ def test_k2_scrfd_heads_vs_oracle(ctx, det_wdict):
     assert max(px) < 1e-3, px                  # bbox / kps error in pixels after decode
 
 
+@pytest.mark.parametrize("n", [2, 9])
+def test_k2_scrfd_fused_front_matches_separate_kernels(ctx, n, monkeypatch):
+    """front_fused_kernel (stem -> b0 -> s0.0 through shared-memory rings) against the three separate
+    kernels: the stem and b0 use the same fragments and accumulation order, so their activations must be
+    bit-identical; s0.0 moves from the tcgen05 pipeline to warp-level MMA (same three-term split), so it
+    and the heads agree to fp32-grade error.  n = 2: short units (2 groups); n = 9: long units (10 groups),
+    i.e. both unit lengths, every strip, frame borders on all four sides."""
+    rng = np.random.default_rng(33 + n)
+    x = ((rng.integers(0, 256, (n, 3, 640, 640)).astype(np.float32)) - 127.5) / 128
+    x[0, :, :5] = 1.0      # something non-random on the top / left borders
+    x[0, :, :, -3:] = -1.0
+    monkeypatch.setenv("FR_SCRFD_FRONT_FUSED", "0")
+    ref_heads = ctx.scrfd_forward(x)
+    ref_taps = [ctx.scrfd_tap(i, n, s) for i, s in ((0, (16, 320, 320)), (1, (16, 320, 320)), (2, (40, 160, 160)))]
+    monkeypatch.setenv("FR_SCRFD_FRONT_FUSED", "1")
+    got_heads = ctx.scrfd_forward(x)
+    got_taps = [ctx.scrfd_tap(i, n, s) for i, s in ((0, (16, 320, 320)), (1, (16, 320, 320)), (2, (40, 160, 160)))]
+    assert np.array_equal(got_taps[0], ref_taps[0])
+    assert np.array_equal(got_taps[1], ref_taps[1])
+    err = float(np.abs(got_taps[2] - ref_taps[2]).max() / np.abs(ref_taps[2]).max())
+    assert err < 4e-6, err
+    for k, (g, r) in enumerate(zip(got_heads, ref_heads)):
+        e = float(np.abs(g - r).max())
+        assert e < (1e-5 if k < 3 else 2e-5), (k, e)
+
+
 def test_k2_scrfd_batch_invariance(ctx):
     rng = np.random.default_rng(32)
     x = ((rng.integers(0, 256, (5, 3, 640, 640)).astype(np.float32)) - 127.5) / 128
