@@ -10,6 +10,7 @@
 
 bool DevBuf::reserve(size_t bytes, bool zero) {
   if (bytes <= cap && p) return true;
+  fr_alloc_epoch()++;
   if (p) cudaFree(p);
   p = nullptr;
   cap = 0;
@@ -23,6 +24,7 @@ bool DevBuf::reserve(size_t bytes, bool zero) {
   return true;
 }
 void DevBuf::release() {
+  if (p) fr_alloc_epoch()++;
   if (p) cudaFree(p);
   p = nullptr;
   cap = 0;
@@ -60,6 +62,12 @@ enum {  // indices into ctx->misc
   B_DET_IN = 0, B_DET_OUT, B_DET_N, B_SEL, B_FACE_IMG, B_VALID, B_ALIGN, B_CROPS, B_EMB_RAW,
   B_EMB, B_TMP0, B_TMP1
 };
+
+inline int __float_as_int_host(float f) {
+  int i;
+  memcpy(&i, &f, 4);
+  return i;
+}
 
 struct Guard {
   fr_ctx* c;
@@ -201,6 +209,90 @@ int run_detect(fr_ctx* ctx, const ImgDesc* d_desc, int n_img, float score_thr, f
   return s;
 }
 
+// Run `enqueue` (a chain of kernel launches / memsets on ctx->stream whose arguments are fully determined by
+// `key`), replayed as a CUDA graph from the third call with the same key on: the first call runs eagerly
+// (buffers grow, shared-memory opt-ins happen), the second is captured, later ones are one cudaGraphLaunch.
+// At batch 1 the ~90 launches of a detect + embed cost more host time than GPU time; nothing else changes.
+// A graph is dropped when any device buffer was reallocated since (fr_alloc_epoch).  FR_GRAPHS=0 disables.
+template <typename F>
+int run_graphed(fr_ctx* ctx, const std::vector<long long>& key, F&& enqueue) {
+  static const bool enabled = !(getenv("FR_GRAPHS") && atoi(getenv("FR_GRAPHS")) == 0);
+  if (!enabled || ctx->timing) return enqueue();
+  cudaStreamCaptureStatus cap_status = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(ctx->stream, &cap_status) != cudaSuccess || cap_status != cudaStreamCaptureStatusNone) {
+    cudaGetLastError();
+    return enqueue();                          // the caller is capturing this stream itself
+  }
+  fr_ctx::GraphSlot* slot = nullptr;
+  for (auto& g : ctx->graphs)
+    if (g.key == key) slot = &g;
+  if (!slot) {
+    if (ctx->graphs.size() >= 16) {            // forget the oldest key
+      if (ctx->graphs.front().exec) cudaGraphExecDestroy(ctx->graphs.front().exec);
+      ctx->graphs.erase(ctx->graphs.begin());
+    }
+    ctx->graphs.emplace_back();
+    slot = &ctx->graphs.back();
+    slot->key = key;
+  }
+  const uint64_t epoch = fr_alloc_epoch().load();
+  if (slot->state == 2 && slot->epoch == epoch) {
+    FR_CUDA_OK(ctx, cudaGraphLaunch(slot->exec, ctx->stream));
+    ctx->launches += slot->launches;
+    return FR_OK;
+  }
+  if (slot->state == 2) {                      // buffers moved under the graph
+    cudaGraphExecDestroy(slot->exec);
+    slot->exec = nullptr;
+    slot->state = 0;
+  }
+  if (slot->state <= 0 || slot->epoch != epoch) {
+    const int failed = slot->state < 0;
+    const int s = enqueue();
+    slot->epoch = fr_alloc_epoch().load();
+    if (!failed) slot->state = 1;
+    return s;
+  }
+  const uint64_t l0 = ctx->launches;
+  if (cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
+    cudaGetLastError();
+    slot->state = -1;
+    return enqueue();
+  }
+  const int s = enqueue();
+  cudaGraph_t graph = nullptr;
+  const cudaError_t e = cudaStreamEndCapture(ctx->stream, &graph);
+  cudaGraphExec_t exec = nullptr;
+  const bool ok = s == FR_OK && e == cudaSuccess && graph && fr_alloc_epoch().load() == epoch &&
+                  cudaGraphInstantiate(&exec, graph, 0) == cudaSuccess;
+  if (graph) cudaGraphDestroy(graph);
+  if (!ok) {
+    cudaGetLastError();
+    ctx->launches = l0;
+    slot->state = -1;
+    return s != FR_OK ? s : enqueue();
+  }
+  slot->exec = exec;
+  slot->launches = ctx->launches - l0;
+  slot->state = 2;
+  FR_CUDA_OK(ctx, cudaGraphLaunch(exec, ctx->stream));
+  return FR_OK;
+}
+
+void graph_key_images(std::vector<long long>& key, const ImgDesc* d_desc, const uint8_t* const* bgr, const int* rows,
+                      const int* cols, const size_t* step, int n_img, const DevBuf& stage) {
+  key.push_back(n_img);
+  key.push_back((long long)(uintptr_t)d_desc);
+  key.push_back((long long)(uintptr_t)stage.p);
+  for (int i = 0; i < n_img; ++i) {
+    key.push_back(rows[i]);
+    key.push_back(cols[i]);
+    key.push_back(step ? (long long)step[i] : -1);
+  }
+}
+
+constexpr int GRAPH_MAX_IMAGES = 4, GRAPH_MAX_FACES = 16;
+
 // align + embed for n_faces faces already on the device.
 int run_embed(fr_ctx* ctx, const ImgDesc* d_desc, int n_img, const fr_face* d_faces, const int* d_face_img,
               int n_faces, int* d_valid, float* d_emb) {
@@ -261,6 +353,8 @@ void fr_destroy(fr_ctx* ctx) {
   det_model_destroy(ctx);
   rec_model_destroy(ctx);
   ctx->img_stage.release();
+  for (auto& g : ctx->graphs)
+    if (g.exec) cudaGraphExecDestroy(g.exec);
   for (auto& sl : ctx->pslots) {
     sl.stage.release();
     if (sl.h2d) cudaEventDestroy(sl.h2d);
@@ -336,8 +430,18 @@ int fr_detect_batch(fr_ctx* ctx, const uint8_t* const* bgr, const int* rows, con
   const size_t fb = sizeof(fr_face) * (size_t)n_img * cap_per_img;
   if (!ctx->misc[B_DET_OUT].reserve(fb) || !ctx->misc[B_DET_N].reserve(sizeof(int) * n_img))
     return fr_fail(ctx, FR_ERR_CUDA, "det output allocation failed");
-  FR_CHECK(run_detect(ctx, d_desc, n_img, score_thr, nms_thr, ctx->misc[B_DET_OUT].as<fr_face>(),
-                      cap_per_img, ctx->misc[B_DET_N].as<int>()));
+  auto enqueue = [&]() {
+    return run_detect(ctx, d_desc, n_img, score_thr, nms_thr, ctx->misc[B_DET_OUT].as<fr_face>(), cap_per_img,
+                      ctx->misc[B_DET_N].as<int>());
+  };
+  if (n_img <= GRAPH_MAX_IMAGES) {
+    std::vector<long long> key{1, cap_per_img, (long long)__float_as_int_host(score_thr), (long long)__float_as_int_host(nms_thr),
+                               (long long)(uintptr_t)ctx->misc[B_DET_OUT].p, (long long)(uintptr_t)ctx->misc[B_DET_N].p};
+    graph_key_images(key, d_desc, bgr, rows, cols, step, n_img, ctx->img_stage);
+    FR_CHECK(run_graphed(ctx, key, enqueue));
+  } else {
+    FR_CHECK(enqueue());
+  }
   FR_CHECK(copy_out(ctx, n_out, ctx->misc[B_DET_N].p, sizeof(int) * n_img, memspace));
   FR_CHECK(copy_out(ctx, out, ctx->misc[B_DET_OUT].p, fb, memspace));
   FR_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
@@ -379,8 +483,18 @@ int fr_embed_faces_batch(fr_ctx* ctx, const uint8_t* const* bgr, const int* rows
   else
     FR_CHECK(upload(ctx, ctx->misc[B_FACE_IMG].p, fi.data(), sizeof(int) * n_faces));
   FR_CHECK(upload(ctx, ctx->misc[B_VALID].p, ones.data(), sizeof(int) * n_faces));
-  FR_CHECK(run_embed(ctx, d_desc, n_img, ctx->misc[B_SEL].as<fr_face>(), ctx->misc[B_FACE_IMG].as<int>(),
-                     n_faces, ctx->misc[B_VALID].as<int>(), ctx->misc[B_EMB].as<float>()));
+  auto enqueue = [&]() {
+    return run_embed(ctx, d_desc, n_img, ctx->misc[B_SEL].as<fr_face>(), ctx->misc[B_FACE_IMG].as<int>(), n_faces,
+                     ctx->misc[B_VALID].as<int>(), ctx->misc[B_EMB].as<float>());
+  };
+  if (memspace != FR_MEM_DEVICE && n_img <= GRAPH_MAX_IMAGES && n_faces <= GRAPH_MAX_FACES) {
+    std::vector<long long> key{2, n_faces, (long long)(uintptr_t)ctx->misc[B_SEL].p, (long long)(uintptr_t)ctx->misc[B_FACE_IMG].p,
+                               (long long)(uintptr_t)ctx->misc[B_VALID].p, (long long)(uintptr_t)ctx->misc[B_EMB].p};
+    graph_key_images(key, d_desc, bgr, rows, cols, step, n_img, ctx->img_stage);
+    FR_CHECK(run_graphed(ctx, key, enqueue));
+  } else {
+    FR_CHECK(enqueue());
+  }
   FR_CHECK(copy_out(ctx, out, ctx->misc[B_EMB].p, (size_t)n_faces * FR_FEAT_DIM * 4, memspace));
   FR_CHECK(copy_out(ctx, valid, ctx->misc[B_VALID].p, sizeof(int) * n_faces, memspace));
   if (memspace != FR_MEM_DEVICE) FR_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));

@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
 
+#include <atomic>
 #include <cstdint>
 #include <cstdio>
 #include <map>
@@ -40,6 +41,14 @@ struct fr_weights {
 void fr_weights_build_spec(fr_weights& w);                 // names + dims, zero data
 void fr_weights_random_init(fr_weights& w, uint64_t seed); // seeded init of every tensor
 int fr_weights_load_onnx(fr_weights& w, const char* path, std::string& err);
+
+// Bumped whenever the library frees or reallocates device memory that kernels of an earlier call may have
+// been pointed at: a cached CUDA graph (capi.cu) is only replayed while the epoch it was captured under
+// is still the current one.
+inline std::atomic<uint64_t>& fr_alloc_epoch() {
+  static std::atomic<uint64_t> e{0};
+  return e;
+}
 
 // --------------------------------------------------------------------- ctx --
 struct DetModel;  // k_scrfd.cu
@@ -112,6 +121,15 @@ struct fr_ctx {
   cudaStream_t copy_stream = nullptr;
   PipeSlot pslots[2];
   int pslot_next = 0;
+  // small-batch launch chains (fr_detect / fr_embed at a handful of images) replayed as CUDA graphs
+  struct GraphSlot {
+    std::vector<long long> key;      // everything the captured kernel arguments depend on
+    cudaGraphExec_t exec = nullptr;
+    uint64_t epoch = 0;              // fr_alloc_epoch() the key was last run / captured under
+    uint64_t launches = 0;           // kernels per replay (for fr_launch_count)
+    int state = 0;                   // 0 new, 1 ran eagerly once, 2 captured, -1 capture failed: stay eager
+  };
+  std::vector<GraphSlot> graphs;
 };
 
 #define FR_CUDA_OK(ctx, expr)                                                          \

@@ -106,6 +106,7 @@ nms_kernel(DecodeArgs args, float nms_thr, unsigned long long* keys_g, int4* box
   int* pref = reinterpret_cast<int*>(keep + (NA / 32 + 2));
   __shared__ unsigned int blockmask;
   __shared__ int kept_total;
+  __shared__ int cur_block;
 
   const int img = blockIdx.x;
   const int tid = threadIdx.x;
@@ -147,42 +148,62 @@ nms_kernel(DecodeArgs args, float nms_thr, unsigned long long* keys_g, int4* box
   }
   __syncthreads();
 
+  // Greedy suppression in sorted order, 32 candidates (one warp) at a time.  Warp 0 walks the blocks: a block
+  // whose candidates were all suppressed by earlier keepers costs one ballot; in a block with survivors only
+  // the candidates still alive are visited (each may suppress later lanes).  The block's keepers are then
+  // published and ALL threads apply them to the rest of the list, so the block-wide barriers are paid once
+  // per block that keeps something, not once per 32 candidates.
   const int nblk = (n + 31) >> 5;
-  for (int blk = 0; blk < nblk; ++blk) {
-    const int base = blk << 5;
+  int blk = 0;
+  while (true) {
     if (tid < 32) {
-      const int j = base + tid;
-      const bool valid = j < n;
-      int4 bj = valid ? B[j] : make_int4(0, 0, 0, 0);
-      bool alive = valid && !supp[j];
-      for (int t = 0; t < 32; ++t) {
-        const unsigned am = __ballot_sync(0xffffffffu, alive);
-        if (!((am >> t) & 1u)) continue;
-        int4 bi;
-        bi.x = __shfl_sync(0xffffffffu, bj.x, t);
-        bi.y = __shfl_sync(0xffffffffu, bj.y, t);
-        bi.z = __shfl_sync(0xffffffffu, bj.z, t);
-        bi.w = __shfl_sync(0xffffffffu, bj.w, t);
-        if (tid > t && alive && iou_gt(bi, bj, nms_thr)) alive = false;
-      }
-      const unsigned am = __ballot_sync(0xffffffffu, alive);
-      if (tid == 0) { blockmask = am; keep[blk] = am; }
-    }
-    __syncthreads();
-    const unsigned am = blockmask;
-    if (am != 0) {
-      for (int j = base + 32 + tid; j < n; j += NMS_THREADS) {
-        if (supp[j]) continue;
-        const int4 bj = B[j];
-        unsigned m = am;
-        while (m) {
-          const int t = __ffs(m) - 1;
-          m &= m - 1;
-          if (iou_gt(B[base + t], bj, nms_thr)) { supp[j] = 1; break; }
+      unsigned am = 0;
+      int bcur = blk;
+      for (; bcur < nblk; ++bcur) {
+        const int j = (bcur << 5) + tid;
+        const bool valid = j < n;
+        bool alive = valid && !supp[j];
+        unsigned rem = __ballot_sync(0xffffffffu, alive);
+        if (rem == 0) {
+          if (tid == 0) keep[bcur] = 0;
+          continue;
         }
+        const int4 bj = valid ? B[j] : make_int4(0, 0, 0, 0);
+        unsigned cand = rem;
+        while (cand) {
+          const int t = __ffs(cand) - 1;               // lowest candidate still alive: it is kept
+          int4 bi;
+          bi.x = __shfl_sync(0xffffffffu, bj.x, t);
+          bi.y = __shfl_sync(0xffffffffu, bj.y, t);
+          bi.z = __shfl_sync(0xffffffffu, bj.z, t);
+          bi.w = __shfl_sync(0xffffffffu, bj.w, t);
+          if (tid > t && alive && iou_gt(bi, bj, nms_thr)) alive = false;
+          rem = __ballot_sync(0xffffffffu, alive);
+          cand = rem & ~((2u << t) - 1u);              // alive lanes above t
+        }
+        am = rem;
+        if (tid == 0) keep[bcur] = am;
+        break;
+      }
+      if (tid == 0) { blockmask = am; cur_block = bcur; }
+    }
+    __syncthreads();
+    const int bcur = cur_block;
+    if (bcur >= nblk) break;
+    const unsigned am = blockmask;
+    const int base = bcur << 5;
+    for (int j = base + 32 + tid; j < n; j += NMS_THREADS) {
+      if (supp[j]) continue;
+      const int4 bj = B[j];
+      unsigned m = am;
+      while (m) {
+        const int t = __ffs(m) - 1;
+        m &= m - 1;
+        if (iou_gt(B[base + t], bj, nms_thr)) { supp[j] = 1; break; }
       }
     }
     __syncthreads();
+    blk = bcur + 1;
   }
   // compaction in sorted order: exclusive prefix over the keep words, then scatter
   if (tid == 0) {

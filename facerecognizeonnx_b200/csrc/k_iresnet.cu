@@ -815,6 +815,7 @@ int rec_model_create(fr_ctx* ctx, const fr_weights* w) {
 }
 
 static void rec_free_plan(RecModel* m) {
+  fr_alloc_epoch()++;          // cached CUDA graphs (capi.cu) point into the plan's buffers
   for (void* p : m->plan_allocs) cudaFree(p);
   m->plan_allocs.clear();
   m->bufs.clear();

@@ -1823,6 +1823,7 @@ float* act_alloc(DetModel* m, size_t elems) {
 }
 
 void det_free_acts(DetModel* m) {
+  if (!m->act_allocs.empty()) fr_alloc_epoch()++;
   for (void* p : m->act_allocs) cudaFree(p);
   m->act_allocs.clear();
   m->a_stage.clear();
@@ -1865,6 +1866,7 @@ int det_build_acts(fr_ctx* ctx, int cap) {
     return fr_fail(ctx, FR_ERR_CUDA, "det activation allocation failed");
   }
   m->cap = cap;
+  fr_alloc_epoch()++;
   return FR_OK;
 }
 

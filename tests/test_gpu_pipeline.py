@@ -201,3 +201,47 @@ def test_detect_edge_cases_vs_oracle(ctx, capi, det_wdict):
     # the fused pipeline with no detection and no padding faces marks every slot invalid and returns zeros
     faces, n_det, emb, valid = ctx.pipeline([ims[4]], 4, None, score_thr=0.9999)
     assert n_det[0] == 0 and not valid.any() and not emb.any()
+
+
+def test_small_batch_graph_replay_is_transparent(ctx, capi):
+    """fr_detect / fr_embed at a handful of images replay their launch chain as a CUDA graph from the third
+    call with the same shapes on (capi.cu: run_graphed).  Eager run, capture, and replays must return the
+    same bytes for the same input, different inputs of the same shape must not see each other's results,
+    other shapes in between must not disturb a cached graph, and a reallocation of the scratch buffers (a
+    larger batch) must retire the graphs instead of replaying stale pointers."""
+    rng = np.random.default_rng(47)
+    a, b = _frames(rng, 2)
+    c = _frames(rng, 1, 480, 600)[0]
+    l0 = ctx.launch_count()
+    first_a = ctx.detect(a, 0.5, 0.4, cap=64)          # eager
+    per_call = ctx.launch_count() - l0
+    first_b = ctx.detect(b, 0.5, 0.4, cap=64)          # captured
+    assert len(first_a) > 0 and not np.array_equal(first_a, first_b)
+    for _ in range(3):                                 # replays
+        l1 = ctx.launch_count()
+        assert np.array_equal(ctx.detect(a, 0.5, 0.4, cap=64), first_a)
+        assert ctx.launch_count() - l1 == per_call     # replays still count their kernels
+        assert np.array_equal(ctx.detect(b, 0.5, 0.4, cap=64), first_b)
+    first_c = ctx.detect(c, 0.5, 0.4, cap=64)          # another shape: its own key
+    assert np.array_equal(ctx.detect(a, 0.5, 0.4, cap=64), first_a)
+    assert np.array_equal(ctx.detect(c, 0.5, 0.4, cap=64), first_c)
+    assert np.array_equal(ctx.detect(c, 0.5, 0.4, cap=64), first_c)
+    assert np.array_equal(ctx.detect(a, 0.3, 0.4, cap=64), ctx.detect(a, 0.3, 0.4, cap=64))   # threshold is in the key
+    assert np.array_equal(ctx.detect(a, 0.5, 0.4, cap=64), first_a)
+    # embeddings of detected faces: eager / capture / replay
+    fa, fb = first_a[:3].copy(), first_b[:2].copy()
+    ea = [ctx.embed_faces([a], fa, [0] * len(fa))[0] for _ in range(4)]
+    eb = [ctx.embed_faces([b], fb, [0] * len(fb))[0] for _ in range(3)]
+    for e in ea[1:]:
+        assert np.array_equal(e, ea[0])
+    for e in eb[1:]:
+        assert np.array_equal(e, eb[0])
+    assert np.array_equal(ctx.embed_faces([a], fa, [0] * len(fa))[0], ea[0])
+    # grow every scratch buffer (64 frames, 128 faces), then the small calls again
+    big = _frames(rng, 6)
+    ctx.detect_batch(big, 0.5, 0.4, cap=512)
+    lms = synth_landmarks(rng, 200, 640, 640)
+    ctx.embed_faces([a], faces_from_landmarks(capi, lms), [0] * 200)
+    for _ in range(3):
+        assert np.array_equal(ctx.detect(a, 0.5, 0.4, cap=64), first_a)
+        assert np.array_equal(ctx.embed_faces([a], fa, [0] * len(fa))[0], ea[0])
