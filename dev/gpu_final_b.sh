@@ -9,4 +9,6 @@ ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,
 echo "pass2 rc=$?"
 ncu --set full --clock-control none --import-source on -k regex:halo_gemm2 -s 30 -c 2 -o gpurun_out/r2_halo_gemm2_full $CMD > gpurun_out/r2_ncu3.log 2>&1
 echo "pass3 rc=$?"
+ncu --set full --clock-control none --import-source on -k regex:front_fused -s 2 -c 1 -o gpurun_out/r2_front_fused_full $CMD > gpurun_out/r2_ncu4.log 2>&1
+echo "pass4 rc=$?"
 ls -la gpurun_out/ | tail -8
