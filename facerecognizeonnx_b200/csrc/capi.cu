@@ -357,10 +357,13 @@ void fr_destroy(fr_ctx* ctx) {
     if (g.exec) cudaGraphExecDestroy(g.exec);
   for (auto& sl : ctx->pslots) {
     sl.stage.release();
+    sl.pad.release(); sl.r_faces.release(); sl.r_ndet.release(); sl.r_emb.release(); sl.r_valid.release();
+    if (sl.computed) cudaEventDestroy(sl.computed);
     if (sl.h2d) cudaEventDestroy(sl.h2d);
     if (sl.done) cudaEventDestroy(sl.done);
   }
   if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+  if (ctx->d2h_stream) cudaStreamDestroy(ctx->d2h_stream);
   ctx->img_desc.release();
   for (auto& sl : ctx->desc_cache) sl.d.release();
   ctx->faces_dev.release();
@@ -643,22 +646,47 @@ int fr_pipeline_submit(fr_ctx* ctx, const uint8_t* const* bgr, const int* rows, 
   if (!ctx->det || !ctx->rec) return fr_fail(ctx, FR_ERR_NOT_LOADED, "Model not loaded!");
   if (faces_per_img <= 0 || !out_emb || !ticket) return fr_fail(ctx, FR_ERR_INVALID_ARG, "bad pipeline arguments");
   if (!ctx->copy_stream) FR_CUDA_OK(ctx, cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+  if (!ctx->d2h_stream) FR_CUDA_OK(ctx, cudaStreamCreateWithFlags(&ctx->d2h_stream, cudaStreamNonBlocking));
   const int si = ctx->pslot_next;
   fr_ctx::PipeSlot& sl = ctx->pslots[si];
   if (!sl.h2d) {
     FR_CUDA_OK(ctx, cudaEventCreateWithFlags(&sl.h2d, cudaEventDisableTiming));
+    FR_CUDA_OK(ctx, cudaEventCreateWithFlags(&sl.computed, cudaEventDisableTiming));
     FR_CUDA_OK(ctx, cudaEventCreateWithFlags(&sl.done, cudaEventDisableTiming));
   }
-  // the slot's staging buffer may still be read by the batch submitted two calls ago
-  if (sl.busy) FR_CUDA_OK(ctx, cudaStreamWaitEvent(ctx->copy_stream, sl.done, 0));
+  const int n_faces = n_img * faces_per_img;
+  if (!sl.r_faces.reserve(sizeof(fr_face) * n_faces) || !sl.r_ndet.reserve(sizeof(int) * n_img) ||
+      !sl.r_emb.reserve((size_t)n_faces * FR_FEAT_DIM * 4) || !sl.r_valid.reserve(sizeof(int) * n_faces) ||
+      (pad_faces && !sl.pad.reserve(sizeof(fr_face) * n_faces)))
+    return fr_fail(ctx, FR_ERR_CUDA, "pipeline slot allocation failed");
+  // the slot's staging and result buffers may still be in use by the batch submitted two calls ago
+  // (sl.done = its results have reached the host)
+  if (sl.busy) {
+    FR_CUDA_OK(ctx, cudaStreamWaitEvent(ctx->copy_stream, sl.done, 0));
+    FR_CUDA_OK(ctx, cudaStreamWaitEvent(ctx->stream, sl.done, 0));
+  }
   const ImgDesc* d_desc = nullptr;
   FR_CHECK(prepare_images(ctx, bgr, rows, cols, step, n_img, FR_MEM_HOST, true, &d_desc, nullptr, &sl.stage,
                           ctx->copy_stream));
+  if (pad_faces)
+    FR_CUDA_OK(ctx, cudaMemcpyAsync(sl.pad.p, pad_faces, sizeof(fr_face) * n_faces, cudaMemcpyHostToDevice, ctx->copy_stream));
   FR_CUDA_OK(ctx, cudaEventRecord(sl.h2d, ctx->copy_stream));
   FR_CUDA_OK(ctx, cudaStreamWaitEvent(ctx->stream, sl.h2d, 0));
-  FR_CHECK(pipeline_enqueue(ctx, d_desc, n_img, FR_MEM_HOST, score_thr, nms_thr, faces_per_img, pad_faces,
-                            out_faces, out_n_det, out_emb, out_valid));
-  FR_CUDA_OK(ctx, cudaEventRecord(sl.done, ctx->stream));
+  // compute into the slot's own result buffers; the D2H copies run on their own stream, so the next batch's
+  // kernels start as soon as this batch's last kernel has finished
+  FR_CHECK(pipeline_enqueue(ctx, d_desc, n_img, FR_MEM_DEVICE, score_thr, nms_thr, faces_per_img,
+                            pad_faces ? sl.pad.as<fr_face>() : nullptr, sl.r_faces.as<fr_face>(), sl.r_ndet.as<int>(),
+                            sl.r_emb.as<float>(), sl.r_valid.as<int>()));
+  FR_CUDA_OK(ctx, cudaEventRecord(sl.computed, ctx->stream));
+  FR_CUDA_OK(ctx, cudaStreamWaitEvent(ctx->d2h_stream, sl.computed, 0));
+  auto back = [&](void* dst, const DevBuf& src, size_t bytes) {
+    return dst ? cudaMemcpyAsync(dst, src.p, bytes, cudaMemcpyDeviceToHost, ctx->d2h_stream) : cudaSuccess;
+  };
+  FR_CUDA_OK(ctx, back(out_emb, sl.r_emb, (size_t)n_faces * FR_FEAT_DIM * 4));
+  FR_CUDA_OK(ctx, back(out_faces, sl.r_faces, sizeof(fr_face) * n_faces));
+  FR_CUDA_OK(ctx, back(out_n_det, sl.r_ndet, sizeof(int) * n_img));
+  FR_CUDA_OK(ctx, back(out_valid, sl.r_valid, sizeof(int) * n_faces));
+  FR_CUDA_OK(ctx, cudaEventRecord(sl.done, ctx->d2h_stream));
   sl.busy = true;
   ctx->pslot_next = si ^ 1;
   *ticket = si;

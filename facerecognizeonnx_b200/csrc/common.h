@@ -114,11 +114,13 @@ struct fr_ctx {
   // asynchronous pipeline (fr_pipeline_submit / fr_pipeline_wait): the frames of batch i+1 are
   // copied on copy_stream into the other staging slot while batch i computes on `stream`
   struct PipeSlot {
-    DevBuf stage;
-    cudaEvent_t h2d = nullptr, done = nullptr;
+    DevBuf stage;                                  // frames
+    DevBuf pad, r_faces, r_ndet, r_emb, r_valid;   // padding faces (H2D) and the batch's results (D2H)
+    cudaEvent_t h2d = nullptr, computed = nullptr, done = nullptr;
     bool busy = false;
   };
-  cudaStream_t copy_stream = nullptr;
+  cudaStream_t copy_stream = nullptr;              // H2D
+  cudaStream_t d2h_stream = nullptr;               // results go back while the next batch already computes
   PipeSlot pslots[2];
   int pslot_next = 0;
   // small-batch launch chains (fr_detect / fr_embed at a handful of images) replayed as CUDA graphs
