@@ -311,6 +311,7 @@ struct RecModel {
   float* stem_b = nullptr;
   uint2* stem_bfrag = nullptr;  // stem weights as m16n8k16 B fragments [kstep][ntile][hi/lo][lane]
   float* stem_prelu = nullptr;
+  float stem_prelu_h[64] = {0};   // host copy: stem_mma_kernel reads the slopes through the kernel-parameter bank
   std::vector<BlockW> blocks;
   bf16* fc_w = nullptr;     // [512][64*512] (bn2, feat affine folded; zero at halo cells)
   float* fc_b = nullptr;
@@ -476,11 +477,12 @@ __device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a
       : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b.x), "r"(b.y));
 }
 
-__global__ void __launch_bounds__(STEM_WARPS * 32)
+struct StemSlopes { float v[64]; };
+
+__global__ void __launch_bounds__(STEM_WARPS * 32, 2)
 stem_mma_kernel(const uint8_t* __restrict__ crops, const uint2* __restrict__ bfrag,
-                const float* __restrict__ slope, bf16* __restrict__ x0, bf16* __restrict__ x0e) {
+                const StemSlopes slope, bf16* __restrict__ x0, bf16* __restrict__ x0e) {
   __shared__ __align__(16) uint16_t strip[(STEM_STRIP + 7) / 8 * 8];
-  __shared__ __align__(16) uint2 sfrag[2 * 8 * 2 * 32];              // [kstep][ntile][hi/lo][lane]
   __shared__ __align__(16) uint8_t stage[STEM_WARPS][16 * STEM_STAGE_PITCH];
   constexpr int NT = STEM_WARPS * 32;
   constexpr int ROW_WORDS = REC * 3 / 4;                             // 84 u32 per input row
@@ -505,18 +507,23 @@ stem_mma_kernel(const uint8_t* __restrict__ crops, const uint2* __restrict__ bfr
   };
   prefetch(yblk);
   for (int i = threadIdx.x; i < (STEM_STRIP + 7) / 8; i += NT) reinterpret_cast<uint4*>(strip)[i] = make_uint4(0, 0, 0, 0);
-  for (int i = threadIdx.x; i < 2 * 8 * 2 * 32 / 2; i += NT)
-    reinterpret_cast<uint4*>(sfrag)[i] = __ldg(reinterpret_cast<const uint4*>(bfrag) + i);
-  // per-thread constants: strip offsets of its 8 k indices, PReLU slopes of its 16 channels
+  // The weight fragments [kstep][ntile][hi/lo] of this lane stay in registers for the whole block (64 registers):
+  // read from shared memory per tile they were half of the kernel's shared-memory wavefronts, and the kernel
+  // is bound by that pipe (ncu: L1 / shared 93 % busy, 131 wavefronts per 16-pixel tile, 64 of them these).
+  uint2 bfr[2][8][2];
+#pragma unroll
+  for (int ks = 0; ks < 2; ++ks)
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+#pragma unroll
+      for (int h = 0; h < 2; ++h) bfr[ks][j][h] = __ldg(bfrag + ((ks * 8 + j) * 2 + h) * 32 + lane);
+  // per-thread constants: strip offsets of its 8 k indices
   int koff[8];
 #pragma unroll
   for (int q = 0; q < 8; ++q) {
     const int k = (q >> 2) * 16 + ((q >> 1) & 1) * 8 + 2 * t + (q & 1);
     koff[q] = (k / 9) * STEM_ROWP + (k % 9);
   }
-  float2 sl[8];
-#pragma unroll
-  for (int j = 0; j < 8; ++j) sl[j] = __ldg(reinterpret_cast<const float2*>(slope + 8 * j + 2 * t));
   constexpr int Wp = REC + 1, Hp = REC + 1, We = REC / 2 + 1, He = REC / 2 + 1;
   uint8_t* st = stage[warp];
 #pragma unroll 1
@@ -546,37 +553,46 @@ stem_mma_kernel(const uint8_t* __restrict__ crops, const uint2* __restrict__ bfr
 #pragma unroll 1
     for (int m = 0; m < REC / 16; ++m) {
       const uint16_t* s0 = strip + warp * STEM_ROWP + (16 * m + g) * 3;
-      float acc[8][4];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) { acc[j][0] = 0.f; acc[j][1] = 0.f; acc[j][2] = 0.f; acc[j][3] = 0.f; }
+      uint32_t a[2][4];
 #pragma unroll
       for (int ks = 0; ks < 2; ++ks) {
-        uint32_t a[4];
 #pragma unroll
         for (int q = 0; q < 4; ++q) {                     // a0:(g,k lo) a1:(g+8,k lo) a2:(g,k hi) a3:(g+8,k hi)
           const uint16_t* sp = s0 + (q & 1) * 24;
           const int ko = ks * 4 + (q >> 1) * 2;
-          a[q] = (uint32_t)sp[koff[ko]] | ((uint32_t)sp[koff[ko + 1]] << 16);
-        }
-        if (ks == 1 && t == 1) {                          // k = 27 carries the bias: A = 1.0
-          a[2] = (a[2] & 0xffffu) | 0x3f800000u;
-          a[3] = (a[3] & 0xffffu) | 0x3f800000u;
-        }
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          mma_bf16_16816(acc[j], a, sfrag[((ks * 8 + j) * 2 + 0) * 32 + lane]);
-          mma_bf16_16816(acc[j], a, sfrag[((ks * 8 + j) * 2 + 1) * 32 + lane]);
+          a[ks][q] = (uint32_t)sp[koff[ko]] | ((uint32_t)sp[koff[ko + 1]] << 16);
         }
       }
-      // PReLU, bf16, stage: pixel r of the tile at st + r*144, channel pair (8j + 2t) at byte 16j + 4t
-      __syncwarp();
+      if (t == 1) {                                       // k = 27 carries the bias: A = 1.0
+        a[1][2] = (a[1][2] & 0xffffu) | 0x3f800000u;
+        a[1][3] = (a[1][3] & 0xffffu) | 0x3f800000u;
+      }
+      __syncwarp();                                       // the previous tile's staged pixels have been read
+      // two halves of 32 channels: 16 accumulators live at a time (same accumulation order as before:
+      // per n tile k step 0 hi, lo, k step 1 hi, lo)
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        float v0 = acc[j][0], v1 = acc[j][1], v2 = acc[j][2], v3 = acc[j][3];
-        v0 = v0 > 0.f ? v0 : v0 * sl[j].x; v1 = v1 > 0.f ? v1 : v1 * sl[j].y;
-        v2 = v2 > 0.f ? v2 : v2 * sl[j].x; v3 = v3 > 0.f ? v3 : v3 * sl[j].y;
-        *reinterpret_cast<uint32_t*>(st + g * STEM_STAGE_PITCH + 16 * j + 4 * t) = tc::pack_bf16(v0, v1);
-        *reinterpret_cast<uint32_t*>(st + (g + 8) * STEM_STAGE_PITCH + 16 * j + 4 * t) = tc::pack_bf16(v2, v3);
+      for (int half = 0; half < 2; ++half) {
+        float acc[4][4];
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) { acc[jj][0] = 0.f; acc[jj][1] = 0.f; acc[jj][2] = 0.f; acc[jj][3] = 0.f; }
+#pragma unroll
+        for (int ks = 0; ks < 2; ++ks)
+#pragma unroll
+          for (int jj = 0; jj < 4; ++jj) {
+            mma_bf16_16816(acc[jj], a[ks], bfr[ks][4 * half + jj][0]);
+            mma_bf16_16816(acc[jj], a[ks], bfr[ks][4 * half + jj][1]);
+          }
+        // PReLU, bf16, stage: pixel r of the tile at st + r*144, channel pair (8j + 2t) at byte 16j + 4t
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) {
+          const int j = 4 * half + jj;
+          const float2 sl = *reinterpret_cast<const float2*>(&slope.v[8 * j + 2 * t]);   // constant bank (LDC)
+          float v0 = acc[jj][0], v1 = acc[jj][1], v2 = acc[jj][2], v3 = acc[jj][3];
+          v0 = v0 > 0.f ? v0 : v0 * sl.x; v1 = v1 > 0.f ? v1 : v1 * sl.y;
+          v2 = v2 > 0.f ? v2 : v2 * sl.x; v3 = v3 > 0.f ? v3 : v3 * sl.y;
+          *reinterpret_cast<uint32_t*>(st + g * STEM_STAGE_PITCH + 16 * j + 4 * t) = tc::pack_bf16(v0, v1);
+          *reinterpret_cast<uint32_t*>(st + (g + 8) * STEM_STAGE_PITCH + 16 * j + 4 * t) = tc::pack_bf16(v2, v3);
+        }
       }
       __syncwarp();
       // a quarter warp moves one pixel's 128 bytes: conflict-free reads, whole-line stores
@@ -750,6 +766,8 @@ int rec_model_create(fr_ctx* ctx, const fr_weights* w) {
     m->stem_bfrag = dev_upload(ctx, m.get(), frag);
     m->stem_b = dev_upload(ctx, m.get(), w->at("stem.b").data);
     m->stem_prelu = dev_upload(ctx, m.get(), w->at("stem.prelu").data);
+    if (w->at("stem.prelu").data.size() != 64) return fr_fail(ctx, FR_ERR_MODEL, "stem.prelu must have 64 slopes");
+    memcpy(m->stem_prelu_h, w->at("stem.prelu").data.data(), sizeof(m->stem_prelu_h));
   }
   const int layers[4][2] = {{3, 64}, {4, 128}, {14, 256}, {3, 512}};
   int cin = 64;
@@ -1014,8 +1032,10 @@ static int rec_launch_stem(fr_ctx* ctx, const uint8_t* d_crops, int n) {
     stem_kernel<true><<<(unsigned)((threads + 127) / 128), 128, 0, ctx->stream>>>(
         d_crops, n, m->stem_w, m->stem_b, m->stem_prelu, m->x0.p, m->x0e.p);
   } else {
+    StemSlopes sl;
+    memcpy(sl.v, m->stem_prelu_h, sizeof(sl.v));
     stem_mma_kernel<<<(unsigned)(n * (REC / (STEM_WARPS * STEM_GROUPS))), STEM_WARPS * 32, 0, ctx->stream>>>(
-        d_crops, m->stem_bfrag, m->stem_prelu, m->x0.p, m->x0e.p);
+        d_crops, m->stem_bfrag, sl, m->x0.p, m->x0e.p);
   }
   ctx->stage_end();
   ctx->launches++;
