@@ -94,6 +94,8 @@ struct SepParams {
   int bw, bh, halo;     // input box (pixels) and its halo (1 for 3x3 stencils, 0 for 1x1)
   int in_bytes;         // bytes per input stage (rounded up to 1024)
   int in_merged;        // cin == kc == 16: the map is 2-D over (W * 8 u64, N*H): one request per box row
+  int tail8;            // depthwise, kc = 32, stride 1, cin % 32 == 8: the last K block has 8 real channels; its box is
+                        // loaded 8 channels wide (tmInTail) and converted one pixel x one chunk per thread
   int s_in, s_ab;       // ring depths
   int tmem_cols;
   int nbig;             // hi*hi accumulators per tile (k steps alternate between them)
@@ -339,6 +341,13 @@ __device__ __forceinline__ void converter_loop(const SepParams& p, const Rings& 
     b4 = kin ? lds4(dw_base + (uint32_t)((9 * p.cin + k0) * 4)) : zero4();
   };
   if (MODE == LD_DW) load_dw(chunk * 4);
+  // tail block (p.tail8): 128 pixels x 2 chunks = one (pixel, chunk) per thread, box pixel pitch 32 bytes; a
+  // quarter warp reads 4 adjacent pixels = 128 contiguous bytes
+  const int t_row = t >> 1, t_chunk = t & 1;
+  const int t_ty = t_row / p.tw, t_tx = t_row - t_ty * p.tw;
+  const bool t_active = t_ty < p.th;
+  const uint32_t t_soff = sw128(t_row, t_chunk);
+  const int t_box_off = (t_ty * p.bw + t_tx) * 32 + t_chunk * 16;
   int si = 0, sa = 0;
   uint32_t ph_in = 0, ph_ab = 0, dbg_kb = 0, dbg_box = 0;
   for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -352,6 +361,41 @@ __device__ __forceinline__ void converter_loop(const SepParams& p, const Rings& 
       const uint32_t box = in_base + (uint32_t)(si * p.in_bytes + box_off);
       const int k0 = i * KC + chunk * 4;
       const bool kv = k0 < p.cin && pix_ok;
+      if (KC == 32 && STRIDE == 1 && MODE == LD_DW && p.tail8 && i == p.n_in - 1) {
+        load_dw(i * KC + t_chunk * 4);
+        mbar_wait_spin(&r.empty_ab[sa], ph_ab ^ 1u, p.err_flag);
+        if (t == 0) dbg_stamp(p, 0, dbg_kb, 0);
+        if (t_active) {
+          float4 acc = zero4();
+          if (tc.gy0 + t_ty < p.rows_out) {
+            int yy = tc.y0 + t_ty;
+            if (yy >= p.hout) yy -= p.hout;
+            acc = b4;
+            const uint32_t tb = in_base + (uint32_t)(si * p.in_bytes + t_box_off);
+#pragma unroll
+            for (int rr = 0; rr < 3; ++rr) {
+              const int iy = yy - 1 + rr;
+              if (iy >= 0 && iy < p.hin) {
+                const uint32_t rb = tb + (uint32_t)(rr * p.bw * 32);
+#pragma unroll
+                for (int s2 = 0; s2 < 3; ++s2) fma4(acc, lds4(rb + s2 * 32), w[rr * 3 + s2]);
+              }
+            }
+            acc.x = fmaxf(acc.x, 0.f); acc.y = fmaxf(acc.y, 0.f); acc.z = fmaxf(acc.z, 0.f); acc.w = fmaxf(acc.w, 0.f);
+          }
+          const uint32_t hi = ab_base + (uint32_t)(sa * r.ab_bytes);
+          split_store(hi, hi + A_BYTES, t_soff, acc);
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&r.full_ab[sa]);
+        if (t == 0) dbg_stamp(p, 0, dbg_kb++, 1);
+        if (++sa == p.s_ab) { sa = 0; ph_ab ^= 1u; }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&r.empty_in[si]);
+        if (++si == p.s_in) { si = 0; ph_in ^= 1u; }
+        continue;
+      }
       if (MODE == LD_DW && p.n_in > 1) load_dw(k0);
       for (int tap = 0; tap < p.taps; ++tap) {
         mbar_wait_spin(&r.empty_ab[sa], ph_ab ^ 1u, p.err_flag);
@@ -416,8 +460,8 @@ __device__ __forceinline__ void converter_loop(const SepParams& p, const Rings& 
 }
 
 __global__ void __launch_bounds__(THREADS, 1)
-sep_gemm_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant__ CUtensorMap tmW,
-                const __grid_constant__ SepParams p) {
+sep_gemm_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant__ CUtensorMap tmInTail,
+                const __grid_constant__ CUtensorMap tmW, const __grid_constant__ SepParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
@@ -457,6 +501,7 @@ sep_gemm_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant_
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     tc::prefetch_tmap(&tmIn);
+    tc::prefetch_tmap(&tmInTail);
     tc::prefetch_tmap(&tmW);
   }
   if (warp == 2) {
@@ -484,6 +529,13 @@ sep_gemm_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant_
         for (int i = 0; i < p.n_in; ++i) {
           mbar_wait(&r.empty_in[s], ph ^ 1u, p.err_flag);
           dbg_stamp(p, 3, dbg_box++, 0);
+          if (p.tail8 && i == p.n_in - 1) {
+            mbar_expect_tx(&r.full_in[s], box_bytes >> 2);
+            tma_load_3d(r.in + s * p.in_bytes, &tmInTail, &r.full_in[s], i * p.kc, x0 * p.stride - p.halo,
+                        tc.gy0 * p.stride - p.halo);
+            if (++s == p.s_in) { s = 0; ph ^= 1u; }
+            continue;
+          }
           mbar_expect_tx(&r.full_in[s], box_bytes);
           if (p.in_merged)
             tma_load_2d(r.in + s * p.in_bytes, &tmIn, &r.full_in[s], (x0 * p.stride - p.halo) * 8,
@@ -1721,7 +1773,7 @@ struct PackedConv {        // device-side packed parameters of one (fused) layer
   int stride = 1;          // fixed per layer (decides kc)
   int kc = 32, n_in = 1, taps = 1;
   // input tensor map, re-encoded only when the input pointer / batch changes
-  mutable CUtensorMap tmIn;
+  mutable CUtensorMap tmIn, tmInTail;
   mutable const float* tm_in = nullptr;
   mutable int tm_rows = 0, tm_bw = 0, tm_bh = 0;
 };
@@ -1931,6 +1983,8 @@ int launch_layer(fr_ctx* ctx, const PackedConv& pc, const LayerIO& io, int n) {
   }
   p.in_bytes = (p.bh * p.bw * p.kc * 4 + 1023) / 1024 * 1024;
   p.in_merged = (pc.cin == 16 && pc.kc == 16 && p.bw * 8 <= 256) ? 1 : 0;
+  static const bool tail_on = !(getenv("FR_SCRFD_TAIL8") && atoi(getenv("FR_SCRFD_TAIL8")) == 0);   // A/B switch
+  p.tail8 = (tail_on && pc.mode == LD_DW && pc.kc == 32 && pc.stride == 1 && pc.n_in > 1 && pc.cin % 32 == 8) ? 1 : 0;
   const int ab_bytes = 2 * A_BYTES + 2 * pc.nt * 128;
   const int dw_bytes = pc.mode == LD_DW ? (10 * pc.cin * 4 + 15) / 16 * 16 : 0;
   const int budget = 227 * 1024 - 1024 - 512 - dw_bytes - pc.npad_total * 4;
@@ -1960,6 +2014,10 @@ int launch_layer(fr_ctx* ctx, const PackedConv& pc, const LayerIO& io, int n) {
                              (uint32_t)p.bw, (uint32_t)p.bh);
     if (!ok_map)
       return fr_fail(ctx, FR_ERR_CUDA, "scrfd input tensor map creation failed");
+    pc.tmInTail = pc.tmIn;
+    if (p.tail8 && !tc_make_map_3d_f32(&pc.tmInTail, io.in, (uint64_t)pc.cin, (uint64_t)io.hin, (uint64_t)rows_in, 8u,
+                                       (uint32_t)p.bw, (uint32_t)p.bh))
+      return fr_fail(ctx, FR_ERR_CUDA, "scrfd input tensor map creation failed");
     pc.tm_in = io.in;
     pc.tm_rows = rows_in;
     pc.tm_bw = p.bw;
@@ -1976,7 +2034,7 @@ int launch_layer(fr_ctx* ctx, const PackedConv& pc, const LayerIO& io, int n) {
     memset(dbg_buf, 0, 5 * 256 * 2 * sizeof(long long));
     p.dbg = dbg_buf;
   }
-  sep_gemm_kernel<<<grid, THREADS, smem, ctx->stream>>>(pc.tmIn, pc.tmW, p);
+  sep_gemm_kernel<<<grid, THREADS, smem, ctx->stream>>>(pc.tmIn, pc.tmInTail, pc.tmW, p);
   if (dbg_buf) {
     cudaStreamSynchronize(ctx->stream);
     FILE* f = fopen(strchr(dbg_env, ':') + 1, "w");
