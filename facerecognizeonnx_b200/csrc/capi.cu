@@ -293,6 +293,24 @@ void graph_key_images(std::vector<long long>& key, const ImgDesc* d_desc, const 
 
 constexpr int GRAPH_MAX_IMAGES = 4, GRAPH_MAX_FACES = 16;
 
+// key of a whole-batch pipeline launch chain (device-resident inputs): every pointer the kernels will see
+void graph_key_pipeline(std::vector<long long>& key, const ImgDesc* d_desc, const uint8_t* const* bgr, const int* rows,
+                        const int* cols, const size_t* step, int n_img, float score_thr, float nms_thr, int K,
+                        const void* pad, const void* o_faces, const void* o_ndet, const void* o_emb, const void* o_valid) {
+  unsigned long long h = 1469598103934665603ull;             // FNV-1a over the per-image (pointer, rows, cols, step)
+  auto mix = [&](unsigned long long v) {
+    for (int b = 0; b < 8; ++b) { h ^= (v >> (8 * b)) & 0xffull; h *= 1099511628211ull; }
+  };
+  for (int i = 0; i < n_img; ++i) {
+    mix((unsigned long long)(uintptr_t)bgr[i]);
+    mix(((unsigned long long)(unsigned)rows[i] << 32) | (unsigned)cols[i]);
+    mix(step ? (unsigned long long)step[i] : ~0ull);
+  }
+  key = {3, n_img, K, (long long)h, (long long)(uintptr_t)d_desc, (long long)__float_as_int_host(score_thr),
+         (long long)__float_as_int_host(nms_thr), (long long)(uintptr_t)pad, (long long)(uintptr_t)o_faces,
+         (long long)(uintptr_t)o_ndet, (long long)(uintptr_t)o_emb, (long long)(uintptr_t)o_valid};
+}
+
 // align + embed for n_faces faces already on the device.
 int run_embed(fr_ctx* ctx, const ImgDesc* d_desc, int n_img, const fr_face* d_faces, const int* d_face_img,
               int n_faces, int* d_valid, float* d_emb) {
@@ -631,8 +649,18 @@ int fr_pipeline_batch(fr_ctx* ctx, const uint8_t* const* bgr, const int* rows, c
   if (faces_per_img <= 0 || !out_emb) return fr_fail(ctx, FR_ERR_INVALID_ARG, "bad pipeline arguments");
   const ImgDesc* d_desc = nullptr;
   FR_CHECK(prepare_images(ctx, bgr, rows, cols, step, n_img, memspace, true, &d_desc));
-  FR_CHECK(pipeline_enqueue(ctx, d_desc, n_img, memspace, score_thr, nms_thr, faces_per_img, pad_faces, out_faces,
-                            out_n_det, out_emb, out_valid));
+  auto enqueue = [&]() {
+    return pipeline_enqueue(ctx, d_desc, n_img, memspace, score_thr, nms_thr, faces_per_img, pad_faces, out_faces,
+                            out_n_det, out_emb, out_valid);
+  };
+  if (memspace == FR_MEM_DEVICE) {             // fixed device buffers: the ~90-launch chain replays as one graph
+    std::vector<long long> key;
+    graph_key_pipeline(key, d_desc, bgr, rows, cols, step, n_img, score_thr, nms_thr, faces_per_img, pad_faces,
+                       out_faces, out_n_det, out_emb, out_valid);
+    FR_CHECK(run_graphed(ctx, key, enqueue));
+  } else {
+    FR_CHECK(enqueue());
+  }
   if (memspace != FR_MEM_DEVICE) FR_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
   return FR_OK;
 }
@@ -674,9 +702,19 @@ int fr_pipeline_submit(fr_ctx* ctx, const uint8_t* const* bgr, const int* rows, 
   FR_CUDA_OK(ctx, cudaStreamWaitEvent(ctx->stream, sl.h2d, 0));
   // compute into the slot's own result buffers; the D2H copies run on their own stream, so the next batch's
   // kernels start as soon as this batch's last kernel has finished
-  FR_CHECK(pipeline_enqueue(ctx, d_desc, n_img, FR_MEM_DEVICE, score_thr, nms_thr, faces_per_img,
-                            pad_faces ? sl.pad.as<fr_face>() : nullptr, sl.r_faces.as<fr_face>(), sl.r_ndet.as<int>(),
-                            sl.r_emb.as<float>(), sl.r_valid.as<int>()));
+  {
+    const fr_face* d_pad = pad_faces ? sl.pad.as<fr_face>() : nullptr;
+    auto enqueue = [&]() {
+      return pipeline_enqueue(ctx, d_desc, n_img, FR_MEM_DEVICE, score_thr, nms_thr, faces_per_img, d_pad,
+                              sl.r_faces.as<fr_face>(), sl.r_ndet.as<int>(), sl.r_emb.as<float>(), sl.r_valid.as<int>());
+    };
+    // the frames sit in the slot's staging buffer: its address stands in for the host pointers in the key
+    std::vector<const uint8_t*> staged(n_img, sl.stage.as<uint8_t>());
+    std::vector<long long> key;
+    graph_key_pipeline(key, d_desc, staged.data(), rows, cols, step, n_img, score_thr, nms_thr, faces_per_img, d_pad,
+                       sl.r_faces.p, sl.r_ndet.p, sl.r_emb.p, sl.r_valid.p);
+    FR_CHECK(run_graphed(ctx, key, enqueue));
+  }
   FR_CUDA_OK(ctx, cudaEventRecord(sl.computed, ctx->stream));
   FR_CUDA_OK(ctx, cudaStreamWaitEvent(ctx->d2h_stream, sl.computed, 0));
   auto back = [&](void* dst, const DevBuf& src, size_t bytes) {

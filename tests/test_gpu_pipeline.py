@@ -245,3 +245,52 @@ def test_small_batch_graph_replay_is_transparent(ctx, capi):
     for _ in range(3):
         assert np.array_equal(ctx.detect(a, 0.5, 0.4, cap=64), first_a)
         assert np.array_equal(ctx.embed_faces([a], fa, [0] * len(fa))[0], ea[0])
+
+
+def test_pipeline_graph_replay_is_transparent(ctx, capi):
+    """fr_pipeline_batch on device-resident frames and fr_pipeline_submit replay the whole ~90-launch chain as a
+    CUDA graph from the third call with the same buffers on.  The frame CONTENT changes between calls (same
+    device buffers, new pixels): eager, captured and replayed calls must agree with each other for the same
+    content, with the host-buffer entry point (which never uses a graph), and two submit slots must not mix."""
+    rng = np.random.default_rng(48)
+    n_img, K = 3, 4
+    sets = [np.stack(_frames(rng, n_img)) for _ in range(2)]
+    lms = synth_landmarks(rng, n_img * K, 640, 640)
+    pad = faces_from_landmarks(capi, lms).reshape(n_img, K)
+    ref = [ctx.pipeline([s[i] for i in range(n_img)], K, pad) for s in sets]       # host buffers: eager launches
+    dev = torch.device("cuda", 0)
+    frames_d = torch.empty((n_img, 640, 640, 3), dtype=torch.uint8, device=dev)
+    pad_d = torch.from_numpy(pad.view(np.uint8).reshape(n_img * K, 60).copy()).to(dev)
+    o_faces = torch.empty((n_img * K, 60), dtype=torch.uint8, device=dev)
+    o_ndet = torch.empty(n_img, dtype=torch.int32, device=dev)
+    o_emb = torch.empty((n_img * K, 512), dtype=torch.float32, device=dev)
+    o_valid = torch.empty(n_img * K, dtype=torch.int32, device=dev)
+    fb = 640 * 640 * 3
+    for it in range(6):                                  # eager, capture, 4 replays; content alternates
+        which = it % 2
+        frames_d.copy_(torch.from_numpy(sets[which]))
+        torch.cuda.synchronize()
+        ctx.pipeline_dev([frames_d.data_ptr() + j * fb for j in range(n_img)], 640, 640, 640 * 3, K, pad_d.data_ptr(),
+                         o_faces.data_ptr(), o_ndet.data_ptr(), o_emb.data_ptr(), o_valid.data_ptr())
+        ctx.synchronize()
+        faces, n_det, emb, valid = ref[which]
+        assert np.array_equal(o_ndet.cpu().numpy(), n_det), it
+        assert np.array_equal(o_emb.cpu().numpy().reshape(n_img, K, 512), emb), it
+        assert np.array_equal(o_faces.cpu().numpy().view(capi.FACE_DTYPE).reshape(n_img, K), faces), it
+        assert np.array_equal(o_valid.cpu().numpy().reshape(n_img, K), valid), it
+    # streaming entry point: two slots in flight, content alternates, 8 batches (each slot: eager, capture, replays)
+    outs = [(np.zeros((n_img, K), capi.FACE_DTYPE), np.zeros(n_img, np.int32), np.zeros((n_img, K, 512), np.float32),
+             np.zeros((n_img, K), np.int32)) for _ in range(2)]
+    tickets = []
+    for it in range(8):
+        which = (it // 2) % 2                            # AABBAABB: both slots see both contents
+        o = outs[it % 2]
+        if len(tickets) == 2:
+            t_old, w_old, o_old = tickets.pop(0)
+            ctx.pipeline_wait(t_old)
+            assert np.array_equal(o_old[2], ref[w_old][2]) and np.array_equal(o_old[1], ref[w_old][1])
+        tk = ctx.pipeline_submit([sets[which][i] for i in range(n_img)], K, pad, o[0], o[1], o[2], o[3])
+        tickets.append((tk, which, o))
+    for t_old, w_old, o_old in tickets:
+        ctx.pipeline_wait(t_old)
+        assert np.array_equal(o_old[2], ref[w_old][2]) and np.array_equal(o_old[0], ref[w_old][0])
