@@ -17,6 +17,8 @@ namespace {
 constexpr int NA = FR_NUM_ANCHORS;     // 16800
 constexpr int KEY_STRIDE = 32768;      // per-image key capacity (power of two >= NA)
 constexpr int SMEM_CAND = 4096;        // candidates handled entirely in shared memory
+constexpr int MAT_CAND = 512;          // ... and with the bit-matrix NMS (512 x 16 words behind the first 512 boxes)
+static_assert(MAT_CAND * 16 + MAT_CAND * (MAT_CAND / 32) * 4 <= SMEM_CAND * 16, "bit matrix aliases the unused boxes");
 constexpr int NMS_THREADS = 1024;
 
 struct DecodeArgs {
@@ -148,12 +150,48 @@ nms_kernel(DecodeArgs args, float nms_thr, unsigned long long* keys_g, int4* box
   }
   __syncthreads();
 
+  const int nblk = (n + 31) >> 5;
+  if (n <= MAT_CAND) {
+    // Few candidates (the usual case): the whole suppression relation as a bit matrix, in parallel
+    // (word (i, w) = candidates j of word w behind i with IoU(i, j) > thr: independent IoU evaluations, no
+    // serial chain), then ONE warp walks the candidates in score order with the 'removed' set in registers
+    // (lane w = word w): candidate i is kept iff no earlier kept candidate removed it -- the same greedy
+    // rule, ~30 cycles per candidate instead of a ballot / shuffle / IoU chain per keeper.
+    unsigned int* mat = reinterpret_cast<unsigned int*>(boxes_s + MAT_CAND);      // [n][nblk], behind the n boxes
+    for (int e = tid; e < n * nblk; e += NMS_THREADS) {
+      const int i = e / nblk, w = e - i * nblk;
+      unsigned int bits = 0;
+      if ((w << 5) + 31 > i) {
+        const int4 bi = B[i];
+        const int j0 = w << 5;
+#pragma unroll 4
+        for (int b = 0; b < 32; ++b) {
+          const int j = j0 + b;
+          if (j > i && j < n && iou_gt(bi, B[j], nms_thr)) bits |= 1u << b;
+        }
+      }
+      mat[e] = bits;
+    }
+    __syncthreads();
+    if (tid < 32) {
+      unsigned int removed = 0;                      // lane w: bits of word w
+      for (int i = 0; i < n; ++i) {
+        const unsigned int r = __shfl_sync(0xffffffffu, removed, i >> 5);
+        if (!((r >> (i & 31)) & 1u) && tid < nblk) removed |= mat[i * nblk + tid];
+      }
+      if (tid < nblk) {
+        const int left = n - (tid << 5);
+        const unsigned int valid_bits = left >= 32 ? 0xffffffffu : ((1u << left) - 1u);
+        keep[tid] = ~removed & valid_bits;
+      }
+    }
+    __syncthreads();
+  } else {
   // Greedy suppression in sorted order, 32 candidates (one warp) at a time.  Warp 0 walks the blocks: a block
   // whose candidates were all suppressed by earlier keepers costs one ballot; in a block with survivors only
   // the candidates still alive are visited (each may suppress later lanes).  The block's keepers are then
   // published and ALL threads apply them to the rest of the list, so the block-wide barriers are paid once
   // per block that keeps something, not once per 32 candidates.
-  const int nblk = (n + 31) >> 5;
   int blk = 0;
   while (true) {
     if (tid < 32) {
@@ -204,6 +242,7 @@ nms_kernel(DecodeArgs args, float nms_thr, unsigned long long* keys_g, int4* box
     }
     __syncthreads();
     blk = bcur + 1;
+  }
   }
   // compaction in sorted order: exclusive prefix over the keep words, then scatter
   if (tid == 0) {
