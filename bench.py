@@ -299,12 +299,14 @@ def run_gpu(args, rank, world, local_rank):
     # runs a launch chain eagerly the first time it sees a set of buffers, captures it as a CUDA graph the
     # second time and replays it from then on (capi.cu: run_graphed)
     n_warm = max(args.warmup, 3, 2 * n_rot + 1)
-    for i in range(n_warm):
-        step_dev(i)
-    barrier()
+    # the clock sampler (an nvidia-smi loop) starts BEFORE the warm-up: its start-up does not overlap the timed
+    # region, and the GPU goes from the warm-up straight into the timed steps (no idle gap, clocks already up)
     sampler = ClockSampler(local_rank)
     sampler.start()
     time.sleep(0.25)
+    for i in range(n_warm):
+        step_dev(i)
+    barrier()
     l0 = ctx.launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t_wall0 = time.time()
