@@ -1,6 +1,8 @@
 #!/bin/bash
 # final round-2 measurement, part B: ncu passes of the command that part A ran clean (same binary, same args
 # except the shorter step count)
+# FR_GRAPHS=0: the launches go out one by one (the kernels are the same ones the graph replays)
+export FR_GRAPHS=0
 CMD="python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-gallery"
 $CMD > gpurun_out/r2_plain.log 2>&1 &&
 ncu --metrics gpu__time_duration.sum --clock-control none -c 700 --csv --log-file gpurun_out/r2_launches_step.csv $CMD > gpurun_out/r2_ncu1.log 2>&1
