@@ -295,10 +295,11 @@ def run_gpu(args, rank, world, local_rank):
             dist.barrier()
 
     # ---- device-resident throughput
-    # warm-up: at least 3 steps, and at least two visits of every rotating input batch plus one: the library
+    # warm-up: at least 3 steps, and at least three visits of every rotating input batch plus one: the library
     # runs a launch chain eagerly the first time it sees a set of buffers, captures it as a CUDA graph the
-    # second time and replays it from then on (capi.cu: run_graphed)
-    n_warm = max(args.warmup, 3, 2 * n_rot + 1)
+    # second time and replays it from then on (capi.cu: run_graphed); the first REPLAY of a graph still has a
+    # one-time host cost (1-8 ms, once 52 ms: profiles/r2_anomaly_hunt2.txt), so it belongs to the warm-up too
+    n_warm = max(args.warmup, 3, 3 * n_rot + 1)
     # the clock sampler (an nvidia-smi loop) starts BEFORE the warm-up: its start-up does not overlap the timed
     # region, and the GPU goes from the warm-up straight into the timed steps (no idle gap, clocks already up)
     sampler = ClockSampler(local_rank)
@@ -311,12 +312,20 @@ def run_gpu(args, rank, world, local_rank):
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t_wall0 = time.time()
     ev0.record(stream)
+    step_evs = []
+    submit_s = []
     for i in range(args.steps):
+        tc0 = time.perf_counter()
         step_dev(i)
+        submit_s.append(time.perf_counter() - tc0)
+        e = torch.cuda.Event(enable_timing=True)     # between two graph launches: per-step times for diagnostics
+        e.record(stream)
+        step_evs.append(e)
     ev1.record(stream)
     torch.cuda.synchronize()
     t_wall1 = time.time()
     ms = ev0.elapsed_time(ev1)
+    per_step = [a.elapsed_time(b) for a, b in zip([ev0] + step_evs[:-1], step_evs)]
     launches = ctx.launch_count() - l0
     clocks = sampler.stop(t_wall0, t_wall1)
     # per-stage CUDA events: a second pass over the same K steps with stage timing on (an event pair around every
@@ -360,7 +369,7 @@ def run_gpu(args, rank, world, local_rank):
         o = outs[i % 2]
         return ctx.pipeline_submit([fr[j] for j in range(n_img)], K, pad_view, o[0], o[1], o[2], o[3])
 
-    for i in range(max(5, min(args.warmup, 8))):   # both staging slots: eager, captured, replayed
+    for i in range(max(6, min(args.warmup, 8))):   # both staging slots: eager, captured, replayed once
         ctx.pipeline_wait(submit(i))
     barrier()
     t0 = time.perf_counter()
@@ -407,6 +416,9 @@ def run_gpu(args, rank, world, local_rank):
     det_ms = stages["preprocess"] + stages["scrfd"] + stages["decode_nms"]
     emb_ms = stages["align"] + stages["stem"] + stages["trunk"] + stages["l2norm"]
     extra = {"stage_ms_per_step": stages, "ms_per_step_instrumented_pass": ms_staged / args.steps,
+             "step_ms_min_median_max": [min(per_step), statistics.median(per_step), max(per_step)],
+             "slowest_step_index": int(np.argmax(per_step)), "host_submit_ms_max": 1e3 * max(submit_s),
+             "host_submit_slowest_index": int(np.argmax(submit_s)),
              "det_only_frames_per_s_per_gpu": n_img / (det_ms / 1e3) if det_ms > 0 else None,       # configs[1]
              "embed_only_faces_per_s_per_gpu": n_faces / (emb_ms / 1e3) if emb_ms > 0 else None,    # configs[2]
              "k1_preprocess_gbs": k1_bytes / (stage_ms["preprocess"] / 1e3) / 1e9 if stage_ms["preprocess"] > 0 else None,

@@ -23,6 +23,9 @@ for spec in sys.argv[1:]:
               f"pre {st['preprocess']:.3f} nms {st['decode_nms']:.3f}  launches {d['gpu_launches']}  "
               f"c2 {d['detail']['configs']['config2_det_only_batch64']['ms_per_batch']:.3f} "
               f"c3 {d['detail']['configs']['config3_embed_only_batch1024']['ms_per_batch']:.3f} "
-              f"c1 {d['detail']['configs']['config1_compare_batch1']['ms_per_compare_median']:.3f}", flush=True)
+              f"c1 {d['detail']['configs']['config1_compare_batch1']['ms_per_compare_median']:.3f} "
+              f"steps(min/med/max) {'/'.join('%.2f' % v for v in d['detail']['step_ms_min_median_max'])} "
+              f"clk {d['clocks']['sm_mhz']} slowest {d['detail']['slowest_step_index']} "
+              f"submit max {d['detail']['host_submit_ms_max']:.1f} ms at {d['detail']['host_submit_slowest_index']}", flush=True)
     except Exception as e:
         print(spec, "FAILED", e, r.stderr[-800:], flush=True)

@@ -170,6 +170,40 @@ def test_k3_k4_many_candidates_spill_path(ctx):
     _check_faces(got[0], exp)
 
 
+@pytest.mark.parametrize("k", [1, 2, 31, 32, 33, 64, 511, 512, 513, 1000])
+def test_k4_nms_candidate_count_boundaries(ctx, k):
+    """Exactly k candidates per frame around the limits of the two NMS algorithms (bit matrix up to 512
+    candidates, 32-candidate blocks above; warp / word boundaries at 32): clustered boxes so that chains of
+    suppressions cross word boundaries, exact score ties, zero-area and inverted boxes."""
+    rng = np.random.default_rng(100 + k)
+    heads = _random_heads(rng, 2, -30.0)                 # nothing passes on its own
+    for img in range(2):
+        picks = rng.choice(12800 + 3200 + 800, size=k, replace=False)
+        # neighbouring anchors overlap heavily: take half of the picks as runs of adjacent anchors
+        run = min(k // 2, 12000)
+        picks[:run] = 2000 + np.arange(run) + img
+        picks = np.unique(picks)
+        while len(picks) < k:                            # refill after de-duplication
+            extra = rng.choice(16800, size=k - len(picks), replace=False)
+            picks = np.unique(np.concatenate([picks, extra]))
+        picks = picks[:k]
+        sc = rng.uniform(0.55, 0.95, size=k).astype(np.float32)
+        sc[::5] = 0.75                                   # ties
+        for a, v in zip(picks, sc):
+            s, local = (0, a) if a < 12800 else ((1, a - 12800) if a < 16000 else (2, a - 16000))
+            heads[s][img, local, 0] = v
+            if a % 13 == 0:
+                heads[3 + s][img, local] = 0.0           # zero-area box: IoU 0/0 -> NaN -> never suppresses
+            if a % 17 == 0:
+                heads[3 + s][img, local] = -0.5          # inverted box
+    scales = np.array([1.0, 0.75], np.float32)
+    got = ctx.scrfd_decode_nms(heads, scales, 0.5, 0.4, cap=4096)
+    for img in range(2):
+        exp = odet.postprocess(odet.scrfd_decode([h[img] for h in heads]), scales[img], 0.5, 0.4)
+        assert 0 < len(exp) <= k
+        _check_faces(got[img], exp)
+
+
 def test_k4_cap_truncates_in_score_order(ctx):
     rng = np.random.default_rng(12)
     heads = _random_heads(rng, 1, -3.0)
