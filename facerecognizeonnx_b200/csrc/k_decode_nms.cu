@@ -174,17 +174,32 @@ nms_kernel(DecodeArgs args, float nms_thr, unsigned long long* keys_g, int4* box
     }
     __syncthreads();
     if (tid < 32) {
-      // (a word-at-a-time variant -- keepers resolved inside each 32-candidate word, then ORed into the later words --
-      // measured 5 us slower: most candidates survive here, so it runs as many serial steps plus a gather)
-      unsigned int removed = 0;                      // lane w: bits of word w
-      for (int i = 0; i < n; ++i) {
-        const unsigned int r = __shfl_sync(0xffffffffu, removed, i >> 5);
-        if (!((r >> (i & 31)) & 1u) && tid < nblk) removed |= mat[i * nblk + tid];
-      }
-      if (tid < nblk) {
-        const int left = n - (tid << 5);
-        const unsigned int valid_bits = left >= 32 ? 0xffffffffu : ((1u << left) - 1u);
-        keep[tid] = ~removed & valid_bits;
+      // One 32-candidate word at a time, without a shuffle or a branch per candidate: every lane walks the word's
+      // greedy chain itself on the word's diagonal block (broadcast loads that do not depend on the chain, so they
+      // pipeline; the chain is three ALU operations per candidate), then lane w ORs the rows of the word's keepers
+      // into its own word of the removed set.  (A per-candidate loop with a shuffle + a divergent load per step
+      // took ~190 cycles per candidate; a variant with one shuffle per keeper was slower still.)
+      unsigned int removed = 0;                      // lane w: bits of word w removed by keepers of earlier words
+      const int lw = min(tid, nblk - 1);
+      for (int wi = 0; wi < nblk; ++wi) {
+        const int i0 = wi << 5, left = min(32, n - i0);
+        unsigned int alive = ~__shfl_sync(0xffffffffu, removed, wi) & (left >= 32 ? 0xffffffffu : ((1u << left) - 1u));
+        unsigned int kept = 0;
+#pragma unroll 8
+        for (int b = 0; b < 32; ++b) {
+          const unsigned int d = mat[(i0 + min(b, left - 1)) * nblk + wi];   // bits above b only
+          const unsigned int k = (alive >> b) & 1u;
+          kept |= k << b;
+          alive &= ~(d & (0u - k));
+        }
+        unsigned int acc = 0;
+#pragma unroll 8
+        for (int b = 0; b < 32; ++b) {
+          const unsigned int row = mat[(i0 + min(b, left - 1)) * nblk + lw];
+          acc |= row & (0u - ((kept >> b) & 1u));
+        }
+        if (tid > wi) removed |= acc;
+        if (tid == 0) keep[wi] = kept;
       }
     }
     __syncthreads();
