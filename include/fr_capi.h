@@ -143,7 +143,13 @@ FR_API int fr_pipeline_batch(fr_ctx* ctx, const uint8_t* const* bgr, const int* 
  * copied on a separate copy stream into one of two staging slots, so the upload of batch i+1
  * overlaps the compute of batch i; outputs are valid after fr_pipeline_wait(ticket).  At most
  * two batches may be in flight; input and output buffers must stay alive (and should be
- * page-locked for the copies to be asynchronous) until the wait returns. */
+ * page-locked for the copies to be asynchronous) until the wait returns.  The results return on a
+ * third stream, so batch i+1 starts computing as soon as the last kernel of batch i has finished.
+ *
+ * Launch chains whose arguments repeat (this call, fr_pipeline_batch on device-resident frames,
+ * fr_detect(_batch) / fr_embed(_faces_batch) on up to 4 images) are replayed as CUDA graphs from
+ * the third identical call on; the results are the same bytes either way.  FR_GRAPHS=0 in the
+ * environment turns that off. */
 FR_API int fr_pipeline_submit(fr_ctx* ctx, const uint8_t* const* bgr, const int* rows,
                               const int* cols, const size_t* step, int n_img, float score_thr,
                               float nms_thr, int faces_per_img, const fr_face* pad_faces,
