@@ -1804,6 +1804,8 @@ struct DetModel {
   float* kps[3] = {nullptr, nullptr, nullptr};
   int* err_flag = nullptr;
   int num_sms = 148;
+  cudaStream_t aux_stream = nullptr;     // FR_SCRFD_FORK: second branch of the neck / head graph
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
 };
 
 namespace {
@@ -2291,6 +2293,9 @@ void det_model_destroy(fr_ctx* ctx) {
   if (!m) return;
   det_free_acts(m);
   for (void* p : m->allocs) cudaFree(p);
+  if (m->aux_stream) cudaStreamDestroy(m->aux_stream);
+  if (m->ev_fork) cudaEventDestroy(m->ev_fork);
+  if (m->ev_join) cudaEventDestroy(m->ev_join);
   delete m;
   ctx->det = nullptr;
 }
@@ -2472,13 +2477,8 @@ int det_forward(fr_ctx* ctx, const __nv_bfloat16* d_in_chw, int n, HeadPtrs* hea
     io.in = in; io.out = out; io.hin = hin; io.stride = stride; io.accumulate = accumulate;
     return launch_layer(ctx, m->conv.at(name), io, n);
   };
-  for (int i = 0; i < 3; ++i) FR_CHECK(conv3("fpn" + std::to_string(i), m->lat[i], m->inter[i], fh[i], 1, 0));
-  for (int i = 0; i < 2; ++i)
-    FR_CHECK(conv3("down" + std::to_string(i), m->inter[i], m->inter[i + 1], fh[i], 2, 1));
   const float* outs[3] = {m->inter[0], m->pout[1], m->pout[2]};
-  for (int i = 1; i < 3; ++i)
-    FR_CHECK(conv3("pafpn" + std::to_string(i - 1), m->inter[i], m->pout[i], fh[i], 1, 0));
-  for (int i = 0; i < 3; ++i) {
+  auto head = [&](int i) -> int {
     const std::string h = "h" + std::to_string(i);
     FR_CHECK(dwsep(h + ".t0", outs[i], m->tw0[i], fh[i], 1));
     FR_CHECK(dwsep(h + ".t1", m->tw0[i], m->tw1[i], fh[i], 1));
@@ -2493,7 +2493,34 @@ int det_forward(fr_ctx* ctx, const __nv_bfloat16* d_in_chw, int n, HeadPtrs* hea
     heads->score[i] = m->score[i];
     heads->bbox[i] = m->bbox[i];
     heads->kps[i] = m->kps[i];
+    return FR_OK;
+  };
+  FR_CHECK(conv3("fpn0", m->lat[0], m->inter[0], fh[0], 1, 0));
+  // FR_SCRFD_FORK=1 (experiment): the stride-8 head (3 launches, ~325 us) depends on fpn0 only; on a second stream
+  // its CTAs fill the SMs that the short 40^2 / 20^2 launches of the other branch leave idle in their last wave
+  static const bool fork = getenv("FR_SCRFD_FORK") && atoi(getenv("FR_SCRFD_FORK")) != 0;
+  cudaStream_t main_stream = ctx->stream;
+  if (fork) {
+    if (!m->aux_stream) {
+      FR_CUDA_OK(ctx, cudaStreamCreateWithFlags(&m->aux_stream, cudaStreamNonBlocking));
+      FR_CUDA_OK(ctx, cudaEventCreateWithFlags(&m->ev_fork, cudaEventDisableTiming));
+      FR_CUDA_OK(ctx, cudaEventCreateWithFlags(&m->ev_join, cudaEventDisableTiming));
+    }
+    FR_CUDA_OK(ctx, cudaEventRecord(m->ev_fork, main_stream));
+    FR_CUDA_OK(ctx, cudaStreamWaitEvent(m->aux_stream, m->ev_fork, 0));
+    ctx->stream = m->aux_stream;
+    const int s = head(0);
+    ctx->stream = main_stream;
+    FR_CHECK(s);
+    FR_CUDA_OK(ctx, cudaEventRecord(m->ev_join, m->aux_stream));
   }
+  for (int i = 1; i < 3; ++i) FR_CHECK(conv3("fpn" + std::to_string(i), m->lat[i], m->inter[i], fh[i], 1, 0));
+  for (int i = 0; i < 2; ++i)
+    FR_CHECK(conv3("down" + std::to_string(i), m->inter[i], m->inter[i + 1], fh[i], 2, 1));
+  for (int i = 1; i < 3; ++i)
+    FR_CHECK(conv3("pafpn" + std::to_string(i - 1), m->inter[i], m->pout[i], fh[i], 1, 0));
+  for (int i = fork ? 1 : 0; i < 3; ++i) FR_CHECK(head(i));
+  if (fork) FR_CUDA_OK(ctx, cudaStreamWaitEvent(main_stream, m->ev_join, 0));
   return FR_OK;
 }
 
